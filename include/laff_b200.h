@@ -1,0 +1,206 @@
+/*
+ * laff_b200 — C ABI of the B200-native (sm_100a) LAFF retrieval hot path.
+ *
+ * This is the drop-in boundary.  The reference (ruc-aimc-lab/LAFF) has no FFI layer: its hot path is Python calling
+ * PyTorch/numpy ops.  Each entry point below replaces the reference call sites cited next to it (paths relative to
+ * the reference repo); the Python host side (laff_b200/*.py) mirrors the reference's module/function names and
+ * binds these symbols with ctypes (INTEGRATION.md shows the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no torch types.  All pointers are DEVICE pointers unless named host_*.
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns without synchronising.
+ *   - no allocation inside: ops that need scratch take (workspace, workspace_bytes); query the size with the
+ *     matching *_workspace_bytes().  Distinct streams need distinct workspaces.
+ *   - return value: 0 = ok, < 0 = LAFF_E* (bad argument / unsupported), > 0 = a cudaError_t.
+ *     laff_last_error() returns a thread-local message for the last failure.
+ *   - 16-bit operand dtype codes are the tcgen05 kind::f16 format codes: 0 = fp16, 1 = bf16.
+ *   - there is no CPU fallback: on a machine without an sm_100 device every compute call fails.
+ */
+#ifndef LAFF_B200_H_
+#define LAFF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAFF_OK 0
+#define LAFF_EINVAL (-1)   /* bad argument */
+#define LAFF_ENOTSUP (-2)  /* unsupported shape / option */
+#define LAFF_ENODEV (-3)   /* no sm_100 device / driver entry point missing */
+#define LAFF_EWORKSPACE (-4)
+
+#define LAFF_F16 0
+#define LAFF_BF16 1
+#define LAFF_F32 2
+
+#define LAFF_MAX_FEATURES 8
+#define LAFF_MAX_TOPK 16
+
+#define LAFF_ACT_NONE 0
+#define LAFF_ACT_TANH 1
+#define LAFF_ACT_RELU 2
+#define LAFF_ACT_SIGMOID 3
+
+#define LAFF_DIR_T2I 0
+#define LAFF_DIR_I2T 1
+#define LAFF_DIR_BIDIR 2
+
+const char* laff_last_error(void);
+int laff_abi_version(void);
+
+/* Tuning knobs of the tcgen05 GEMM engine (0 keeps the current value).
+ *   cta_group   1: one CTA per 128x256 tile, 2: CTA pair per 256x256 tile (cta_group::2 MMA).
+ *   chunk_tiles number of consecutive 256-column gallery tiles one work unit sweeps with per-row top-k state.
+ *   m_group     number of query row-tiles that sweep the gallery together (L2 residency of the query block). */
+int laff_set_tuning(int cta_group, int chunk_tiles, int m_group);
+int laff_get_tuning(int* cta_group, int* chunk_tiles, int* m_group);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * S1  loss.l2norm (loss.py:8-13) applied per head, then rounding to the tensor-core operand type.
+ *     x [rows, heads*head_dim] fp32, row stride ldx.  out[r, h, :] = x[r, h, :] / (||x[r, h, :]||_2 + eps)
+ *     with eps = the reference's (eps + 1e-14) passed as a double; out_dtype LAFF_F16 / LAFF_BF16 / LAFF_F32.
+ *     ld_out in elements of out_dtype.  eps < 0 skips the normalisation (pure cast). */
+int laff_l2norm_quantize(const float* x, long long rows, int heads, int head_dim, long long ldx, double eps,
+                         int out_dtype, void* out, long long ld_out, void* stream);
+
+/* Split an fp32 matrix into 3-term 16-bit operands for near-fp32 tensor-core products:
+ *   x ~= hi + lo with hi = round16(x), lo = round16(x - hi).
+ *   side 0 (left operand):  out[r] = [hi | lo | hi]      side 1 (right operand): out[r] = [hi | hi | lo]
+ *   so that dot(out_left[i], out_right[j]) = hi.hi + lo.hi + hi.lo.  cols_pad >= cols (zero filled), ld_out >= 3*cols_pad. */
+int laff_split3_16(const float* x, long long rows, int cols, long long ldx, int side, int out_dtype, void* out,
+                   int cols_pad, long long ld_out, void* stream);
+
+/* fp32 -> 16-bit cast with zero padding of columns [cols, cols_pad) (TMA needs 16-byte aligned row pitches). */
+int laff_cast_pad_16(const float* x, long long rows, int cols, long long ldx, int out_dtype, void* out, int cols_pad,
+                     long long ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * S2  W2VVPP.get_txt2vis_matrix / compute_sim (model/model.py:1003-1016, :1567-1578) -> loss.cosine_sim's
+ *     query.mm(retrio.t()) (loss.py:34) on already normalised + rounded operands, mean over heads = scale 1/H.
+ *     out[i, j] = scale * sum_k q[i, k] * g[j, k]      q [Q, D] ldq, g [V, D] ldg (16-bit, D % 8 == 0), out fp32.
+ *     tcgen05 GEMM, fp32 accumulate in TMEM. */
+int laff_sim_dense(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                   float scale, float* out, long long ld_out, void* stream);
+
+/* Diagnostics: run the GEMM mainloop of laff_sim_* with a null epilogue (mode 1 drains TMEM, mode < 0 only sets the
+ * TMA L2 eviction hints used by later laff_sim_* calls; hint codes 0 default, 1 normal, 2 evict-first, 3 evict-last). */
+int laff_debug_gemm(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                    int mode, int hint_a, int hint_b, float* sink, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * E2  rank extraction: np.argsort(t2i_matrix, axis=1) + the per-query ground-truth search
+ *     (predictor.py:232-244, trainer.py:584-594, evaluation.py:64-79) fused into the similarity GEMM; the Q x V
+ *     matrix is never written.
+ *
+ *     Tie rule (documented, = np.argsort(kind='stable')[::-1]): order by (score desc, index desc);
+ *       rank0[i] = #{j != gt: s_ij > s_i,gt} + #{j > gt: s_ij == s_i,gt}.
+ *
+ *  step 1  laff_sim_gt_scores: sgt_raw[i] = sum_k q[i,k] * g[gt_local[i], k] computed by the same MMA sequence as the
+ *          sweep (unscaled fp32 accumulator).  gt_local[i] < 0 (ground truth lives on another shard) -> 0.
+ *          Multi-GPU: all_reduce(sum) sgt_raw across gallery shards before step 2.
+ *  step 2  laff_sim_rank_topk: one sweep over the local gallery shard g [V, D] whose column j has global index
+ *          col_offset + j.  count[i] (int32) = local contribution to rank0[i]  (all_reduce(sum) across shards);
+ *          topk_val/topk_idx [Q, k]: local top-k (scaled scores, global indices) ordered by the tie rule
+ *          (entries beyond the shard size: -inf / -1).
+ *  step 3  laff_topk_merge: merge n_lists ordered lists per query (all_gather'ed shards) into the global top-k. */
+size_t laff_sim_gt_workspace_bytes(int Q, int D);
+int laff_sim_gt_scores(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                       const int32_t* gt_local, float* sgt_raw, void* workspace, size_t workspace_bytes, void* stream);
+
+size_t laff_sim_rank_workspace_bytes(int Q, int V, int D);
+int laff_sim_rank_topk(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                       float scale, const float* sgt_raw, const int32_t* gt_global, int col_offset, int k,
+                       int32_t* count, float* topk_val, int32_t* topk_idx, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* vals/idx: n_lists lists per query, list l of query i at vals + l*list_stride + i*k_in, each ordered by the tie rule.
+ * out_val[i, 0..k_out) = in_scale * merged values. */
+int laff_topk_merge(const float* vals, const int32_t* idx, int n_lists, int Q, int k_in, long long list_stride,
+                    int k_out, float in_scale, float* out_val, int32_t* out_idx, void* stream);
+
+/* Rank / top-k of an already materialised fp32 score matrix (the small-config predict() path and the integer
+ * parity check of the fused kernel): same tie rule as above. */
+int laff_rank_from_scores(const float* scores, int Q, int V, long long ld, const int32_t* gt, int k, int32_t* rank0,
+                          float* topk_val, int32_t* topk_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * E3  evaluation.eval_qry2retro metrics (evaluation.py:81-89) / evaluation.eval (evaluation.py:105-109) on device.
+ *     rank0 int32 [Q] (0-based rank of the first ground truth).  out (device, 8 doubles):
+ *       [0] R@1  [1] R@5  [2] R@10  (percent)  [3] MedR = floor(median(rank0)) + 1  [4] MeanR = mean(rank0) + 1
+ *       [5] MIR = mean(1 / (rank0 + 1))  [6] mAP (= MIR for a single ground truth)  [7] Q. */
+int laff_rank_metrics(const int32_t* rank0, int Q, double* out8, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * F1  TransformNet.forward (model/model.py:257-276): y = BN(act(x W^T + b)), eval mode (dropout = identity,
+ *     BatchNorm1d running stats, eps bn_eps).  x16 [rows, K] ldx, w16 [D, K] ldw (16-bit, K-major, pitches % 8 == 0).
+ *     Eval-mode BatchNorm is the per-column affine map y*bn_scale + bn_shift produced by laff_bn_fold.
+ *     bias / bn_scale / bn_shift may be NULL (stage absent).  y fp32 [rows, D] ldy.  tcgen05 GEMM, epilogue fused. */
+int laff_project(const void* x16, const void* w16, long long rows, int K, int D, long long ldx, long long ldw,
+                 int dtype, const float* bias, int activation, const float* bn_scale, const float* bn_shift,
+                 float* y, long long ldy, void* stream);
+
+/* nn.BatchNorm1d in eval mode (model/model.py:232, :273-274): scale = weight / sqrt(running_var + eps),
+ * shift = bias - running_mean * scale.  weight / bias may be NULL (affine=False). */
+int laff_bn_fold(const float* weight, const float* bias, const float* running_mean, const float* running_var,
+                 double eps, int D, float* scale, float* shift, void* stream);
+
+/* F2-F6  VisMutiTransformNet(AddAttnetion) / MultiScaleTxtEncoderAttention (model/model.py:1807-1876, :1663-1705),
+ *     Multi_head_MyApply_Attention + Attention_1 (model/Attention.py:508-531, :78-105), loss.l2norm(eps=0).
+ *     Per feature l the source is either a projected y_l [rows, D] (kind 0, from laff_project) or a "no-transform"
+ *     raw feature x_l [rows, in_dim] that is tiled D/in_dim times across the D axis and passed through BN only
+ *     (kind 1; model/model.py:1822-1823, :1675-1676, :1804-1805).
+ *     Per head h: e_l = w_h . Y[l,h,:] + c_h ; a = softmax_l(e) ; out_h = l2norm(sum_l (a_l [+ omega]) Y[l,h,:]).
+ *     mul: logits taken on Y[l,h,:] * mean_l Y[.,h,:] (Attention.py:83-86).  with_ave: + omega * mean-pool
+ *     (Attention.py:94-99; omega = global_emb_weight_net.weight).
+ *     out fp32 [rows, H*dh] ld_out (may be NULL), out16 (may be NULL) the same values rounded to out16_dtype,
+ *     att (may be NULL) fp32 [rows, H, L] the attention weights the reference keeps in self.weights. */
+typedef struct {
+  int kind;            /* 0 = projected fp32 [rows, D]; 1 = raw fp32 [rows, in_dim] tiled + BN */
+  int in_dim;          /* kind 1 only */
+  const float* src;
+  long long ld;
+  const float* bn_scale; /* kind 1: folded BatchNorm1d(D) (laff_bn_fold), may be NULL = identity */
+  const float* bn_shift;
+} laff_pool_source;
+
+typedef struct {
+  int n_features;
+  int heads;
+  int head_dim;
+  int with_ave;
+  int mul;
+  float omega;
+  double norm_eps;        /* added to the L2 norm: the reference's l2norm(eps=0) adds 1e-14 */
+  const float* att_weight; /* [heads, head_dim]  attention_layer.<h>.embedding_common.0.weight */
+  const float* att_bias;   /* [heads] */
+  laff_pool_source src[LAFF_MAX_FEATURES];
+} laff_pool_desc;
+
+int laff_attention_pool(const laff_pool_desc* desc, long long rows, float* out, long long ld_out, void* out16,
+                        int out16_dtype, long long ld_out16, float* att, void* stream);
+
+/* F7  frame-level LAFF (model/model.py:2160-2173 -> Attention_1(dim), model/Attention.py:78-105):
+ *     frames fp32 [B, F, dim] (zero padded frames take part in the softmax exactly like the reference),
+ *     out fp32 [B, dim] unit norm. */
+int laff_frame_pool(const float* frames, long long B, int F, int dim, const float* att_weight, float att_bias,
+                    int with_ave, int mul, float omega, double norm_eps, float* out, long long ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * L1/L2  sum over heads of MarginRankingLoss.forward(s = txt[:, h, :], im = vis[:, h, :])
+ *     (loss.py:95-135, model/model.py:852-862, :2036-2038), forward and backward in one call.
+ *     txt, vis fp32 [B, H, dh] contiguous.  loss: device scalar.  d_txt / d_vis (may be NULL): dLoss/dtxt, dLoss/dvis.
+ * L3     MarginRankingLossWithScore.forward(score) (loss.py:161-200): score fp32 [B, B] ld; d_score may be NULL. */
+size_t laff_mrl_workspace_bytes(int B, int H, int dh);
+int laff_mrl_forward_backward(const float* txt, const float* vis, int B, int H, int dh, float margin,
+                              int max_violation, int direction, int cost_mean, float* loss, float* d_txt,
+                              float* d_vis, void* workspace, size_t workspace_bytes, void* stream);
+int laff_mrl_score_forward_backward(const float* score, int B, long long ld, float margin, int max_violation,
+                                    int direction, int cost_mean, float* loss, float* d_score, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAFF_B200_H_ */

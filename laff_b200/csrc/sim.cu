@@ -1,0 +1,607 @@
+// Similarity + ranking kernels.
+//   laff_sim_dense       : Q x V fp32 score matrix (small-config predict() path)            model/model.py:1003-1016
+//   laff_sim_gt_scores   : s_i,gt by the same MMA sequence as the sweep                     predictor.py:239-244
+//   laff_sim_rank_topk   : similarity GEMM fused with exact rank counting + streaming top-k predictor.py:232, evaluation.py:64-79
+//   laff_topk_merge      : merge per-chunk / per-shard ordered lists
+//   laff_rank_from_scores: the same tie rule applied to a materialised score matrix
+//   laff_rank_metrics    : R@1/5/10, MedR, MeanR, MIR on device                             evaluation.py:81-89, :105-109
+#include <cfloat>
+#include <climits>
+#include <cstring>
+
+#include "gemm_engine.cuh"
+#include "host_util.cuh"
+
+namespace laff {
+
+// ------------------------------------------------------------------------------------------------------------
+// Epilogues
+// ------------------------------------------------------------------------------------------------------------
+struct EpiDense {
+  struct Params {
+    float* out;
+    long long ld;
+    int M, N;
+    float scale;
+  };
+  Params p;
+  __device__ explicit EpiDense(const Params& p_) : p(p_) {}
+  __device__ __forceinline__ void unit_begin(int, const Unit&) {}
+  __device__ __forceinline__ void unit_end(int, const Unit&) {}
+  __device__ __forceinline__ void chunk(const uint32_t (&r)[32], int row, int col0) {
+    if (row >= p.M || col0 >= p.N) return;
+    float* dst = p.out + static_cast<long long>(row) * p.ld + col0;
+    if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 v = make_float4(__uint_as_float(r[j]) * p.scale, __uint_as_float(r[j + 1]) * p.scale,
+                               __uint_as_float(r[j + 2]) * p.scale, __uint_as_float(r[j + 3]) * p.scale);
+        *reinterpret_cast<float4*>(dst + j) = v;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]) * p.scale;
+    }
+  }
+};
+
+// Diagnostics only: drains TMEM (mode 1) or skips the loads entirely (mode 0) so the mainloop can be timed alone.
+struct EpiNull {
+  struct Params {
+    float* sink;
+    int mode;
+  };
+  Params p;
+  float acc;
+  __device__ explicit EpiNull(const Params& p_) : p(p_), acc(0.f) {}
+  __device__ __forceinline__ void unit_begin(int, const Unit&) {}
+  __device__ __forceinline__ void unit_end(int row, const Unit&) {
+    if (acc == 123.456f) p.sink[row & 1023] = acc;
+  }
+  __device__ __forceinline__ void chunk(const uint32_t (&r)[32], int, int) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc = fmaxf(acc, __uint_as_float(r[j]));
+  }
+};
+
+// D[r, r] of A x gather(B)[r]: the raw accumulator the sweep would produce for (query r, its ground-truth video).
+struct EpiDiag {
+  struct Params {
+    float* sgt;
+    const int32_t* gt_local;
+    int M;
+  };
+  Params p;
+  __device__ explicit EpiDiag(const Params& p_) : p(p_) {}
+  __device__ __forceinline__ void unit_begin(int, const Unit&) {}
+  __device__ __forceinline__ void unit_end(int, const Unit&) {}
+  __device__ __forceinline__ void chunk(const uint32_t (&r)[32], int row, int col0) {
+    if (row >= p.M || row < col0 || row >= col0 + 32) return;
+    const int j = row - col0;
+    uint32_t v = 0;
+#pragma unroll
+    for (int t = 0; t < 32; ++t)
+      if (t == j) v = r[t];
+    p.sgt[row] = p.gt_local[row] >= 0 ? __uint_as_float(v) : 0.0f;
+  }
+};
+
+// total order used everywhere: (score desc, index desc)
+__device__ __forceinline__ bool better(float va, int ia, float vb, int ib) {
+  return va > vb || (va == vb && ia > ib);
+}
+
+template <int KMAX>
+struct EpiRank {
+  struct Params {
+    const float* sgt;     // raw accumulator of (i, gt_i)
+    const int32_t* gt;    // global gallery index of the ground truth
+    int32_t* count;       // [M] += local rank contribution
+    float* part_val;      // [n_chunks, M, KMAX]
+    int32_t* part_idx;
+    int M, N;             // queries, local gallery size
+    int col_offset;       // global index of local column 0
+  };
+  Params p;
+  float tv[KMAX];
+  int ti[KMAX];
+  int cnt;
+  float sg;
+  int g;
+  __device__ explicit EpiRank(const Params& p_) : p(p_) {}
+
+  __device__ __forceinline__ void unit_begin(int row, const Unit&) {
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      tv[i] = -INFINITY;
+      ti[i] = -1;
+    }
+    cnt = 0;
+    sg = 0.f;
+    g = -1;
+    if (row < p.M) {
+      sg = p.sgt[row];
+      g = p.gt[row];
+    }
+  }
+
+  __device__ __forceinline__ void insert(float v, int idx) {
+    // replace the worst entry, then bubble the new one up; fully unrolled so the lists stay in registers
+    tv[KMAX - 1] = v;
+    ti[KMAX - 1] = idx;
+#pragma unroll
+    for (int i = KMAX - 1; i > 0; --i) {
+      const bool sw = better(tv[i], ti[i], tv[i - 1], ti[i - 1]);
+      const float fv = sw ? tv[i - 1] : tv[i];
+      const int fi = sw ? ti[i - 1] : ti[i];
+      tv[i - 1] = sw ? tv[i] : tv[i - 1];
+      ti[i - 1] = sw ? ti[i] : ti[i - 1];
+      tv[i] = fv;
+      ti[i] = fi;
+    }
+  }
+
+  __device__ __forceinline__ void chunk(const uint32_t (&r)[32], int row, int col0) {
+    if (row >= p.M) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      if (col < p.N) {
+        const float v = __uint_as_float(r[j]);
+        const int gcol = col + p.col_offset;
+        const bool beats = (v > sg) || (v == sg && gcol > g);
+        cnt += (beats && gcol != g) ? 1 : 0;
+        if (better(v, gcol, tv[KMAX - 1], ti[KMAX - 1])) insert(v, gcol);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void unit_end(int row, const Unit& un) {
+    if (row >= p.M) return;
+    if (cnt) atomicAdd(p.count + row, cnt);
+    const long long o = (static_cast<long long>(un.chunk) * p.M + row) * KMAX;
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      p.part_val[o + i] = tv[i];
+      p.part_idx[o + i] = ti[i];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Launch helper
+// ------------------------------------------------------------------------------------------------------------
+static uint64_t g_hint_override[2] = {0, 0};
+
+template <int CG, class Epi>
+static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, int num_kb, uint32_t idesc, const Sched& s,
+                          const typename Epi::Params& ep, int sms, cudaStream_t st) {
+  using Cfg = EngineCfg<CG>;
+  auto kern = gemm_kernel<CG, Epi>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    LAFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  if (s.total_units <= 0) return LAFF_OK;
+  int clusters = sms / CG;
+  if (clusters > s.total_units) clusters = s.total_units;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // queries (A) are re-read by every gallery tile: keep them in L2; the gallery (B) streams through once per m-group
+  uint64_t hintA = ptx::kEvictLast, hintB = ptx::kEvictNormal;
+  if (g_hint_override[0]) hintA = g_hint_override[0];
+  if (g_hint_override[1]) hintB = g_hint_override[1];
+  LAFF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, num_kb, idesc, s, hintA, hintB, ep));
+  return LAFF_OK;
+}
+
+struct GemmOperands {
+  CUtensorMap tmA, tmB;
+  int num_kb;
+  uint32_t idesc;
+  int cg;
+  int sms;
+};
+
+// A [M, K] pitch lda, B [N, K] pitch ldb
+static int prepare_operands(GemmOperands* op, const void* A, const void* B, long long M, long long N, int K,
+                            long long lda, long long ldb, int dtype, int cg) {
+  LAFF_REQUIRE(is16(dtype), LAFF_EINVAL, "operand dtype must be LAFF_F16 or LAFF_BF16, got %d", dtype);
+  LAFF_REQUIRE(M > 0 && N > 0 && K > 0, LAFF_EINVAL, "empty GEMM operand (M=%lld N=%lld K=%d)", M, N, K);
+  LAFF_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, LAFF_EINVAL,
+               "K (%d) and operand pitches (%lld, %lld) must be multiples of 8 and pitches >= K", K, lda, ldb);
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  op->cg = cg;
+  op->sms = di.sms;
+  op->num_kb = (K + kBlockK - 1) / kBlockK;
+  op->idesc = make_idesc_f16(dtype, kBlockM * cg, kBlockN);
+  rc = make_tmap_2d(&op->tmA, A, dtype, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), kBlockM);
+  if (rc) return rc;
+  rc = make_tmap_2d(&op->tmB, B, dtype, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb),
+                    static_cast<uint32_t>(kBlockN / cg));
+  return rc;
+}
+
+template <class Epi>
+static int launch_gemm(const GemmOperands& op, const Sched& s, const typename Epi::Params& ep, cudaStream_t st) {
+  if (op.cg == 2) return launch_gemm_cg<2, Epi>(op.tmA, op.tmB, op.num_kb, op.idesc, s, ep, op.sms, st);
+  return launch_gemm_cg<1, Epi>(op.tmA, op.tmB, op.num_kb, op.idesc, s, ep, op.sms, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Small CUDA-core kernels around the GEMM
+// ------------------------------------------------------------------------------------------------------------
+__global__ void gather_rows16_kernel(const uint4* __restrict__ g, long long ldg16, const int32_t* __restrict__ gt_local,
+                                     int Q, int vec_per_row, uint4* __restrict__ out) {
+  const long long total = static_cast<long long>(Q) * vec_per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / vec_per_row);
+    const int v = static_cast<int>(i - static_cast<long long>(row) * vec_per_row);
+    int src = gt_local[row];
+    if (src < 0) src = 0;
+    out[i] = g[static_cast<long long>(src) * ldg16 + v];
+  }
+}
+
+// One warp per query: k_out rounds of "best candidate strictly worse than the previous pick".
+__global__ void topk_merge_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx, int n_lists, int Q,
+                                  int k_in, long long list_stride, int k_out, float in_scale, float* __restrict__ out_val,
+                                  int32_t* __restrict__ out_idx) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= Q) return;
+  const int n_cand = n_lists * k_in;
+  float last_v = INFINITY;
+  int last_i = INT_MAX;
+  for (int r = 0; r < k_out; ++r) {
+    float bv = -INFINITY;
+    int bi = -1;
+    for (int c = lane; c < n_cand; c += 32) {
+      const int l = c / k_in, e = c - l * k_in;
+      const long long o = static_cast<long long>(l) * list_stride + static_cast<long long>(warp) * k_in + e;
+      const float v = vals[o];
+      const int i = idx[o];
+      if (i >= 0 && better(last_v, last_i, v, i) && better(v, i, bv, bi)) {
+        bv = v;
+        bi = i;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (better(ov, oi, bv, bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      out_val[static_cast<long long>(warp) * k_out + r] = bi >= 0 ? bv * in_scale : -INFINITY;
+      out_idx[static_cast<long long>(warp) * k_out + r] = bi;
+    }
+    if (bi < 0) {
+      // nothing left: fill the tail
+      for (int t = r + 1 + lane; t < k_out; t += 32) {
+        out_val[static_cast<long long>(warp) * k_out + t] = -INFINITY;
+        out_idx[static_cast<long long>(warp) * k_out + t] = -1;
+      }
+      break;
+    }
+    last_v = bv;
+    last_i = bi;
+  }
+}
+
+// One block per query on a materialised score row.
+__global__ void rank_from_scores_kernel(const float* __restrict__ scores, int V, long long ld,
+                                        const int32_t* __restrict__ gt, int k, int32_t* __restrict__ rank0,
+                                        float* __restrict__ topk_val, int32_t* __restrict__ topk_idx) {
+  __shared__ int s_cnt[32];
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  __shared__ float s_lastv;
+  __shared__ int s_lasti;
+  const int q = blockIdx.x;
+  const float* row = scores + static_cast<long long>(q) * ld;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (rank0 != nullptr) {
+    const int g = gt[q];
+    const float sg = row[g];
+    int cnt = 0;
+    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+      const float v = row[j];
+      cnt += (j != g && better(v, j, sg, g)) ? 1 : 0;
+    }
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if (lane == 0) s_cnt[w] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int i = 0; i < nw; ++i) t += s_cnt[i];
+      rank0[q] = t;
+    }
+    __syncthreads();
+  }
+  if (k <= 0) return;
+  if (threadIdx.x == 0) {
+    s_lastv = INFINITY;
+    s_lasti = INT_MAX;
+  }
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    const float lv = s_lastv;
+    const int li = s_lasti;
+    float bv = -INFINITY;
+    int bi = -1;
+    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+      const float v = row[j];
+      if (better(lv, li, v, j) && better(v, j, bv, bi)) {
+        bv = v;
+        bi = j;
+      }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (better(ov, oi, bv, bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      s_v[w] = bv;
+      s_i[w] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float fv = -INFINITY;
+      int fi = -1;
+      for (int i = 0; i < nw; ++i)
+        if (better(s_v[i], s_i[i], fv, fi)) {
+          fv = s_v[i];
+          fi = s_i[i];
+        }
+      topk_val[static_cast<long long>(q) * k + r] = fi >= 0 ? fv : -INFINITY;
+      topk_idx[static_cast<long long>(q) * k + r] = fi;
+      s_lastv = fi >= 0 ? fv : -INFINITY;
+      s_lasti = fi;
+    }
+    __syncthreads();
+  }
+}
+
+// Single block.  Order statistics by a 31-step bitwise descent (ranks are non-negative int32), sums in fp64.
+__device__ int block_kth_smallest(const int32_t* __restrict__ x, int n, int kth, int* s_red) {
+  // returns the value v such that #(x < v) <= kth < #(x <= v)
+  int prefix = 0;
+  int remaining = kth;  // index among the elements that match the prefix so far
+  for (int bit = 30; bit >= 0; --bit) {
+    const int mask_hi = static_cast<int>(~((1u << (bit + 1)) - 1u));  // bits above `bit`
+    int c0 = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int v = x[i];
+      c0 += (((v & mask_hi) == (prefix & mask_hi)) && !((v >> bit) & 1)) ? 1 : 0;
+    }
+    for (int off = 16; off > 0; off >>= 1) c0 += __shfl_xor_sync(0xffffffffu, c0, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = c0;
+    __syncthreads();
+    int tot = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) tot += s_red[i];
+    if (remaining >= tot) {
+      remaining -= tot;
+      prefix |= (1 << bit);
+    }
+  }
+  return prefix;
+}
+
+__global__ void rank_metrics_kernel(const int32_t* __restrict__ rank0, int Q, double* __restrict__ out) {
+  __shared__ int s_red[32];
+  __shared__ double s_d[32][4];
+  int c1 = 0, c5 = 0, c10 = 0;
+  double sum_r = 0.0, sum_inv = 0.0;
+  for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+    const int r = rank0[i];
+    c1 += r < 1;
+    c5 += r < 5;
+    c10 += r < 10;
+    sum_r += static_cast<double>(r);
+    sum_inv += 1.0 / (static_cast<double>(r) + 1.0);
+  }
+  double v[5] = {static_cast<double>(c1), static_cast<double>(c5), static_cast<double>(c10), sum_r, sum_inv};
+  double tot[5];
+  for (int t = 0; t < 5; ++t) {
+    double x = v[t];
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_d[threadIdx.x >> 5][0] = x;
+    __syncthreads();
+    double a = 0.0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) a += s_d[i][0];
+    tot[t] = a;
+  }
+  // np.median: middle element (odd Q) or the mean of the two middle elements (even Q)
+  const int lo = block_kth_smallest(rank0, Q, (Q - 1) / 2, s_red);
+  const int hi = block_kth_smallest(rank0, Q, Q / 2, s_red);
+  if (threadIdx.x == 0) {
+    const double q = static_cast<double>(Q);
+    const double med = 0.5 * (static_cast<double>(lo) + static_cast<double>(hi));
+    out[0] = 100.0 * tot[0] / q;
+    out[1] = 100.0 * tot[1] / q;
+    out[2] = 100.0 * tot[2] / q;
+    out[3] = floor(med) + 1.0;
+    out[4] = tot[3] / q + 1.0;
+    out[5] = tot[4] / q;
+    out[6] = tot[4] / q;
+    out[7] = q;
+  }
+}
+
+}  // namespace laff
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+using namespace laff;
+
+extern "C" {
+
+int laff_sim_dense(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                   float scale, float* out, long long ld_out, void* stream) {
+  LAFF_REQUIRE(q && g && out, LAFF_EINVAL, "laff_sim_dense: null pointer");
+  LAFF_REQUIRE(ld_out >= V, LAFF_EINVAL, "laff_sim_dense: ld_out %lld < V %d", ld_out, V);
+  const Tuning t = get_tuning();
+  GemmOperands op;
+  int rc = prepare_operands(&op, q, g, Q, V, D, ldq, ldg, dtype, t.cta_group);
+  if (rc) return rc;
+  const Sched s = make_sched(Q, V, op.cg, t.chunk_tiles, t.m_group, 0);
+  EpiDense::Params ep{out, ld_out, Q, V, scale};
+  return launch_gemm<EpiDense>(op, s, ep, static_cast<cudaStream_t>(stream));
+}
+
+int laff_debug_gemm(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                    int mode, int hint_a, int hint_b, float* sink, void* stream) {
+  static const uint64_t hints[4] = {0, ptx::kEvictNormal, ptx::kEvictFirst, ptx::kEvictLast};
+  g_hint_override[0] = hints[hint_a & 3];
+  g_hint_override[1] = hints[hint_b & 3];
+  if (mode < 0) return LAFF_OK;  // only set the hint override
+  const Tuning t = get_tuning();
+  GemmOperands op;
+  int rc = prepare_operands(&op, q, g, Q, V, D, ldq, ldg, dtype, t.cta_group);
+  if (rc) return rc;
+  const Sched s = make_sched(Q, V, op.cg, t.chunk_tiles, t.m_group, 0);
+  EpiNull::Params ep{sink, mode};
+  return launch_gemm<EpiNull>(op, s, ep, static_cast<cudaStream_t>(stream));
+}
+
+size_t laff_sim_gt_workspace_bytes(int Q, int D) {
+  if (Q <= 0 || D <= 0) return 0;
+  return static_cast<size_t>(Q) * static_cast<size_t>(D) * 2 + 256;
+}
+
+int laff_sim_gt_scores(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                       const int32_t* gt_local, float* sgt_raw, void* workspace, size_t workspace_bytes, void* stream) {
+  LAFF_REQUIRE(q && g && gt_local && sgt_raw && workspace, LAFF_EINVAL, "laff_sim_gt_scores: null pointer");
+  LAFF_REQUIRE(workspace_bytes >= laff_sim_gt_workspace_bytes(Q, D), LAFF_EWORKSPACE,
+               "laff_sim_gt_scores: workspace too small (%zu < %zu)", workspace_bytes, laff_sim_gt_workspace_bytes(Q, D));
+  LAFF_REQUIRE(D % 8 == 0 && ldg % 8 == 0, LAFF_EINVAL, "laff_sim_gt_scores: D and ldg must be multiples of 8");
+  LAFF_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, LAFF_EINVAL, "gallery not 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // 256-byte aligned gather buffer inside the workspace
+  uintptr_t wp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255);
+  void* ggt = reinterpret_cast<void*>(wp);
+  const Tuning t = get_tuning();
+  GemmOperands op;
+  int rc = prepare_operands(&op, q, ggt, Q, Q, D, ldq, D, dtype, t.cta_group);
+  if (rc) return rc;
+  const int vec_per_row = D / 8;
+  const long long total = static_cast<long long>(Q) * vec_per_row;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > op.sms * 8) blocks = op.sms * 8;
+  gather_rows16_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint4*>(g), ldg / 8, gt_local, Q, vec_per_row,
+                                               static_cast<uint4*>(ggt));
+  LAFF_CUDA(cudaGetLastError());
+  const Sched s = make_sched(Q, Q, op.cg, 1, 1, 1);
+  EpiDiag::Params ep{sgt_raw, gt_local, Q};
+  (void)V;
+  return launch_gemm<EpiDiag>(op, s, ep, st);
+}
+
+size_t laff_sim_rank_workspace_bytes(int Q, int V, int D) {
+  (void)D;
+  if (Q <= 0 || V <= 0) return 0;
+  const Tuning t = get_tuning();
+  const Sched s = make_sched(Q, V, t.cta_group, t.chunk_tiles, t.m_group, 0);
+  return static_cast<size_t>(s.n_chunks) * static_cast<size_t>(Q) * LAFF_MAX_TOPK * 8 + 512;
+}
+
+int laff_sim_rank_topk(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                       float scale, const float* sgt_raw, const int32_t* gt_global, int col_offset, int k,
+                       int32_t* count, float* topk_val, int32_t* topk_idx, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  LAFF_REQUIRE(q && g && sgt_raw && gt_global && count && workspace, LAFF_EINVAL, "laff_sim_rank_topk: null pointer");
+  LAFF_REQUIRE(k >= 0 && k <= LAFF_MAX_TOPK, LAFF_ENOTSUP, "laff_sim_rank_topk: k=%d outside [0, %d]", k, LAFF_MAX_TOPK);
+  LAFF_REQUIRE(k == 0 || (topk_val && topk_idx), LAFF_EINVAL, "laff_sim_rank_topk: top-k outputs missing");
+  LAFF_REQUIRE(workspace_bytes >= laff_sim_rank_workspace_bytes(Q, V, D), LAFF_EWORKSPACE,
+               "laff_sim_rank_topk: workspace too small (%zu < %zu)", workspace_bytes,
+               laff_sim_rank_workspace_bytes(Q, V, D));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Tuning t = get_tuning();
+  GemmOperands op;
+  int rc = prepare_operands(&op, q, g, Q, V, D, ldq, ldg, dtype, t.cta_group);
+  if (rc) return rc;
+  const Sched s = make_sched(Q, V, op.cg, t.chunk_tiles, t.m_group, 0);
+  uintptr_t wp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255);
+  float* part_val = reinterpret_cast<float*>(wp);
+  int32_t* part_idx = reinterpret_cast<int32_t*>(wp + static_cast<size_t>(s.n_chunks) * Q * LAFF_MAX_TOPK * 4);
+  LAFF_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * static_cast<size_t>(Q), st));
+  EpiRank<LAFF_MAX_TOPK>::Params ep{sgt_raw, gt_global, count, part_val, part_idx, Q, V, col_offset};
+  rc = launch_gemm<EpiRank<LAFF_MAX_TOPK>>(op, s, ep, st);
+  if (rc) return rc;
+  if (k > 0) {
+    const int threads = 128;
+    const int blocks = (Q * 32 + threads - 1) / threads;
+    topk_merge_kernel<<<blocks, threads, 0, st>>>(part_val, part_idx, s.n_chunks, Q, LAFF_MAX_TOPK,
+                                                  static_cast<long long>(Q) * LAFF_MAX_TOPK, k, scale, topk_val, topk_idx);
+    LAFF_CUDA(cudaGetLastError());
+  }
+  return LAFF_OK;
+}
+
+int laff_topk_merge(const float* vals, const int32_t* idx, int n_lists, int Q, int k_in, long long list_stride,
+                    int k_out, float in_scale, float* out_val, int32_t* out_idx, void* stream) {
+  LAFF_REQUIRE(vals && idx && out_val && out_idx, LAFF_EINVAL, "laff_topk_merge: null pointer");
+  LAFF_REQUIRE(n_lists > 0 && Q > 0 && k_in > 0 && k_out > 0, LAFF_EINVAL, "laff_topk_merge: bad sizes");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const int threads = 128;
+  const int blocks = (Q * 32 + threads - 1) / threads;
+  topk_merge_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(vals, idx, n_lists, Q, k_in, list_stride,
+                                                                              k_out, in_scale, out_val, out_idx);
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}
+
+int laff_rank_from_scores(const float* scores, int Q, int V, long long ld, const int32_t* gt, int k, int32_t* rank0,
+                          float* topk_val, int32_t* topk_idx, void* stream) {
+  LAFF_REQUIRE(scores && Q > 0 && V > 0 && ld >= V, LAFF_EINVAL, "laff_rank_from_scores: bad arguments");
+  LAFF_REQUIRE(rank0 == nullptr || gt != nullptr, LAFF_EINVAL, "laff_rank_from_scores: rank0 needs gt");
+  LAFF_REQUIRE(k == 0 || (topk_val && topk_idx), LAFF_EINVAL, "laff_rank_from_scores: top-k outputs missing");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  rank_from_scores_kernel<<<Q, 256, 0, static_cast<cudaStream_t>(stream)>>>(scores, V, ld, gt, k, rank0, topk_val,
+                                                                           topk_idx);
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}
+
+int laff_rank_metrics(const int32_t* rank0, int Q, double* out8, void* stream) {
+  LAFF_REQUIRE(rank0 && out8 && Q > 0, LAFF_EINVAL, "laff_rank_metrics: bad arguments");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  rank_metrics_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(rank0, Q, out8);
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}
+
+}  // extern "C"

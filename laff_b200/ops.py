@@ -1,0 +1,337 @@
+"""Tensor-level wrappers over the C ABI (``include/laff_b200.h``).
+
+PyTorch is used for device memory and streams only; every computation below is a hand-written sm_100a kernel reached
+through ctypes.  All functions require CUDA tensors and raise :class:`LaffError` on failure — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _capi
+from ._capi import BF16, F16, F32, MAX_TOPK, LaffError, PoolDesc
+
+_DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
+_TORCH_DT = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32, "fp16": torch.float16,
+             "bf16": torch.bfloat16, "fp32": torch.float32}
+
+
+def torch_dtype(d) -> torch.dtype:
+    return d if isinstance(d, torch.dtype) else _TORCH_DT[d]
+
+
+def _stream(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise LaffError("laff_b200 ops need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+
+
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    """2-D view whose last dim is contiguous (row pitch = stride(0))."""
+    if t.dim() != 2:
+        t = t.reshape(t.shape[0], -1)
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def set_tuning(cta_group: int = 0, chunk_tiles: int = 0, m_group: int = 0) -> None:
+    _capi.call("laff_set_tuning", cta_group, chunk_tiles, m_group)
+
+
+def get_tuning() -> tuple[int, int, int]:
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    _capi.call("laff_get_tuning", C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# operand preparation
+# ----------------------------------------------------------------------------------------------------------------
+def l2norm_quantize(x: torch.Tensor, heads: int, out_dtype=torch.bfloat16, eps: float = 1e-13 + 1e-14,
+                    normalise: bool = True) -> torch.Tensor:
+    """loss.l2norm per head (loss.py:8-13) then rounding to ``out_dtype``. x [rows, heads*dh] (or [rows, heads, dh])."""
+    _need_cuda(x)
+    shape = x.shape
+    x2 = _rowmajor(x.float() if x.dtype != torch.float32 else x)
+    rows, D = x2.shape
+    if D % heads:
+        raise LaffError("feature dim %d not divisible by heads %d" % (D, heads))
+    out_dtype = torch_dtype(out_dtype)
+    out = torch.empty((rows, D), dtype=out_dtype, device=x.device)
+    if rows:
+        _capi.call("laff_l2norm_quantize", _ptr(x2), rows, heads, D // heads, x2.stride(0),
+                   float(eps) if normalise else -1.0, _DT[out_dtype], _ptr(out), out.stride(0), _stream(x))
+    return out.reshape(shape)
+
+
+def cast_pad_16(x: torch.Tensor, dtype=torch.bfloat16, multiple: int = 8) -> torch.Tensor:
+    """fp32 [rows, cols] -> 16-bit [rows, cols_pad] with zero padding so the row pitch is TMA-legal."""
+    _need_cuda(x)
+    x2 = _rowmajor(x.float() if x.dtype != torch.float32 else x)
+    rows, cols = x2.shape
+    cols_pad = (cols + multiple - 1) // multiple * multiple
+    dtype = torch_dtype(dtype)
+    out = torch.empty((rows, cols_pad), dtype=dtype, device=x.device)
+    if rows:
+        _capi.call("laff_cast_pad_16", _ptr(x2), rows, cols, x2.stride(0), _DT[dtype], _ptr(out), cols_pad,
+                   out.stride(0), _stream(x))
+    return out
+
+
+def split3_16(x: torch.Tensor, side: int, dtype=torch.bfloat16, multiple: int = 8) -> torch.Tensor:
+    """3-term split operands ([hi|lo|hi] for side 0, [hi|hi|lo] for side 1) for near-fp32 tensor-core products."""
+    _need_cuda(x)
+    x2 = _rowmajor(x.float() if x.dtype != torch.float32 else x)
+    rows, cols = x2.shape
+    cols_pad = (cols + multiple - 1) // multiple * multiple
+    dtype = torch_dtype(dtype)
+    out = torch.empty((rows, 3 * cols_pad), dtype=dtype, device=x.device)
+    if rows:
+        _capi.call("laff_split3_16", _ptr(x2), rows, cols, x2.stride(0), side, _DT[dtype], _ptr(out), cols_pad,
+                   out.stride(0), _stream(x))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# similarity / ranking
+# ----------------------------------------------------------------------------------------------------------------
+def _check_operands(q: torch.Tensor, g: torch.Tensor):
+    _need_cuda(q, g)
+    if q.dtype != g.dtype or q.dtype not in (torch.float16, torch.bfloat16):
+        raise LaffError("similarity operands must both be fp16 or bf16 (got %s, %s)" % (q.dtype, g.dtype))
+    q, g = _rowmajor(q), _rowmajor(g)
+    if q.shape[1] != g.shape[1]:
+        raise LaffError("operand K mismatch: %d vs %d" % (q.shape[1], g.shape[1]))
+    return q, g
+
+
+def sim_dense(q: torch.Tensor, g: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i, j] = scale * <q_i, g_j>, fp32. q [Q, D], g [V, D] 16-bit."""
+    q, g = _check_operands(q, g)
+    Q, D = q.shape
+    V = g.shape[0]
+    if out is None:
+        out = torch.empty((Q, V), dtype=torch.float32, device=q.device)
+    if Q and V:
+        _capi.call("laff_sim_dense", _ptr(q), _ptr(g), Q, V, D, q.stride(0), g.stride(0), _DT[q.dtype], float(scale),
+                   _ptr(out), out.stride(0), _stream(q))
+    return out
+
+
+def sim_gt_scores(q: torch.Tensor, g: torch.Tensor, gt_local: torch.Tensor) -> torch.Tensor:
+    """Raw (unscaled) accumulator of <q_i, g_{gt_local[i]}>; 0 where gt_local[i] < 0."""
+    q, g = _check_operands(q, g)
+    _need_cuda(gt_local)
+    Q, D = q.shape
+    gt_local = gt_local.to(torch.int32).contiguous()
+    sgt = torch.zeros(Q, dtype=torch.float32, device=q.device)
+    nbytes = _capi.lib().laff_sim_gt_workspace_bytes(Q, D)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    _capi.call("laff_sim_gt_scores", _ptr(q), _ptr(g), Q, g.shape[0], D, q.stride(0), g.stride(0), _DT[q.dtype],
+               _ptr(gt_local), _ptr(sgt), _ptr(ws), nbytes, _stream(q))
+    return sgt
+
+
+def sim_rank_topk(q: torch.Tensor, g: torch.Tensor, sgt_raw: torch.Tensor, gt_global: torch.Tensor, k: int,
+                  scale: float = 1.0, col_offset: int = 0, workspace: Optional[torch.Tensor] = None):
+    """One fused sweep: (count int32 [Q], topk_val fp32 [Q,k], topk_idx int32 [Q,k]) over the local gallery shard."""
+    q, g = _check_operands(q, g)
+    _need_cuda(sgt_raw, gt_global)
+    Q, D = q.shape
+    V = g.shape[0]
+    gt_global = gt_global.to(torch.int32).contiguous()
+    sgt_raw = sgt_raw.float().contiguous()
+    count = torch.empty(Q, dtype=torch.int32, device=q.device)
+    tv = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+    ti = torch.empty((Q, k), dtype=torch.int32, device=q.device)
+    nbytes = _capi.lib().laff_sim_rank_workspace_bytes(Q, V, D)
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    _capi.call("laff_sim_rank_topk", _ptr(q), _ptr(g), Q, V, D, q.stride(0), g.stride(0), _DT[q.dtype], float(scale),
+               _ptr(sgt_raw), _ptr(gt_global), int(col_offset), int(k), _ptr(count), _ptr(tv), _ptr(ti),
+               _ptr(workspace), workspace.numel(), _stream(q))
+    return count, tv, ti
+
+
+def topk_merge(vals: torch.Tensor, idx: torch.Tensor, k_out: int, in_scale: float = 1.0):
+    """vals/idx [n_lists, Q, k_in] ordered lists -> merged ([Q, k_out], [Q, k_out])."""
+    _need_cuda(vals, idx)
+    vals = vals.float().contiguous()
+    idx = idx.to(torch.int32).contiguous()
+    n_lists, Q, k_in = vals.shape
+    ov = torch.empty((Q, k_out), dtype=torch.float32, device=vals.device)
+    oi = torch.empty((Q, k_out), dtype=torch.int32, device=vals.device)
+    _capi.call("laff_topk_merge", _ptr(vals), _ptr(idx), n_lists, Q, k_in, Q * k_in, k_out, float(in_scale), _ptr(ov),
+               _ptr(oi), _stream(vals))
+    return ov, oi
+
+
+def rank_from_scores(scores: torch.Tensor, gt: Optional[torch.Tensor], k: int = 0):
+    """Tie-rule rank / top-k of a materialised fp32 score matrix."""
+    _need_cuda(scores, gt)
+    scores = _rowmajor(scores.float() if scores.dtype != torch.float32 else scores)
+    Q, V = scores.shape
+    rank0 = None
+    if gt is not None:
+        gt = gt.to(torch.int32).contiguous()
+        rank0 = torch.empty(Q, dtype=torch.int32, device=scores.device)
+    tv = ti = None
+    if k > 0:
+        tv = torch.empty((Q, k), dtype=torch.float32, device=scores.device)
+        ti = torch.empty((Q, k), dtype=torch.int32, device=scores.device)
+    _capi.call("laff_rank_from_scores", _ptr(scores), Q, V, scores.stride(0), _ptr(gt), int(k), _ptr(rank0), _ptr(tv),
+               _ptr(ti), _stream(scores))
+    return rank0, tv, ti
+
+
+def rank_metrics(rank0: torch.Tensor) -> torch.Tensor:
+    """Device tensor of 8 doubles: R@1, R@5, R@10, MedR, MeanR, MIR, mAP, Q (evaluation.py:81-89)."""
+    _need_cuda(rank0)
+    rank0 = rank0.to(torch.int32).contiguous()
+    out = torch.empty(8, dtype=torch.float64, device=rank0.device)
+    _capi.call("laff_rank_metrics", _ptr(rank0), rank0.numel(), _ptr(out), _stream(rank0))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fusion
+# ----------------------------------------------------------------------------------------------------------------
+def bn_fold(weight, bias, running_mean, running_var, eps: float = 1e-5):
+    _need_cuda(running_mean, running_var)
+    D = running_mean.numel()
+    scale = torch.empty(D, dtype=torch.float32, device=running_mean.device)
+    shift = torch.empty_like(scale)
+    f = lambda t: None if t is None else t.detach().float().contiguous()
+    weight, bias, running_mean, running_var = f(weight), f(bias), f(running_mean), f(running_var)
+    _capi.call("laff_bn_fold", _ptr(weight), _ptr(bias), _ptr(running_mean), _ptr(running_var), float(eps), D,
+               _ptr(scale), _ptr(shift), _stream(running_mean))
+    return scale, shift
+
+
+def project(x16: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tensor], activation, bn_scale=None, bn_shift=None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = BN(act(x W^T + b)) (TransformNet.forward, model/model.py:257-276). x16 [rows, K], w16 [D, K] 16-bit."""
+    x16, w16 = _check_operands(x16, w16)
+    rows, K = x16.shape
+    D = w16.shape[0]
+    if out is None:
+        out = torch.empty((rows, D), dtype=torch.float32, device=x16.device)
+    act = activation if isinstance(activation, int) else _capi.ACT[activation]
+    if rows:
+        _capi.call("laff_project", _ptr(x16), _ptr(w16), rows, K, D, x16.stride(0), w16.stride(0), _DT[x16.dtype],
+                   _ptr(bias), act, _ptr(bn_scale), _ptr(bn_shift), _ptr(out), out.stride(0), _stream(x16))
+    return out
+
+
+def attention_pool(sources: Sequence[dict], att_weight: torch.Tensor, att_bias: torch.Tensor, heads: int, head_dim: int,
+                   with_ave: bool = False, mul: bool = False, omega: float = 1.0, norm_eps: float = 1e-14,
+                   out16_dtype=None, want_att: bool = False):
+    """LAFF block over L feature sources.
+
+    Each source: {'y': fp32 [rows, D]} (projected) or {'x': fp32 [rows, in_dim], 'bn_scale':..., 'bn_shift':...}
+    (no-transform, tiled + BN).  Returns (out fp32 [rows, heads, head_dim], out16 or None, att [rows, heads, L] or None).
+    """
+    desc = PoolDesc()
+    desc.n_features = len(sources)
+    desc.heads, desc.head_dim = heads, head_dim
+    desc.with_ave, desc.mul = int(bool(with_ave)), int(bool(mul))
+    desc.omega = float(omega)
+    desc.norm_eps = float(norm_eps)
+    att_weight = att_weight.detach().float().contiguous()
+    att_bias = att_bias.detach().float().contiguous()
+    _need_cuda(att_weight, att_bias)
+    desc.att_weight, desc.att_bias = att_weight.data_ptr(), att_bias.data_ptr()
+    keep = []
+    rows = None
+    for l, s in enumerate(sources):
+        if "y" in s:
+            t = _rowmajor(s["y"])
+            desc.src[l].kind, desc.src[l].in_dim = 0, 0
+        else:
+            t = _rowmajor(s["x"].float() if s["x"].dtype != torch.float32 else s["x"])
+            desc.src[l].kind, desc.src[l].in_dim = 1, t.shape[1]
+            if s.get("bn_scale") is not None:
+                desc.src[l].bn_scale, desc.src[l].bn_shift = s["bn_scale"].data_ptr(), s["bn_shift"].data_ptr()
+        _need_cuda(t)
+        if t.dtype != torch.float32:
+            raise LaffError("pool sources must be fp32")
+        keep.append(t)
+        desc.src[l].src, desc.src[l].ld = t.data_ptr(), t.stride(0)
+        rows = t.shape[0] if rows is None else rows
+        if t.shape[0] != rows:
+            raise LaffError("pool sources disagree on the number of rows")
+    dev = keep[0].device
+    D = heads * head_dim
+    out = torch.empty((rows, D), dtype=torch.float32, device=dev)
+    out16 = None
+    o16dt = 0
+    if out16_dtype is not None:
+        out16_dtype = torch_dtype(out16_dtype)
+        out16 = torch.empty((rows, D), dtype=out16_dtype, device=dev)
+        o16dt = _DT[out16_dtype]
+    att = torch.empty((rows, heads, len(sources)), dtype=torch.float32, device=dev) if want_att else None
+    if rows:
+        _capi.call("laff_attention_pool", C.byref(desc), rows, _ptr(out), D, _ptr(out16), o16dt, D, _ptr(att),
+                   _stream(keep[0]))
+    return out.view(rows, heads, head_dim), (None if out16 is None else out16.view(rows, heads, head_dim)), att
+
+
+def frame_pool(frames: torch.Tensor, att_weight: torch.Tensor, att_bias: float, with_ave: bool = False,
+               mul: bool = False, omega: float = 1.0, norm_eps: float = 1e-14) -> torch.Tensor:
+    """Frame-level LAFF block: frames fp32 [B, F, dim] -> [B, dim] unit norm."""
+    _need_cuda(frames, att_weight)
+    frames = frames.float().contiguous()
+    B, F, dim = frames.shape
+    att_weight = att_weight.detach().float().contiguous().view(-1)
+    out = torch.empty((B, dim), dtype=torch.float32, device=frames.device)
+    if B:
+        _capi.call("laff_frame_pool", _ptr(frames), B, F, dim, _ptr(att_weight), float(att_bias), int(bool(with_ave)),
+                   int(bool(mul)), float(omega), float(norm_eps), _ptr(out), out.stride(0), _stream(frames))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# loss
+# ----------------------------------------------------------------------------------------------------------------
+def mrl_forward_backward(txt: torch.Tensor, vis: torch.Tensor, margin: float, max_violation: bool, direction: str,
+                         cost_style: str, need_grad: bool = True):
+    """Sum over heads of MarginRankingLoss(s=txt[:,h], im=vis[:,h]); returns (loss scalar tensor, d_txt, d_vis)."""
+    _need_cuda(txt, vis)
+    if txt.dim() == 2:
+        txt, vis = txt.unsqueeze(1), vis.unsqueeze(1)
+    txt = txt.detach().float().contiguous()
+    vis = vis.detach().float().contiguous()
+    B, H, dh = txt.shape
+    loss = torch.empty((), dtype=torch.float32, device=txt.device)
+    d_txt = torch.empty_like(txt) if need_grad else None
+    d_vis = torch.empty_like(vis) if need_grad else None
+    nbytes = _capi.lib().laff_mrl_workspace_bytes(B, H, dh)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=txt.device)
+    _capi.call("laff_mrl_forward_backward", _ptr(txt), _ptr(vis), B, H, dh, float(margin), int(bool(max_violation)),
+               _capi.DIRECTION[direction], int(cost_style != "sum"), _ptr(loss), _ptr(d_txt), _ptr(d_vis), _ptr(ws),
+               nbytes, _stream(txt))
+    return loss, d_txt, d_vis
+
+
+def mrl_score_forward_backward(score: torch.Tensor, margin: float, max_violation: bool, direction: str,
+                               cost_style: str, need_grad: bool = True):
+    _need_cuda(score)
+    score = _rowmajor(score.detach().float())
+    B = score.shape[0]
+    loss = torch.empty((), dtype=torch.float32, device=score.device)
+    d_score = torch.empty((B, B), dtype=torch.float32, device=score.device) if need_grad else None
+    _capi.call("laff_mrl_score_forward_backward", _ptr(score), B, score.stride(0), float(margin),
+               int(bool(max_violation)), _capi.DIRECTION[direction], int(cost_style != "sum"), _ptr(loss),
+               _ptr(d_score), _stream(score))
+    return loss, d_score

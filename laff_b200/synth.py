@@ -1,0 +1,115 @@
+"""Seeded synthetic inputs and parameters for the LAFF hot path (shared by tests, golden generation and bench.py).
+
+Everything is generated with ``numpy.random.RandomState`` keyed by (seed, name) so that any consumer can regenerate a
+tensor by name without depending on generation order (the reference's constructors consume torch RNG while building
+all 16 attention variants, model/model.py:95-206, so seeds alone cannot reproduce its own initialisation).
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Dict, Iterable, Mapping, Tuple
+
+import numpy as np
+
+# Feature dimensions: pinned by the reference unless marked assumed.
+DIMS = {
+    "clip": 512,     # configs/laff.py:36 clip_opt['size']
+    "gru": 1024,     # configs/base_config.py:38 rnn_size
+    "w2v": 500,      # configs/base_config.py:37, trainer.py:190
+    "bow": 3981,     # data/vocab_tgif.zip bow_nsw_5 vocabulary
+    "x3d": 2048,     # assumed (public backbone)
+    "ircsn": 2048,   # assumed
+    "tf": 768,       # assumed (TimeSformer)
+    "c3d": 2048,     # assumed
+}
+
+# reference feature names (configs/laff.py:54-65, FrameLaff...:63-66,104-112)
+VIS_CLIP_FT = "clip_finetune_8frame_uniform_1103"
+VIS_TF = "HowTo100M_TimeSformer_divST_96x4_224"
+VIS_X3D = "X3D_L"
+VIS_IRCSN = "mean_irCSN_152_ig65m_from_scratch"
+VIS_C3D = "mean_C3d_resneXt101_16f"
+VIS_FRAME = "Frame_clip_finetune_8frame_uniform_1103"
+
+
+def rng_for(seed: int, name: str) -> np.random.RandomState:
+    return np.random.RandomState((int(seed) * 1000003 + zlib.crc32(name.encode())) % (2 ** 32))
+
+
+def feature(seed: int, name: str, rows: int, dim: int, kind: str = "dense") -> np.ndarray:
+    """One synthetic feature matrix [rows, dim] float32.
+
+    dense: N(0,1); relu: max(N(0,1),0) (pooled CNN features); bow: counts of 8 random vocabulary ids per row.
+    """
+    r = rng_for(seed, "feat/" + name)
+    if kind == "bow":
+        out = np.zeros((rows, dim), dtype=np.float32)
+        ids = r.randint(0, dim, size=(rows, 8))
+        for i in range(rows):
+            np.add.at(out[i], ids[i], 1.0)
+        return out
+    x = r.standard_normal((rows, dim)).astype(np.float32)
+    if kind == "relu":
+        x = np.maximum(x, 0.0)
+    return x
+
+
+def param(seed: int, key: str, shape: Tuple[int, ...], omega: float = 1.0) -> np.ndarray:
+    """Synthetic value of one state_dict entry, chosen by the reference parameter name."""
+    r = rng_for(seed, "param/" + key)
+    shape = tuple(int(s) for s in shape)
+    if key.endswith("num_batches_tracked"):
+        return np.asarray(1, dtype=np.int64)
+    if key.endswith("global_emb_weight_net.weight"):
+        return np.full(shape, omega, dtype=np.float32)
+    if ".bn1." in key or key.endswith(("bn1.weight", "bn1.bias", "bn1.running_mean", "bn1.running_var")):
+        if key.endswith("running_var"):
+            return r.uniform(0.5, 2.0, shape).astype(np.float32)
+        if key.endswith("running_mean"):
+            return (0.5 * r.standard_normal(shape)).astype(np.float32)
+        if key.endswith("weight"):
+            return r.uniform(0.5, 1.5, shape).astype(np.float32)
+        return (0.1 * r.standard_normal(shape)).astype(np.float32)
+    if "layer_norm" in key:
+        return (np.ones(shape) if key.endswith("weight") else np.zeros(shape)).astype(np.float32)
+    if "embedding_common" in key:
+        dh = shape[-1] if key.endswith("weight") else 1
+        if key.endswith("weight"):
+            return r.uniform(-3.0, 3.0, shape).astype(np.float32) / np.float32(np.sqrt(dh))
+        return r.uniform(-0.1, 0.1, shape).astype(np.float32)
+    if key.endswith("fc1.weight") or (len(shape) == 2 and key.endswith("weight")):
+        bound = np.sqrt(6.0 / (shape[0] + shape[1]))  # xavier_uniform_ (model/model.py:55)
+        return r.uniform(-bound, bound, shape).astype(np.float32)
+    if key.endswith("bias"):
+        return (0.05 * r.standard_normal(shape)).astype(np.float32)
+    return (0.1 * r.standard_normal(shape)).astype(np.float32)
+
+
+def state_dict(seed: int, shapes: Mapping[str, Tuple[int, ...]], omega: float = 1.0) -> Dict[str, np.ndarray]:
+    return {k: param(seed, k, s, omega) for k, s in shapes.items()}
+
+
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even to bfloat16, returned as float32 (numpy has no bf16)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    u = x.view(np.uint32).astype(np.uint64)
+    rounded = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return rounded.astype(np.uint32).view(np.float32).reshape(x.shape)
+
+
+def unit_heads(x: np.ndarray, heads: int) -> np.ndarray:
+    rows = x.shape[0]
+    y = x.reshape(rows, heads, -1).astype(np.float32)
+    y = y / np.sqrt((y * y).sum(2, keepdims=True))
+    return y.reshape(rows, -1)
+
+
+def retrieval_embeddings(seed: int, Q: int, V: int, heads: int = 8, head_dim: int = 512, sigma: float = 1.2):
+    """C5-style synthetic embeddings: gallery = unit-norm noise per head, gt(i) = (i*97) mod V,
+    query = normalize(gallery[gt] + sigma * unit noise).  Returns (q [Q,D], g [V,D], gt [Q]) float32 / int64."""
+    D = heads * head_dim
+    g = unit_heads(rng_for(seed, "emb/gallery").standard_normal((V, D)).astype(np.float32), heads)
+    gt = (np.arange(Q, dtype=np.int64) * 97) % V
+    noise = unit_heads(rng_for(seed, "emb/query").standard_normal((Q, D)).astype(np.float32), heads)
+    q = unit_heads(g[gt] + sigma * noise, heads)
+    return q, g, gt
