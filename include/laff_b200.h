@@ -133,6 +133,12 @@ int laff_rank_from_scores(const float* scores, int Q, int V, long long ld, const
  *       [5] MIR = mean(1 / (rank0 + 1))  [6] mAP (= MIR for a single ground truth)  [7] Q. */
 int laff_rank_metrics(const int32_t* rank0, int Q, double* out8, void* stream);
 
+/* evaluation.eval(label_matrix) (evaluation.py:92-109) for the caller that still builds the 0/1 label matrix
+ * (predictor.py:236-246): label uint8 [Q, V] ld, column p = p-th ranked item.  rank0[i] = 0-based position of the
+ * first 1 (-1 if none), ap[i] = average precision; out8 as laff_rank_metrics with [6] = mAP = mean(ap). */
+int laff_label_metrics(const uint8_t* label, int Q, int V, long long ld, int32_t* rank0, double* ap, double* out8,
+                       void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * F1  TransformNet.forward (model/model.py:257-276): y = BN(act(x W^T + b)), eval mode (dropout = identity,
  *     BatchNorm1d running stats, eps bn_eps).  x16 [rows, K] ldx, w16 [D, K] ldw (16-bit, K-major, pitches % 8 == 0).

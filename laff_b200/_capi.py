@@ -67,6 +67,7 @@ SIGNATURES = {
     "laff_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _ll, _i, _f, _vp, _vp, _vp]),
     "laff_rank_from_scores": (_i, [_vp, _i, _i, _ll, _vp, _i, _vp, _vp, _vp, _vp]),
     "laff_rank_metrics": (_i, [_vp, _i, _vp, _vp]),
+    "laff_label_metrics": (_i, [_vp, _i, _i, _ll, _vp, _vp, _vp, _vp]),
     "laff_project": (_i, [_vp, _vp, _ll, _i, _i, _ll, _ll, _i, _vp, _i, _vp, _vp, _vp, _ll, _vp]),
     "laff_bn_fold": (_i, [_vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _vp]),
     "laff_attention_pool": (_i, [C.POINTER(PoolDesc), _ll, _vp, _ll, _vp, _i, _ll, _vp, _vp]),

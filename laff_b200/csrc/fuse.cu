@@ -128,8 +128,9 @@ struct EpiProject {
     const float* bn_shift;
     int act;
   };
+  static constexpr int kSmemBytes = 0;
   Params p;
-  __device__ explicit EpiProject(const Params& p_) : p(p_) {}
+  __device__ EpiProject(const Params& p_, uint8_t*, int) : p(p_) {}
   __device__ __forceinline__ void unit_begin(int, const Unit&) {}
   __device__ __forceinline__ void unit_end(int, const Unit&) {}
   __device__ __forceinline__ void chunk(const uint32_t (&r)[32], int row, int col0) {
@@ -446,41 +447,11 @@ int laff_project(const void* x16, const void* w16, long long rows, int K, int D,
   const int num_kb = (K + kBlockK - 1) / kBlockK;
   const uint32_t idesc = make_idesc_f16(dtype, kBlockM * cg, kBlockN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (s.total_units <= 0) return LAFF_OK;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = static_cast<unsigned>(cg);
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cfg.blockDim = dim3(kNumThreads);
-  cfg.stream = st;
-  int clusters = di.sms / cg;
-  if (clusters > s.total_units) clusters = s.total_units;
-  cfg.gridDim = dim3(static_cast<unsigned>(clusters * cg));
   const uint64_t hintA = ptx::kEvictNormal, hintB = ptx::kEvictLast;
-  if (cg == 2) {
-    auto kern = gemm_kernel<2, EpiProject>;
-    static bool configured = false;
-    if (!configured) {
-      LAFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, EngineCfg<2>::kSmemBytes));
-      configured = true;
-    }
-    cfg.dynamicSmemBytes = EngineCfg<2>::kSmemBytes;
-    LAFF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, num_kb, idesc, s, hintA, hintB, ep));
-  } else {
-    auto kern = gemm_kernel<1, EpiProject>;
-    static bool configured = false;
-    if (!configured) {
-      LAFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, EngineCfg<1>::kSmemBytes));
-      configured = true;
-    }
-    cfg.dynamicSmemBytes = EngineCfg<1>::kSmemBytes;
-    LAFF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, num_kb, idesc, s, hintA, hintB, ep));
-  }
+  if (cg == 2)
+    LAFF_CUDA((launch_gemm_kernel<2, EpiProject>(tmA, tmB, num_kb, idesc, s, ep, hintA, hintB, di.sms, st)));
+  else
+    LAFF_CUDA((launch_gemm_kernel<1, EpiProject>(tmA, tmB, num_kb, idesc, s, ep, hintA, hintB, di.sms, st)));
   return LAFF_OK;
 }
 

@@ -4,7 +4,8 @@
 //   warp 0      TMA producer      (one lane)  global -> smem ring, SWIZZLE_128B tiles of 64 K-elements
 //   warp 1      MMA issuer        (one lane, leader CTA of the pair only)  tcgen05.mma, commits to mbarriers
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue          tcgen05.ld (warp w reads TMEM lanes 32*(w%4)..+31, one accumulator row per thread)
+//   warps 4..11 epilogue          tcgen05.ld: warp w reads TMEM lanes 32*(w%4)..+31 (one accumulator row per thread);
+//                                 warps 4..7 take columns 0..127 of a tile, warps 8..11 columns 128..255
 //
 // The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile
 // i+1.  CG (cta_group) = 1: one CTA owns a 128 x 256 tile.  CG = 2: a CTA pair (cluster of 2) owns a 256 x 256 tile;
@@ -25,7 +26,10 @@ constexpr int kBlockK = 64;   // 16-bit K elements per pipeline stage = one 128-
 constexpr int kUmmaK = 16;    // K per tcgen05.mma for 16-bit operands
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 384;
+constexpr int kEpiWarps = 8;                  // two per TMEM lane quadrant
+constexpr int kEpiThreads = kEpiWarps * 32;   // epilogue threads per CTA: (row, column half)
+constexpr int kEpiCols = kBlockN / 2;         // columns of a tile one epilogue thread walks
 
 template <int CG>
 struct EngineCfg {
@@ -36,7 +40,9 @@ struct EngineCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTxBytes = kStageBytes * CG;  // bytes landing per stage across the CTAs of one MMA
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kPipeBytes = kStages * kStageBytes + kBarBytes;
+  // + per-epilogue scratch (Epi::kSmemBytes) + alignment slack
+  static constexpr int smem_bytes(int epi_bytes) { return kPipeBytes + epi_bytes + 1024; }
 };
 
 struct Sched {
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     }
     for (int a = 0; a < kAccStages; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);        // one tcgen05.commit per tile
-      ptx::mbar_init(tempty_bar(a), 4 * CG);  // one arrive per epilogue warp of every CTA of the pair
+      ptx::mbar_init(tempty_bar(a), kEpiWarps * CG);  // one arrive per epilogue warp of every CTA of the pair
     }
     ptx::fence_barrier_init();
   }
@@ -212,9 +218,10 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     __syncwarp();
   } else if (warp >= 4) {
     // ============================================= epilogue =============================================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;   // which 128 columns of each tile
     const int row_in_cta = quad * 32 + lane;
-    Epi epi(ep);
+    Epi epi(ep, smem + Cfg::kPipeBytes, half * kBlockM + row_in_cta);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = cluster_id; u < sched.total_units; u += num_clusters) {
@@ -224,13 +231,14 @@ __global__ void __launch_bounds__(kNumThreads, 1)
       for (int n = un.n_begin; n < un.n_end; ++n) {
         ptx::mbar_wait(tfull_bar(acc), acc_phase, 4);
         ptx::tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * kBlockN);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(acc * kBlockN + half * kEpiCols);
 #pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
+        for (int c = 0; c < kEpiCols / 32; ++c) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), r);
           ptx::tmem_ld_wait();
-          epi.chunk(r, row, n * kBlockN + c * 32);
+          epi.chunk(r, row, n * kBlockN + half * kEpiCols + c * 32);
         }
         ptx::tcgen05_fence_before();
         __syncwarp();
@@ -251,6 +259,41 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Host-side launch (one persistent CTA, or CTA pair, per SM)
+// ------------------------------------------------------------------------------------------------------------
+template <int CG, class Epi>
+inline cudaError_t launch_gemm_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, int num_kb, uint32_t idesc,
+                                      const Sched& s, const typename Epi::Params& ep, uint64_t hintA, uint64_t hintB,
+                                      int sms, cudaStream_t st) {
+  using Cfg = EngineCfg<CG>;
+  constexpr int kSmem = Cfg::smem_bytes(Epi::kSmemBytes);
+  static_assert(kSmem <= 227 * 1024, "shared memory budget exceeded");
+  auto kern = gemm_kernel<CG, Epi>;
+  static bool configured = false;  // per instantiation; one device per process
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (s.total_units <= 0) return cudaSuccess;
+  int clusters = sms / CG;
+  if (clusters > s.total_units) clusters = s.total_units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, num_kb, idesc, s, hintA, hintB, ep);
 }
 
 }  // namespace laff

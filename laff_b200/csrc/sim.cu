@@ -24,8 +24,9 @@ struct EpiDense {
     int M, N;
     float scale;
   };
+  static constexpr int kSmemBytes = 0;
   Params p;
-  __device__ explicit EpiDense(const Params& p_) : p(p_) {}
+  __device__ EpiDense(const Params& p_, uint8_t*, int) : p(p_) {}
   __device__ __forceinline__ void unit_begin(int, const Unit&) {}
   __device__ __forceinline__ void unit_end(int, const Unit&) {}
   __device__ __forceinline__ void chunk(const uint32_t (&r)[32], int row, int col0) {
@@ -52,9 +53,10 @@ struct EpiNull {
     float* sink;
     int mode;
   };
+  static constexpr int kSmemBytes = 0;
   Params p;
   float acc;
-  __device__ explicit EpiNull(const Params& p_) : p(p_), acc(0.f) {}
+  __device__ EpiNull(const Params& p_, uint8_t*, int) : p(p_), acc(0.f) {}
   __device__ __forceinline__ void unit_begin(int, const Unit&) {}
   __device__ __forceinline__ void unit_end(int row, const Unit&) {
     if (acc == 123.456f) p.sink[row & 1023] = acc;
@@ -72,8 +74,9 @@ struct EpiDiag {
     const int32_t* gt_local;
     int M;
   };
+  static constexpr int kSmemBytes = 0;
   Params p;
-  __device__ explicit EpiDiag(const Params& p_) : p(p_) {}
+  __device__ EpiDiag(const Params& p_, uint8_t*, int) : p(p_) {}
   __device__ __forceinline__ void unit_begin(int, const Unit&) {}
   __device__ __forceinline__ void unit_end(int, const Unit&) {}
   __device__ __forceinline__ void chunk(const uint32_t (&r)[32], int row, int col0) {
@@ -92,82 +95,167 @@ __device__ __forceinline__ bool better(float va, int ia, float vb, int ib) {
   return va > vb || (va == vb && ia > ib);
 }
 
+// Monotone float <-> int key so that a per-query score threshold can be raised with atomicMax.
+__device__ __forceinline__ int float_key(float v) {
+  const int b = __float_as_int(v);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+// (score, index) packed so that "better" under the tie rule (score desc, index desc) is a plain signed 64-bit ">".
+__device__ __forceinline__ long long pack_entry(float v, int idx) {
+  return (static_cast<long long>(float_key(v)) << 32) | static_cast<long long>(static_cast<unsigned>(idx));
+}
+constexpr long long kEmptySlot = static_cast<long long>(0x8000000000000000ull);  // below every real entry
+
+// Out-of-line slow path of the rank epilogue: offer entry e to the query's k global slots (an unordered set that
+// converges to the exact top-k).  Lock-free: replace the current minimum slot by CAS while e beats it.  Slots only
+// ever improve, so any value read here is a valid lower bound of the final k-th best.  Returns the new threshold.
+static __device__ __noinline__ float topk_offer(long long* slots, int32_t* thr_key, long long e, int k) {
+  for (;;) {
+    long long mn = 0x7fffffffffffffffLL, mn2 = 0x7fffffffffffffffLL;
+    int at = 0;
+    for (int i = 0; i < k; ++i) {
+      const long long s = __ldcg(slots + i);
+      if (s < mn) {
+        mn2 = mn;
+        mn = s;
+        at = i;
+      } else if (s < mn2) {
+        mn2 = s;
+      }
+    }
+    if (e <= mn) return key_float(static_cast<int>(mn >> 32));  // not (or no longer) among the k best
+    const long long old = atomicCAS(reinterpret_cast<unsigned long long*>(slots + at),
+                                    static_cast<unsigned long long>(mn), static_cast<unsigned long long>(e));
+    if (old == mn) {
+      const long long new_min = e < mn2 ? e : mn2;  // k == 1: mn2 stays at +max, so new_min = e
+      const int key = static_cast<int>(new_min >> 32);
+      if (new_min != kEmptySlot) atomicMax(thr_key, key);
+      return new_min == kEmptySlot ? -INFINITY : key_float(key);
+    }
+  }
+}
+
+// Similarity sweep epilogue: exact rank counting + streaming exact top-k.  One epilogue thread owns (query row,
+// 128-column half of each tile) for all tiles of a unit.
+//   fast path per score: compare-and-count against s_gt, and two compares OR-ed into one "look closer" predicate;
+//   one branch per 32 scores;
+//   slow path (a score reaches the query's threshold, or ties s_gt exactly): tie rule + topk_offer.
+// The threshold of a query is a published lower bound of its current k-th best over ALL gallery columns any CTA has
+// swept so far, so the slow path dies out like k/columns_seen.
 template <int KMAX>
 struct EpiRank {
   struct Params {
     const float* sgt;     // raw accumulator of (i, gt_i)
     const int32_t* gt;    // global gallery index of the ground truth
     int32_t* count;       // [M] += local rank contribution
-    float* part_val;      // [n_chunks, M, KMAX]
-    int32_t* part_idx;
+    int32_t* thr_key;     // [M] float_key of a lower bound of the k-th best (init: float_key(-inf))
+    long long* slots;     // [M, KMAX] packed entries (init: kEmptySlot)
     int M, N;             // queries, local gallery size
     int col_offset;       // global index of local column 0
+    int k;                // top-k size (<= KMAX); 0: rank only
   };
+  static constexpr int kSmemBytes = 0;
   Params p;
-  float tv[KMAX];
-  int ti[KMAX];
   int cnt;
-  float sg;
-  int g;
-  __device__ explicit EpiRank(const Params& p_) : p(p_) {}
+  float sg;    // s_gt
+  int g;       // gt (global index)
+  float thr;   // current threshold (lower bound of the k-th best)
+  long long* my_slots;
+  int32_t* my_thr;
+
+  __device__ EpiRank(const Params& p_, uint8_t*, int) : p(p_) {}
 
   __device__ __forceinline__ void unit_begin(int row, const Unit&) {
-#pragma unroll
-    for (int i = 0; i < KMAX; ++i) {
-      tv[i] = -INFINITY;
-      ti[i] = -1;
-    }
     cnt = 0;
-    sg = 0.f;
+    sg = INFINITY;  // rows beyond M: nothing counts, nothing is offered
     g = -1;
+    thr = INFINITY;
+    my_slots = nullptr;
+    my_thr = nullptr;
     if (row < p.M) {
       sg = p.sgt[row];
       g = p.gt[row];
-    }
-  }
-
-  __device__ __forceinline__ void insert(float v, int idx) {
-    // replace the worst entry, then bubble the new one up; fully unrolled so the lists stay in registers
-    tv[KMAX - 1] = v;
-    ti[KMAX - 1] = idx;
-#pragma unroll
-    for (int i = KMAX - 1; i > 0; --i) {
-      const bool sw = better(tv[i], ti[i], tv[i - 1], ti[i - 1]);
-      const float fv = sw ? tv[i - 1] : tv[i];
-      const int fi = sw ? ti[i - 1] : ti[i];
-      tv[i - 1] = sw ? tv[i] : tv[i - 1];
-      ti[i - 1] = sw ? ti[i] : ti[i - 1];
-      tv[i] = fv;
-      ti[i] = fi;
-    }
-  }
-
-  __device__ __forceinline__ void chunk(const uint32_t (&r)[32], int row, int col0) {
-    if (row >= p.M) return;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = col0 + j;
-      if (col < p.N) {
-        const float v = __uint_as_float(r[j]);
-        const int gcol = col + p.col_offset;
-        const bool beats = (v > sg) || (v == sg && gcol > g);
-        cnt += (beats && gcol != g) ? 1 : 0;
-        if (better(v, gcol, tv[KMAX - 1], ti[KMAX - 1])) insert(v, gcol);
+      if (p.k > 0) {
+        my_slots = p.slots + static_cast<long long>(row) * KMAX;
+        my_thr = p.thr_key + row;
+        thr = key_float(__ldcg(my_thr));
       }
     }
   }
 
-  __device__ __forceinline__ void unit_end(int row, const Unit& un) {
-    if (row >= p.M) return;
-    if (cnt) atomicAdd(p.count + row, cnt);
-    const long long o = (static_cast<long long>(un.chunk) * p.M + row) * KMAX;
+  __device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], int gcol0) {
+    if (my_thr != nullptr) thr = fmaxf(thr, key_float(__ldcg(my_thr)));  // pick up other CTAs' progress
 #pragma unroll
-    for (int i = 0; i < KMAX; ++i) {
-      p.part_val[o + i] = tv[i];
-      p.part_idx[o + i] = ti[i];
+    for (int j = 0; j < 32; ++j) {
+      const float v = __uint_as_float(r[j]);
+      if (v >= thr || v == sg) {
+        const int gcol = gcol0 + j;
+        if (v == sg && gcol > g) ++cnt;  // tie with the ground truth: higher index ranks first
+        if (v >= thr && v > -INFINITY) thr = fmaxf(thr, topk_offer(my_slots, my_thr, pack_entry(v, gcol), p.k));
+      }
     }
   }
+
+  __device__ __forceinline__ void chunk(uint32_t (&r)[32], int row, int col0) {
+    if (col0 + 32 > p.N) {  // last, partial tile: columns past the gallery read as zero -> make them -inf
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j >= p.N) r[j] = 0xff800000u;
+    }
+    bool look = false;
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float v = __uint_as_float(r[j]);
+      c += (v > sg) ? 1 : 0;
+      look = look || (v >= thr) || (v == sg);
+    }
+    cnt += c;
+    if (look) slow_chunk(r, col0 + p.col_offset);
+  }
+
+  __device__ __forceinline__ void unit_end(int row, const Unit&) {
+    if (row < p.M && cnt) atomicAdd(p.count + row, cnt);
+  }
 };
+
+__global__ void rank_init_kernel(int32_t* count, int32_t* thr_key, long long* slots, int Q, int kmax) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Q) {
+    count[i] = 0;
+    thr_key[i] = float_key(-INFINITY);
+  }
+  if (i < Q * kmax) slots[i] = kEmptySlot;
+}
+
+// Order each query's k slots by the tie rule and unpack: one thread per query, k <= 16.
+__global__ void topk_finalize_kernel(const long long* __restrict__ slots, int Q, int kmax, int k, float scale,
+                                     float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  long long e[LAFF_MAX_TOPK];
+#pragma unroll
+  for (int i = 0; i < LAFF_MAX_TOPK; ++i) e[i] = i < k ? slots[static_cast<long long>(q) * kmax + i] : kEmptySlot;
+#pragma unroll
+  for (int i = 1; i < LAFF_MAX_TOPK; ++i) {  // insertion sort, descending, fully unrolled (registers)
+#pragma unroll
+    for (int j = i; j > 0; --j) {
+      const long long a = e[j - 1], b = e[j];
+      e[j - 1] = a > b ? a : b;
+      e[j] = a > b ? b : a;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LAFF_MAX_TOPK; ++i) {
+    if (i < k) {
+      const bool empty = e[i] == kEmptySlot;
+      out_val[static_cast<long long>(q) * k + i] = empty ? -INFINITY : key_float(static_cast<int>(e[i] >> 32)) * scale;
+      out_idx[static_cast<long long>(q) * k + i] = empty ? -1 : static_cast<int>(e[i] & 0xffffffffLL);
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // Launch helper
@@ -177,34 +265,11 @@ static uint64_t g_hint_override[2] = {0, 0};
 template <int CG, class Epi>
 static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, int num_kb, uint32_t idesc, const Sched& s,
                           const typename Epi::Params& ep, int sms, cudaStream_t st) {
-  using Cfg = EngineCfg<CG>;
-  auto kern = gemm_kernel<CG, Epi>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    LAFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
-  if (s.total_units <= 0) return LAFF_OK;
-  int clusters = sms / CG;
-  if (clusters > s.total_units) clusters = s.total_units;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG));
-  cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   // queries (A) are re-read by every gallery tile: keep them in L2; the gallery (B) streams through once per m-group
   uint64_t hintA = ptx::kEvictLast, hintB = ptx::kEvictNormal;
   if (g_hint_override[0]) hintA = g_hint_override[0];
   if (g_hint_override[1]) hintB = g_hint_override[1];
-  LAFF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, num_kb, idesc, s, hintA, hintB, ep));
+  LAFF_CUDA((launch_gemm_kernel<CG, Epi>(tmA, tmB, num_kb, idesc, s, ep, hintA, hintB, sms, st)));
   return LAFF_OK;
 }
 
@@ -261,8 +326,8 @@ __global__ void gather_rows16_kernel(const uint4* __restrict__ g, long long ldg1
 
 // One warp per query: k_out rounds of "best candidate strictly worse than the previous pick".
 __global__ void topk_merge_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx, int n_lists, int Q,
-                                  int k_in, long long list_stride, int k_out, float in_scale, float* __restrict__ out_val,
-                                  int32_t* __restrict__ out_idx) {
+                                  int k_in, long long list_stride, int row_stride, int k_out, float in_scale,
+                                  float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= Q) return;
@@ -274,7 +339,7 @@ __global__ void topk_merge_kernel(const float* __restrict__ vals, const int32_t*
     int bi = -1;
     for (int c = lane; c < n_cand; c += 32) {
       const int l = c / k_in, e = c - l * k_in;
-      const long long o = static_cast<long long>(l) * list_stride + static_cast<long long>(warp) * k_in + e;
+      const long long o = static_cast<long long>(l) * list_stride + static_cast<long long>(warp) * row_stride + e;
       const float v = vals[o];
       const int i = idx[o];
       if (i >= 0 && better(last_v, last_i, v, i) && better(v, i, bv, bi)) {
@@ -454,6 +519,51 @@ __global__ void rank_metrics_kernel(const int32_t* __restrict__ rank0, int Q, do
   }
 }
 
+// evaluation.eval (evaluation.py:92-109) on a 0/1 label matrix whose column p is the p-th ranked item: one warp per
+// query finds the 1-based rank of the first ground truth and AP = mean_j (j + 1) / rank_j over its ground truths.
+__global__ void label_metrics_kernel(const uint8_t* __restrict__ label, int Q, int V, long long ld,
+                                     int32_t* __restrict__ rank0, double* __restrict__ ap) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= Q) return;
+  const uint8_t* row = label + static_cast<long long>(warp) * ld;
+  int first = -1;
+  int seen = 0;
+  double acc = 0.0;
+  for (int base = 0; base < V; base += 32) {
+    const int p = base + lane;
+    const bool hit = p < V && row[p] == 1;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+      if (first < 0) first = base + __ffs(m) - 1;
+      if (hit) {
+        const int j = seen + __popc(m & ((1u << lane) - 1u));  // index of this ground truth among the row's
+        acc += static_cast<double>(j + 1) / static_cast<double>(p + 1);
+      }
+      seen += __popc(m);
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    rank0[warp] = first;  // -1: no ground truth in the row (the reference would raise IndexError)
+    ap[warp] = seen > 0 ? acc / static_cast<double>(seen) : 0.0;
+  }
+}
+
+__global__ void mean_double_kernel(const double* __restrict__ x, int n, double* __restrict__ out) {
+  __shared__ double s[32];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += x[i];
+  for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += s[i];
+    *out = t / static_cast<double>(n);
+  }
+}
+
 }  // namespace laff
 
 // ------------------------------------------------------------------------------------------------------------
@@ -527,9 +637,8 @@ int laff_sim_gt_scores(const void* q, const void* g, int Q, int V, int D, long l
 size_t laff_sim_rank_workspace_bytes(int Q, int V, int D) {
   (void)D;
   if (Q <= 0 || V <= 0) return 0;
-  const Tuning t = get_tuning();
-  const Sched s = make_sched(Q, V, t.cta_group, t.chunk_tiles, t.m_group, 0);
-  return static_cast<size_t>(s.n_chunks) * static_cast<size_t>(Q) * LAFF_MAX_TOPK * 8 + 512;
+  // per query: LAFF_MAX_TOPK packed slots + one threshold word
+  return static_cast<size_t>(Q) * (LAFF_MAX_TOPK * 8 + 4) + 512;
 }
 
 int laff_sim_rank_topk(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
@@ -549,17 +658,16 @@ int laff_sim_rank_topk(const void* q, const void* g, int Q, int V, int D, long l
   if (rc) return rc;
   const Sched s = make_sched(Q, V, op.cg, t.chunk_tiles, t.m_group, 0);
   uintptr_t wp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255);
-  float* part_val = reinterpret_cast<float*>(wp);
-  int32_t* part_idx = reinterpret_cast<int32_t*>(wp + static_cast<size_t>(s.n_chunks) * Q * LAFF_MAX_TOPK * 4);
-  LAFF_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * static_cast<size_t>(Q), st));
-  EpiRank<LAFF_MAX_TOPK>::Params ep{sgt_raw, gt_global, count, part_val, part_idx, Q, V, col_offset};
+  long long* slots = reinterpret_cast<long long*>(wp);
+  int32_t* thr_key = reinterpret_cast<int32_t*>(wp + static_cast<size_t>(Q) * LAFF_MAX_TOPK * 8);
+  const int init_n = Q * LAFF_MAX_TOPK;
+  rank_init_kernel<<<(init_n + 255) / 256, 256, 0, st>>>(count, thr_key, slots, Q, LAFF_MAX_TOPK);
+  LAFF_CUDA(cudaGetLastError());
+  EpiRank<LAFF_MAX_TOPK>::Params ep{sgt_raw, gt_global, count, thr_key, slots, Q, V, col_offset, k};
   rc = launch_gemm<EpiRank<LAFF_MAX_TOPK>>(op, s, ep, st);
   if (rc) return rc;
   if (k > 0) {
-    const int threads = 128;
-    const int blocks = (Q * 32 + threads - 1) / threads;
-    topk_merge_kernel<<<blocks, threads, 0, st>>>(part_val, part_idx, s.n_chunks, Q, LAFF_MAX_TOPK,
-                                                  static_cast<long long>(Q) * LAFF_MAX_TOPK, k, scale, topk_val, topk_idx);
+    topk_finalize_kernel<<<(Q + 127) / 128, 128, 0, st>>>(slots, Q, LAFF_MAX_TOPK, k, scale, topk_val, topk_idx);
     LAFF_CUDA(cudaGetLastError());
   }
   return LAFF_OK;
@@ -575,7 +683,7 @@ int laff_topk_merge(const float* vals, const int32_t* idx, int n_lists, int Q, i
   const int threads = 128;
   const int blocks = (Q * 32 + threads - 1) / threads;
   topk_merge_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(vals, idx, n_lists, Q, k_in, list_stride,
-                                                                              k_out, in_scale, out_val, out_idx);
+                                                                              k_in, k_out, in_scale, out_val, out_idx);
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }
@@ -590,6 +698,21 @@ int laff_rank_from_scores(const float* scores, int Q, int V, long long ld, const
   if (rc) return rc;
   rank_from_scores_kernel<<<Q, 256, 0, static_cast<cudaStream_t>(stream)>>>(scores, V, ld, gt, k, rank0, topk_val,
                                                                            topk_idx);
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}
+
+int laff_label_metrics(const uint8_t* label, int Q, int V, long long ld, int32_t* rank0, double* ap, double* out8,
+                       void* stream) {
+  LAFF_REQUIRE(label && rank0 && ap && out8 && Q > 0 && V > 0 && ld >= V, LAFF_EINVAL, "laff_label_metrics: bad arguments");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 128;
+  label_metrics_kernel<<<(Q * 32 + threads - 1) / threads, threads, 0, st>>>(label, Q, V, ld, rank0, ap);
+  rank_metrics_kernel<<<1, 1024, 0, st>>>(rank0, Q, out8);
+  mean_double_kernel<<<1, 1024, 0, st>>>(ap, Q, out8 + 6);  // mAP over the per-query APs
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }

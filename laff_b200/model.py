@@ -1,0 +1,591 @@
+"""Drop-in modules for the reference's model-side hot path (model/model.py, model/Attention.py).
+
+Class names, constructor arguments, ``state_dict`` keys/shapes and forward signatures follow the reference so that
+``predictor.py`` / ``trainer.validate`` can use these classes with reference checkpoints
+(``load_state_dict(checkpoint['model'], strict=False)``, predictor.py:167); the arithmetic runs in the sm_100a kernels
+behind ``include/laff_b200.h``:
+
+  TransformNet                        model/model.py:211-276
+  Attention_1                         model/Attention.py:40-105
+  Multi_head_MyApply_Attention        model/Attention.py:473-552
+  VisMutiTransformNet                 model/model.py:1787-1827
+  VisMutiTransformNetAddAttnetion     model/model.py:1830-1881
+  MultiScaleTxtEncoderAttention       model/model.py:1641-1709   (text features are inputs at this tier)
+  VisMutiTransformNetPlusFrameFeat    model/model.py:2101-2194
+  W2VVPP_MultiHeadAttention ('LAFF'), W2VVPP_MutiVisFrameFeat ('FrameLAFF'), get_model   model/model.py:2501-2519
+
+Scope: inference (``eval()``) forward, similarity, ranking, and the margin-ranking loss with its gradient w.r.t. the
+embeddings.  Train-mode forward of the fusion nets (dropout, batch-statistics BN, backward through the projections)
+is the "next" row N4 of SURVEY §8(f) and raises NotImplementedError instead of silently running another path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from . import loss as _loss
+from .loss import MarginRankingLoss, MarginRankingLossWithScore
+
+_ROW_CHUNK = 32768  # rows fused per pass: bounds the projected-feature scratch to L * 512 MB
+
+
+def _cuda_device(hint: Optional[torch.device] = None) -> torch.device:
+    if hint is not None and hint.type == "cuda":
+        return hint
+    if not torch.cuda.is_available():
+        raise ops.LaffError("laff_b200 needs a CUDA (sm_100) device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _op_dtype(precision: str) -> torch.dtype:
+    return torch.float16 if precision == "fp16" else torch.bfloat16
+
+
+def _initialize_weights(m):
+    """model/model.py:51-60."""
+    if type(m) == nn.Linear:
+        nn.init.xavier_uniform_(m.weight)
+        if m.bias is not None:
+            nn.init.zeros_(m.bias)
+    elif type(m) == nn.BatchNorm1d:
+        nn.init.ones_(m.weight)
+        nn.init.zeros_(m.bias)
+
+
+class TransformNet(nn.Module):
+    """fc_layers = (dim_in, dim_out): FC -> activation -> dropout -> BatchNorm, each optional (model/model.py:211-276)."""
+
+    def __init__(self, fc_layers, opt=None, dropout=None, batch_norm=None, activation=None, fc=True):
+        super().__init__()
+        if opt is not None:
+            if batch_norm is None:
+                batch_norm = opt.batch_norm
+            if activation is None:
+                activation = opt.activation
+            if dropout is None:
+                dropout = opt.dropout
+        self.fc1 = nn.Linear(fc_layers[0], fc_layers[1]) if fc else None
+        self.bn1 = nn.BatchNorm1d(fc_layers[1]) if batch_norm else None
+        self.activation_name = activation if activation in ("tanh", "relu", "sigmoid") else None
+        self.dropout_p = dropout if (dropout is not None and dropout > 1e-3) else None
+        self.out_dim = fc_layers[1]
+        self._cache = {}
+        self.apply(_initialize_weights)
+
+    # -- prepared (16-bit / folded) parameters, rebuilt when the parameters change -----------------------------
+    def _version(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def prepared(self, precision: str):
+        key = (precision, self._version())
+        if self._cache.get("key") != key:
+            c = {"key": key}
+            if self.fc1 is not None:
+                w = self.fc1.weight.detach()
+                if precision == "bf16x3":
+                    c["w16"] = ops.split3_16(w, 1, torch.bfloat16)
+                else:
+                    c["w16"] = ops.cast_pad_16(w, _op_dtype(precision))
+                c["bias"] = self.fc1.bias.detach().float().contiguous()
+            if self.bn1 is not None:
+                c["bn_scale"], c["bn_shift"] = ops.bn_fold(self.bn1.weight, self.bn1.bias, self.bn1.running_mean,
+                                                           self.bn1.running_var, self.bn1.eps)
+            self._cache = c
+        return self._cache
+
+    def project(self, x: torch.Tensor, precision: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """y = BN(act(x W^T + b)) for an fc feature; x fp32 [rows, d_in] on the device."""
+        c = self.prepared(precision)
+        if precision == "bf16x3":
+            x16 = ops.split3_16(x, 0, torch.bfloat16)
+        else:
+            x16 = ops.cast_pad_16(x, _op_dtype(precision))
+        return ops.project(x16, c["w16"], c["bias"], self.activation_name, c.get("bn_scale"), c.get("bn_shift"), out=out)
+
+    def forward(self, input_x):
+        if self.training and (self.dropout_p is not None or self.bn1 is not None):
+            raise NotImplementedError("laff_b200.TransformNet: train-mode forward (dropout / batch-stat BN) is not part "
+                                      "of the hot path built so far (SURVEY §8f N4); call .eval()")
+        x = input_x.to(_cuda_device(self._param_device()), non_blocking=True).float()
+        precision = _loss.get_precision()
+        if self.fc1 is not None:
+            return self.project(x, precision)
+        if self.bn1 is not None:
+            c = self.prepared(precision)
+            return x * c["bn_scale"] + c["bn_shift"]
+        return x
+
+    def _param_device(self):
+        for p in self.parameters():
+            return p.device
+        return None
+
+
+class Attention_1(nn.Module):
+    """The LAFF block (model/Attention.py:40-105): logits Linear(d -> 1), softmax over the L features, weighted sum
+    (+ omega * mean-pool when with_ave), L2 normalise."""
+
+    def __init__(self, embed_dim, with_ave=True, mul=False):
+        super().__init__()
+        self.with_ave = with_ave
+        self.mul = mul
+        self.embed_dim = embed_dim
+        self.embedding_common = nn.Sequential(nn.Linear(embed_dim, 1))
+        self.weights = 0
+        self.global_emb_weight_net = nn.Linear(1, 1, False)
+        self.change_raw_global_emb_weight(1)
+
+    def get_raw_global_emb_weight(self):
+        return self.global_emb_weight_net.weight.item()
+
+    def change_raw_global_emb_weight(self, new_value: float):
+        self.global_emb_weight_net.weight.data.fill_(new_value)
+
+    def get_attention_weight(self):
+        return torch.as_tensor(self.weights).clone().detach().cpu()
+
+    def forward(self, local_embs: torch.Tensor, raw_global_emb=None):
+        if raw_global_emb is not None:
+            raise NotImplementedError("Attention_1 with an external raw_global_emb is not used by the LAFF configs")
+        local_embs = local_embs.to(_cuda_device(self.embedding_common[0].weight.device)).float().contiguous()
+        B, L, d = local_embs.shape
+        srcs = [{"y": local_embs[:, l, :]} for l in range(L)]
+        lin = self.embedding_common[0]
+        out, _, att = ops.attention_pool(srcs, lin.weight.view(1, d), lin.bias.view(1), 1, d, self.with_ave, self.mul,
+                                         omega=float(self.global_emb_weight_net.weight.item()) if self.with_ave else 0.0,
+                                         want_att=True)
+        self.weights = att.view(B, L)
+        return out.view(B, d)
+
+
+class Multi_head_MyApply_Attention(nn.Module):
+    """H independent LAFF blocks on the H slices of the common space (model/Attention.py:473-552)."""
+
+    def __init__(self, embed_dim, multi_heads=None, dim_per_head=None, with_ave=True, mul=True, split_head=True,
+                 l2norm_each_head=False):
+        super().__init__()
+        if embed_dim is None:
+            return
+        if not split_head:
+            raise NotImplementedError("split_head=False (every head sees the full vector) is not used by the LAFF configs")
+        if l2norm_each_head:
+            raise NotImplementedError("l2norm_each_head is off in every shipped config (base_config.py:125)")
+        assert dim_per_head == embed_dim // multi_heads
+        self.dim_per_head = dim_per_head
+        self.multi_heads = multi_heads
+        self.split_head = split_head
+        self.with_ave, self.mul = with_ave, mul
+        self.attention_layer = nn.Sequential()
+        for i in range(multi_heads):
+            self.attention_layer.add_module(str(i), Attention_1(dim_per_head, with_ave=with_ave, mul=mul))
+        self.layer_norm = nn.LayerNorm(dim_per_head)  # present in the reference state_dict, unused in forward
+        self.l2norm_each_head = l2norm_each_head
+        self._cache = {}
+
+    def head_params(self):
+        ps = [self.attention_layer[h].embedding_common[0] for h in range(self.multi_heads)]
+        key = tuple((p.weight.data_ptr(), p.weight._version, p.bias._version) for p in ps)
+        if self._cache.get("key") != key:
+            w = torch.cat([p.weight.detach().view(1, -1) for p in ps], 0).float().contiguous()
+            b = torch.cat([p.bias.detach().view(1) for p in ps], 0).float().contiguous()
+            self._cache = {"key": key, "w": w, "b": b}
+        return self._cache["w"], self._cache["b"]
+
+    def pool(self, sources: Sequence[dict], out16_dtype=None, want_att=False):
+        w, b = self.head_params()
+        omega = float(self.attention_layer[0].global_emb_weight_net.weight.item()) if self.with_ave else 0.0
+        out, out16, att = ops.attention_pool(sources, w, b, self.multi_heads, self.dim_per_head, self.with_ave, self.mul,
+                                             omega=omega, out16_dtype=out16_dtype, want_att=want_att)
+        if want_att:
+            for h in range(self.multi_heads):
+                self.attention_layer[h].weights = att[:, h, :]
+        return out, out16
+
+    def forward(self, local_embs, raw_global_emb=None, attn_mask=None):
+        local_embs = local_embs.to(_cuda_device(self.layer_norm.weight.device)).float().contiguous()
+        L = local_embs.shape[1]
+        out, _ = self.pool([{"y": local_embs[:, l, :]} for l in range(L)], want_att=True)
+        return out
+
+    def get_raw_global_emb_weight(self):
+        return self.attention_layer[0].global_emb_weight_net.weight.item()
+
+    def change_raw_global_emb_weight(self, new_value: float):
+        for i in range(self.multi_heads):
+            self.attention_layer[i].global_emb_weight_net.weight.data.fill_(new_value)
+
+    def get_attention_weight(self, head=0):
+        return self.attention_layer[head].get_attention_weight().detach()
+
+
+def get_attention_layer(attention_type: str, common_space_dim, encoder_num, opt):
+    """model/model.py:95-208, restricted to the variants the LAFF / LAFF-ml scripts select."""
+    if attention_type == "Multi_head_MyApply_Attention":
+        return Multi_head_MyApply_Attention(
+            common_space_dim, opt.multi_head_attention["heads"], common_space_dim // opt.multi_head_attention["heads"],
+            with_ave=opt.attention_param_each_head["with_ave"], mul=opt.attention_param_each_head["mul"],
+            split_head=opt.attention_param_each_head["split_head"], l2norm_each_head=getattr(opt, "attention_l2norm", False))
+    table = {"attention_noAverageMul_Ave": (True, False), "attention_noAveNoAverageMul": (False, False),
+             "attention_averageMul": (True, True), "average_AverageMul_noAve": (False, True)}
+    if attention_type in table:
+        a, m = table[attention_type]
+        return Attention_1(common_space_dim, with_ave=a, mul=m)
+    raise NotImplementedError("attention type %r is an ablation variant outside the LAFF hot path" % attention_type)
+
+
+def _fuse(features: Sequence, attention: Multi_head_MyApply_Attention, device, precision, out16_dtype=None,
+          want_att=True):
+    """features: list of (x fp32 [B, d] device tensor, TransformNet). Projection GEMMs + LAFF pooling, chunked by rows."""
+    B = features[0][0].shape[0]
+    D = attention.multi_heads * attention.dim_per_head
+    outs, outs16 = [], []
+    scratch: Dict[int, torch.Tensor] = {}
+    for s in range(0, max(B, 1), _ROW_CHUNK):
+        e = min(B, s + _ROW_CHUNK)
+        srcs = []
+        for i, (x, tn) in enumerate(features):
+            xs = x[s:e]
+            if tn.fc1 is not None:
+                buf = scratch.get(i)
+                if buf is None or buf.shape[0] < e - s:
+                    buf = torch.empty((min(_ROW_CHUNK, B), D), dtype=torch.float32, device=device)
+                    scratch[i] = buf
+                srcs.append({"y": tn.project(xs, precision, out=buf[: e - s])})
+            else:
+                c = tn.prepared(precision)
+                srcs.append({"x": xs, "bn_scale": c.get("bn_scale"), "bn_shift": c.get("bn_shift")})
+        o, o16 = attention.pool(srcs, out16_dtype=out16_dtype, want_att=want_att and B <= _ROW_CHUNK)
+        outs.append(o)
+        outs16.append(o16)
+    out = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+    out16 = None if out16_dtype is None else (outs16[0] if len(outs16) == 1 else torch.cat(outs16, 0))
+    return out, out16
+
+
+class VisMutiTransformNet(nn.Module):
+    """dict of video features -> dict of features in the common space (model/model.py:1787-1827)."""
+
+    def __init__(self, opt, space_dict: dict):
+        super().__init__()
+        if opt is None:
+            return
+        self.opt = opt
+        self.vis_net_space_dict = space_dict
+        self.common_space_dim = opt.vis_fc_layers[1]
+        for each in space_dict.keys():
+            if each not in opt.vis_no_transform:
+                self.add_module(each, TransformNet((space_dict[each], opt.vis_fc_layers[1]), opt))
+            else:
+                self.add_module(each, TransformNet((space_dict[each], opt.vis_fc_layers[1]), None, dropout=None,
+                                                   batch_norm=True, activation=False, fc=False))
+
+    def forward(self, vis_input, txt_emb=None, vis_frame_feat_dict_input=None):
+        out = {}
+        mods = dict(self.named_children())
+        heads = self.opt.multi_head_attention["heads"]
+        for name in self.vis_net_space_dict.keys():
+            x = vis_input[name]
+            if name in self.opt.vis_no_transform:
+                x = x.repeat(1, heads)
+            out[name] = mods[name](x)
+        return out
+
+
+class VisMutiTransformNetAddAttnetion(nn.Module):
+    """dict of video features -> [B, H, d_h] multi-space embedding (model/model.py:1830-1881)."""
+
+    def __init__(self, opt, space_dict: dict):
+        super().__init__()
+        if opt is None:
+            return
+        if getattr(opt, "vis_expert_embedding", {"expert": False}).get("expert") or \
+                getattr(opt, "vis_expert_embedding", {"l2norm": False}).get("l2norm"):
+            raise NotImplementedError("expert embeddings are off in the shipped configs (base_config.py:158)")
+        self.opt = opt
+        self.vis_net_space_dict = space_dict
+        self.common_space_dim = opt.vis_fc_layers[1]
+        self.VisMutiTransformNet = VisMutiTransformNet(opt, space_dict)
+        self.attention_layer = get_attention_layer(opt.vis_attention, self.common_space_dim, len(space_dict), opt)
+        self.expert_embedding = None
+
+    def encode(self, vis_input, out16_dtype=None, precision=None):
+        precision = precision or _loss.get_precision()
+        dev = _cuda_device(self.attention_layer.layer_norm.weight.device)
+        if self.training:
+            raise NotImplementedError("train-mode forward of the fusion net is SURVEY §8f N4; call .eval()")
+        mods = dict(self.VisMutiTransformNet.named_children())
+        feats = [(vis_input[name].to(dev, non_blocking=True).float(), mods[name]) for name in self.vis_net_space_dict.keys()]
+        return _fuse(feats, self.attention_layer, dev, precision, out16_dtype)
+
+    def forward(self, vis_input, txt_emb=None, vis_frame_feat_dict_input=None):
+        return self.encode(vis_input)[0]
+
+    def get_attention_weight(self, vis_input, txt_emb=None):
+        self.forward(vis_input, txt_emb)
+        return self.attention_layer.get_attention_weight()
+
+
+# reference encoder name -> (feature key accepted in caption_feat_dict, alternatives)
+_TXT_ENCODERS = (("rnn_encoder", ("gru", "rnn_encoder")), ("bow_encoder", ("bow", "bow_encoder")),
+                 ("w2v_encoder", ("w2v", "w2v_encoder")), ("CLIP_encoder", ("clip", "CLIP_encoding", "CLIP_encoder")))
+
+
+class MultiScaleTxtEncoderAttention(nn.Module):
+    """Per-encoder text features -> [B, H, d_h] (model/model.py:1641-1709, init_transform :622-681).
+
+    At this tier the encoder outputs are inputs: ``caption_feat_dict`` carries 'gru' [B, rnn_size], 'bow' [B, |V|],
+    'w2v' [B, 500] and 'clip' / 'CLIP_encoding' [B, 512] tensors (the reference reads CLIP text features precomputed
+    when frozen, model/model.py:497-498).  Encoder order = the reference's encoder_name_list (rnn, bow, w2v, CLIP).
+    """
+
+    def __init__(self, opt):
+        super().__init__()
+        if getattr(opt, "txt_expert_embedding", {"expert": False}).get("expert") or \
+                getattr(opt, "txt_expert_embedding", {"l2norm": False}).get("l2norm"):
+            raise NotImplementedError("expert embeddings are off in the shipped configs")
+        self.opt = opt
+        te = opt.text_encoding
+        D = opt.txt_fc_layers[1]
+        self.space_dict = {}
+        if te["rnn_encoding"]["name"].split("_", 1)[0] == "gru":
+            self.space_dict["rnn_encoder"] = opt.rnn_size
+        elif te["rnn_encoding"]["name"].split("_", 1)[0] == "bigru":
+            self.space_dict["rnn_encoder"] = opt.rnn_size * 2
+        if "no" not in te["bow_encoding"]["name"]:
+            self.space_dict["bow_encoder"] = opt.t2v_bow.ndims
+        if "no" not in te["w2v_encoding"]["name"]:
+            self.space_dict["w2v_encoder"] = opt.t2v_w2v.ndims
+        if "no" not in te["CLIP_encoding"]["name"]:
+            self.space_dict["CLIP_encoder"] = opt.clip_opt["size"]
+        self.encoder_name_list = [n for n, _ in _TXT_ENCODERS if n in self.space_dict]
+        self.txt_encoder_num = len(self.encoder_name_list)
+        self.transform_layer = nn.Module()
+        # registration order follows init_transform (rnn, w2v, bow, CLIP) so that state_dict() order matches
+        for name in ("rnn_encoder", "w2v_encoder", "bow_encoder", "CLIP_encoder"):
+            if name not in self.space_dict:
+                continue
+            if name == "CLIP_encoder":
+                co = opt.clip_opt
+                if "CLIP_encoder" in opt.txt_no_transform:
+                    tn = TransformNet((co["size"], D), None, co["transform_dropout"], co["transform_batch_norm"], False, False)
+                else:
+                    tn = TransformNet((co["size"], D), None, co["transform_dropout"], co["transform_batch_norm"],
+                                      co["transform_activation"])
+            else:
+                tn = TransformNet((self.space_dict[name], D), None, opt.dropout, opt.batch_norm, opt.activation)
+            self.transform_layer.add_module(name + "_transform", tn)
+        self.attention_layer = get_attention_layer(opt.txt_attention, D, self.txt_encoder_num, opt)
+
+    def _feature(self, caption_feat_dict, enc):
+        for key in dict(_TXT_ENCODERS)[enc]:
+            if key in caption_feat_dict:
+                return caption_feat_dict[key]
+        raise KeyError("caption_feat_dict has no feature for %s (expected one of %s)" % (enc, dict(_TXT_ENCODERS)[enc]))
+
+    def encode(self, caption_feat_dict, out16_dtype=None, precision=None):
+        precision = precision or _loss.get_precision()
+        dev = _cuda_device(self.attention_layer.layer_norm.weight.device)
+        if self.training:
+            raise NotImplementedError("train-mode forward of the fusion net is SURVEY §8f N4; call .eval()")
+        mods = dict(self.transform_layer.named_children())
+        feats = [(self._feature(caption_feat_dict, n).to(dev, non_blocking=True).float(), mods[n + "_transform"])
+                 for n in self.encoder_name_list]
+        return _fuse(feats, self.attention_layer, dev, precision, out16_dtype)
+
+    def forward(self, caption_feat_dict, visual_emb=None, task3=False):
+        return self.encode(caption_feat_dict)[0]
+
+    def get_attention_weight(self, caption_feat_dict, visual_emb=None):
+        self.forward(caption_feat_dict, visual_emb)
+        return self.attention_layer.get_attention_weight()
+
+
+class VisMutiTransformNetPlusFrameFeat(nn.Module):
+    """LAFF-ml video side: frame-level LAFF per video, then LAFF over [video-level features..., pooled frame feature]
+    (model/model.py:2101-2194)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        space_dict = opt.vis_fc_layers[0]
+        self.vis_net_space_dict = space_dict
+        for each in space_dict.keys():
+            if each not in opt.vis_no_transform:
+                self.add_module(each, TransformNet((space_dict[each], opt.vis_fc_layers[1]), opt))
+            else:
+                self.add_module(each, TransformNet((space_dict[each], opt.vis_fc_layers[1]), None, dropout=None,
+                                                   batch_norm=True, activation=False, fc=False))
+        self.vis_attention_layer = get_attention_layer(opt.vis_attention, opt.vis_fc_layers[1], len(space_dict), opt)
+        self.frame_attention = nn.ModuleDict()
+        for each in opt.vid_frame_feats:
+            if opt.vis_frame_addFC:
+                raise NotImplementedError("vis_frame_addFC=True is not used by the LAFF-ml script (FrameLaff...:58)")
+            self.frame_attention[each] = nn.Sequential(
+                get_attention_layer(opt.vis_frame_attention, opt.vis_fc_layers[0][each], 1, opt))
+
+    def frame_pool(self, feat_name, frames: torch.Tensor) -> torch.Tensor:
+        att: Attention_1 = self.frame_attention[feat_name][0]
+        lin = att.embedding_common[0]
+        return ops.frame_pool(frames, lin.weight, float(lin.bias.item()), att.with_ave, att.mul,
+                              omega=float(att.global_emb_weight_net.weight.item()) if att.with_ave else 0.0)
+
+    def encode(self, vis_input, vis_frame_feat_dict_input, out16_dtype=None, precision=None):
+        precision = precision or _loss.get_precision()
+        dev = _cuda_device(self.vis_attention_layer.layer_norm.weight.device)
+        if self.training:
+            raise NotImplementedError("train-mode forward of the fusion net is SURVEY §8f N4; call .eval()")
+        feats_in = dict(vis_input) if self.opt.frame_feat_with_video_feat else {}
+        for feat_name, fr in vis_frame_feat_dict_input.items():
+            if feat_name == "mask_tensor":
+                continue  # the reference's mask slice is a no-op: zero-padded frames take part
+            feats_in[feat_name] = self.frame_pool(feat_name, fr.to(dev, non_blocking=True).float())
+        mods = dict(self.named_children())
+        feats = [(x.to(dev, non_blocking=True).float(), mods[name]) for name, x in feats_in.items()]
+        return _fuse(feats, self.vis_attention_layer, dev, precision, out16_dtype)
+
+    def forward(self, vis_input, vis_frame_feat_dict_input, txt_emb=None):
+        return self.encode(vis_input, vis_frame_feat_dict_input)[0]
+
+
+class W2VVPP(nn.Module):
+    """Shared model surface (model/model.py:751-1128): similarity, loss, predict."""
+
+    def _init_vis_net(self, opt):
+        raise NotImplementedError
+
+    def _init_txt_net(self, opt):
+        self.txt_net = MultiScaleTxtEncoderAttention(opt)
+
+    def __init__(self, opt):
+        super().__init__()
+        if opt is None:
+            return
+        self._init_vis_net(opt)
+        self._init_txt_net(opt)
+        self.opt = opt
+        self.grad_clip = getattr(opt, "grad_clip", 2)
+        if getattr(opt, "loss", "mrl") != "mrl":
+            raise NotImplementedError("loss %r is outside the LAFF hot path (shipped configs use 'mrl')" % opt.loss)
+        self.criterion = MarginRankingLoss(margin=opt.margin, measure=opt.measure, max_violation=opt.max_violation,
+                                           cost_style=opt.cost_style, direction=opt.direction)
+        self.criterion_with_score = MarginRankingLossWithScore(margin=opt.margin, max_violation=opt.max_violation,
+                                                               cost_style=opt.cost_style, direction=opt.direction)
+        self.iters = 0
+
+    # ---------------------------------------------------------------- similarity (model/model.py:1003-1016, 1567-1578)
+    @staticmethod
+    def compute_sim(query_embs, retro_embs, measure="cosine", device=None):
+        if measure == "cosine":
+            return _loss.cosine_sim(query_embs, retro_embs)
+        elif measure == "hist":
+            raise Exception("measure 'hist' is outside the LAFF hot path")
+        elif measure == "euclidean":
+            raise Exception("Not implemented")
+        else:
+            raise Exception("%s is invalid" % measure)
+
+    def get_txt2vis_matrix(self, txt_embs, vis_embs, measure="cosine"):
+        if txt_embs.dim() == vis_embs.dim() == 2:
+            return self.compute_sim(txt_embs, vis_embs, measure)
+        if measure != "cosine":
+            self.compute_sim(txt_embs[:, 0, :], vis_embs[:, 0, :], measure)  # raises like the reference
+        H = vis_embs.shape[1]
+        q16, g16 = _loss._operands(txt_embs.reshape(txt_embs.shape[0], -1), vis_embs.reshape(vis_embs.shape[0], -1), H,
+                                   _loss.get_precision())
+        return ops.sim_dense(q16, g16, 1.0 / H)  # mean over heads of the per-head cosine
+
+    # ---------------------------------------------------------------- loss (model/model.py:840-865, 2032-2048)
+    def compute_loss(self, vis_embs, txt_embs, vis_embs_multi_labels=0, txt_embs_multi_labels=0, labels_embs=0):
+        if vis_embs.dim() == txt_embs.dim() == 2 or vis_embs.dim() == txt_embs.dim() == 3:
+            loss = self.criterion(txt_embs, vis_embs)  # 3-D: the kernel sums over heads
+            return loss, {"triplet_loss": loss}
+        raise Exception("vis_embs dims are not equal to txt_embs dims")
+
+    def forward(self, train_data, epoch=None):
+        raise NotImplementedError("the full training step (backward through the fusion nets, optimizer) is SURVEY "
+                                  "§8f N4; the loss and its embedding gradients are available via compute_loss")
+
+    # ---------------------------------------------------------------- predict (model/model.py:1018-1079)
+    def _encode_vis(self, output_dict, out16_dtype=None):
+        return self.vis_net.encode(output_dict["vis_feat_dict"], out16_dtype)
+
+    def predict(self, txt_loader, vis_loader, measure, record_emb=False):
+        """Dense score matrix for small galleries; same return contract as the reference:
+        (scores ndarray [Q, V] float32, txt_ids, vis_ids).  Video embeddings stay on the device (the reference parks
+        them on the host and re-uploads them per text batch, model/model.py:1047, :1066)."""
+        self.eval()
+        if measure != "cosine":
+            self.compute_sim(None, None, measure)
+        precision = _loss.get_precision()
+        dt = _op_dtype(precision)
+        H = self.opt.multi_head_attention["heads"]
+        with torch.no_grad():
+            if not record_emb or getattr(self, "video_all_embs", None) is None:
+                embs, self.video_idxs_list, self.vis_ids = [], [], []
+                for output_dict in vis_loader:
+                    self.video_idxs_list.append(output_dict["idxs"])
+                    embs.append(self._encode_vis(output_dict)[0])
+                    self.vis_ids.extend(output_dict["vis_ids"])
+                self.video_all_embs = torch.cat(embs, 0)
+            V = self.video_all_embs.shape[0]
+            order = torch.as_tensor(np.concatenate([np.asarray(i) for i in self.video_idxs_list]), device=self.video_all_embs.device)
+            gal = torch.empty_like(self.video_all_embs)
+            gal[order] = self.video_all_embs  # column j of the score matrix = dataset index j (model/model.py:1071)
+            _, g16 = _loss._operands(gal[:1].reshape(1, -1), gal.reshape(V, -1), H, precision)
+            txt_ids, rows = [], []
+            for caption_feat_dict, txt_idxs, batch_txt_ids in txt_loader:
+                t = self.txt_net(caption_feat_dict)
+                q16, _ = _loss._operands(t.reshape(t.shape[0], -1), gal[:1].reshape(1, -1), H, precision)
+                rows.append(ops.sim_dense(q16, g16, 1.0 / H))
+                txt_ids.extend(batch_txt_ids)
+            scores = torch.cat(rows, 0)
+        return scores.cpu().numpy(), txt_ids, self.vis_ids
+
+
+class W2VVPP_MultiHeadAttention(W2VVPP):
+    """'LAFF' (model/model.py:1930-2048)."""
+
+    def _init_vis_net(self, opt):
+        self.vis_net = VisMutiTransformNetAddAttnetion(opt, opt.vis_fc_layers[0])
+
+    def compute_loss(self, vis_embs, txt_embs, vis_embs_multi_labels=0, txt_embs_multi_labels=0, labels_embs=0):
+        if getattr(self.opt, "multi_space", True) and vis_embs.dim() == txt_embs.dim() == 3:
+            loss = self.criterion(txt_embs, vis_embs)
+        else:
+            scores = self.get_txt2vis_matrix(txt_embs, vis_embs, self.opt.measure)  # rows = sentences (model/model.py:2041)
+            loss = self.criterion_with_score(scores)
+        return loss, {"triplet_loss": loss}
+
+    def change_raw_global_emb_weight(self):
+        """Linear decay of the mean-pool residual weight per epoch (model/model.py:1919-1946)."""
+        for net, rate in ((self.txt_net, self.opt.txt_attention_global_decay_rate),
+                          (self.vis_net, self.opt.vis_attention_global_decay_rate)):
+            att = getattr(net, "attention_layer", None)
+            if att is not None and hasattr(att, "get_raw_global_emb_weight"):
+                att.change_raw_global_emb_weight(max(0.0, rate - 1 + att.get_raw_global_emb_weight()))
+
+
+class W2VVPP_MutiVisFrameFeat(W2VVPP):
+    """'FrameLAFF' / LAFF-ml (model/model.py:2196-2259)."""
+
+    def _init_vis_net(self, opt):
+        self.vis_net = VisMutiTransformNetPlusFrameFeat(opt)
+
+    def _encode_vis(self, output_dict, out16_dtype=None):
+        return self.vis_net.encode(output_dict["vis_feat_dict"], output_dict["vis_frame_feat_dict"], out16_dtype)
+
+
+NAME_TO_MODELS = {"LAFF": W2VVPP_MultiHeadAttention, "FrameLAFF": W2VVPP_MutiVisFrameFeat}
+
+
+def get_model(name, device_, config):
+    """model/model.py:2501-2519 for the two LAFF model names."""
+    assert name in NAME_TO_MODELS, "%s not supported." % name
+    dev = torch.device(device_)
+    if dev.type != "cuda":
+        raise ops.LaffError("laff_b200 models run on a CUDA (sm_100) device only; got %s" % dev)
+    return NAME_TO_MODELS[name](config).float().to(dev)

@@ -1,0 +1,109 @@
+"""Gallery-sharded retrieval: fused similarity + exact rank + top-k + metrics, one process per GPU.
+
+Replaces the reference's evaluation pipeline for large galleries — ``W2VVPP.predict`` building a dense host score
+matrix (model/model.py:1018-1079), ``np.argsort`` over every row (predictor.py:232), the per-query ground-truth search
+(predictor.py:239-244) and ``evaluation.eval`` (evaluation.py:92-109) — with one tensor-core sweep per gallery shard
+that never materialises the Q x V matrix.
+
+Sharding: rank r of W holds gallery rows [r*ceil(V/W), ...) as 16-bit unit-norm embeddings; queries are
+replicated.  Exchange steps, all tiny, over torch.distributed (NCCL on GPUs; gloo in the CPU tests):
+  1. all_reduce(sum) of s_gt[Q]          (each ground truth is owned by exactly one shard, others contribute 0)
+  2. all_reduce(sum) of count[Q] int32   -> exact global rank0
+  3. all_gather of the per-shard ordered top-k lists + a k-way merge under the tie rule (global indices).
+With one process (W = 1) no collective is issued.
+
+The local compute is delegated to a backend object; the product backend is :class:`CudaBackend` (the sm_100a
+kernels).  Tests inject a numpy backend to exercise the sharding / collective logic on CPU with gloo.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def shard_bounds(V: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range of the gallery held by `rank` (the last shards may be short or empty)."""
+    per = (V + world_size - 1) // world_size
+    lo = min(V, rank * per)
+    return lo, min(V, lo + per)
+
+
+class CudaBackend:
+    """Local shard compute on the B200 through the C ABI (no fallback)."""
+
+    def gt_scores(self, q16, g16, gt_local):
+        return ops.sim_gt_scores(q16, g16, gt_local)
+
+    def rank_topk(self, q16, g16, sgt_raw, gt_global, k, scale, col_offset, workspace=None):
+        return ops.sim_rank_topk(q16, g16, sgt_raw, gt_global, k, scale=scale, col_offset=col_offset, workspace=workspace)
+
+    def merge(self, vals, idx, k):
+        return ops.topk_merge(vals, idx, k)
+
+    def metrics(self, rank0):
+        return ops.rank_metrics(rank0)
+
+
+@dataclass
+class SearchResult:
+    rank0: torch.Tensor      # int32 [Q]  0-based rank of the ground truth over the whole gallery
+    topk_val: torch.Tensor   # fp32 [Q, k] scores (mean over heads of the per-head cosine)
+    topk_idx: torch.Tensor   # int32 [Q, k] global gallery indices, ordered by (score desc, index desc)
+    metrics: torch.Tensor    # float64 [8]: R@1, R@5, R@10, MedR, MeanR, MIR, mAP, Q
+
+
+class GalleryIndex:
+    """The local shard of a gallery of fused video embeddings, resident in HBM (the reference's record_emb=True cache,
+    model/model.py:1026-1034, kept on the device and in the tensor-core operand type)."""
+
+    def __init__(self, shard16: torch.Tensor, total: int, heads: int, rank: int = 0, world_size: int = 1,
+                 group=None, backend=None):
+        lo, hi = shard_bounds(total, world_size, rank)
+        if shard16.shape[0] != hi - lo:
+            raise ValueError("shard has %d rows, expected %d for rank %d/%d of a %d-row gallery"
+                             % (shard16.shape[0], hi - lo, rank, world_size, total))
+        self.g16 = shard16
+        self.total, self.heads = total, heads
+        self.rank, self.world_size, self.group = rank, world_size, group
+        self.lo, self.hi = lo, hi
+        self.backend = backend or CudaBackend()
+        self._ws = None
+
+    def _all_reduce(self, t):
+        if self.world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def search(self, q16: torch.Tensor, gt_global: torch.Tensor, k: int = 10) -> SearchResult:
+        """q16 [Q, H*d_h] 16-bit unit-norm query embeddings (replicated on every rank), gt_global int [Q]."""
+        be = self.backend
+        scale = 1.0 / self.heads
+        gt_global = gt_global.to(torch.int32)
+        n_local = self.hi - self.lo
+        owned = (gt_global >= self.lo) & (gt_global < self.hi)
+        gt_local = torch.where(owned, gt_global - self.lo, torch.full_like(gt_global, -1))
+        if n_local > 0:
+            sgt = be.gt_scores(q16, self.g16, gt_local)
+        else:
+            sgt = torch.zeros(q16.shape[0], dtype=torch.float32, device=q16.device)
+        sgt = self._all_reduce(sgt)
+        if n_local > 0:
+            count, tv, ti = be.rank_topk(q16, self.g16, sgt, gt_global, k, scale, self.lo, self._ws)
+        else:
+            Q = q16.shape[0]
+            count = torch.zeros(Q, dtype=torch.int32, device=q16.device)
+            tv = torch.full((Q, k), float("-inf"), dtype=torch.float32, device=q16.device)
+            ti = torch.full((Q, k), -1, dtype=torch.int32, device=q16.device)
+        count = self._all_reduce(count)
+        if self.world_size > 1 and k > 0:
+            vals = [torch.empty_like(tv) for _ in range(self.world_size)]
+            idxs = [torch.empty_like(ti) for _ in range(self.world_size)]
+            dist.all_gather(vals, tv.contiguous(), group=self.group)
+            dist.all_gather(idxs, ti.contiguous(), group=self.group)
+            tv, ti = be.merge(torch.stack(vals, 0), torch.stack(idxs, 0), k)
+        return SearchResult(count, tv, ti, be.metrics(count))

@@ -1,0 +1,418 @@
+"""CPU oracle for the LAFF retrieval hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A plain numpy restatement of the reference's algorithm (ruc-aimc-lab/LAFF), function by function, each citing the
+reference file:line it follows.  Only ``tests/``, ``__graft_entry__.smoke()`` and the CPU-baseline / ``--impl
+reference`` legs of ``bench.py`` may import this module; the product path (``laff_b200``) never does and fails loudly
+when its CUDA library is missing.
+
+Pinning: the reference ships no golden vectors or known-answer tests, so this oracle is pinned against
+outputs of the reference itself, generated in the build container by ``tests/golden/make_golden.py`` (which imports
+the unmodified reference from /root/reference) and committed as ``tests/golden/*.npz``; ``tests/test_oracle_golden.py``
+checks every function here against them.
+
+The arithmetic lives in third-party code the reference calls (PyTorch/ATen ``nn.Linear``, ``mm``, ``softmax``,
+``BatchNorm1d``; numpy ``argsort``/``median``; reference pins torch 1.7.1 / numpy 1.20.1, requirements.txt:1-5); the
+formulas below are those libraries' published semantics in float32 (pass ``dtype=np.float64`` for a high-precision
+variant used to bound rounding noise).
+"""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List, Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+
+F32 = np.float32
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# normalisation and similarity
+# ----------------------------------------------------------------------------------------------------------------
+def l2norm(X: np.ndarray, eps: float = 1e-13, axis: int = 1) -> np.ndarray:
+    """loss.py:8-13 — X / (sqrt(sum(X^2)) + eps + 1e-14); the additions happen in X's dtype like torch does."""
+    dt = X.dtype.type
+    norm = np.sqrt(np.sum(X * X, axis=axis, keepdims=True, dtype=X.dtype))
+    norm = norm + dt(eps)
+    norm = norm + dt(1e-14)
+    return X / norm
+
+
+def l2norm_np(X: np.ndarray) -> np.ndarray:
+    """evaluation.py:11-16 — X / (||X|| + 1e-10)."""
+    norm = np.linalg.norm(X, axis=1, keepdims=True)
+    return 1.0 * X / (norm + 1e-10)
+
+
+def cosine_sim(query: np.ndarray, retrio: np.ndarray) -> np.ndarray:
+    """loss.py:30-34 — l2norm both sides, then query @ retrio^T."""
+    return l2norm(query) @ l2norm(retrio).T
+
+
+def cosine_sim_np(query_embs: np.ndarray, retro_embs: np.ndarray) -> np.ndarray:
+    """evaluation.py:44-50."""
+    return l2norm_np(query_embs).dot(l2norm_np(retro_embs).T)
+
+
+def compute_sim(query_embs, retro_embs, measure: str = "cosine"):
+    """model/model.py:1567-1578 / evaluation.py:53-61 — only 'cosine' is used by the shipped configs."""
+    if measure == "cosine":
+        return cosine_sim(query_embs, retro_embs)
+    if measure in ("hist", "euclidean"):
+        raise Exception("Not implemented")
+    raise Exception("%s is invalid" % measure)
+
+
+def txt2vis_matrix(txt_embs: np.ndarray, vis_embs: np.ndarray) -> np.ndarray:
+    """model/model.py:1003-1016 — 2-D: cosine_sim; 3-D [N, H, d]: mean over heads of the per-head cosine_sim."""
+    if txt_embs.ndim == 2 and vis_embs.ndim == 2:
+        return cosine_sim(txt_embs, vis_embs)
+    H = vis_embs.shape[1]
+    sims = [cosine_sim(np.ascontiguousarray(txt_embs[:, h, :]), np.ascontiguousarray(vis_embs[:, h, :])) for h in range(H)]
+    return np.mean(np.stack(sims, 0), axis=0, dtype=sims[0].dtype)
+
+
+def mm_mean_heads(q_hat: np.ndarray, g_hat: np.ndarray, heads: int) -> np.ndarray:
+    """The `query.mm(retrio.t())` (loss.py:34) + mean over heads (model/model.py:1014) stage alone, on operands that
+    are already normalised and rounded to the tensor-core dtype: the stage the similarity GEMM replaces.  float64."""
+    return (q_hat.astype(np.float64) @ g_hat.astype(np.float64).T) / float(heads)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# projection + LAFF block
+# ----------------------------------------------------------------------------------------------------------------
+def activation_fn(x: np.ndarray, name) -> np.ndarray:
+    """model/model.py:234-241."""
+    if name == "tanh":
+        return np.tanh(x)
+    if name == "relu":
+        return np.maximum(x, 0)
+    if name == "sigmoid":
+        return 1.0 / (1.0 + np.exp(-x))
+    return x
+
+
+def batchnorm_eval(x, weight, bias, mean, var, eps=1e-5):
+    """nn.BatchNorm1d in eval mode (model/model.py:232, :273-274): (x - mean) / sqrt(var + eps) * weight + bias."""
+    dt = x.dtype.type
+    return (x - mean) / np.sqrt(var + dt(eps)) * weight + bias
+
+
+def transform_net(x: np.ndarray, sd: Mapping[str, np.ndarray], prefix: str, activation="tanh") -> np.ndarray:
+    """TransformNet.forward, eval mode (model/model.py:257-276): FC -> activation -> (dropout = id) -> BN.
+    A stage exists iff its parameters are in the state dict (fc1.* / bn1.*)."""
+    y = x
+    if prefix + "fc1.weight" in sd:
+        y = y @ sd[prefix + "fc1.weight"].T + sd[prefix + "fc1.bias"]
+        y = activation_fn(y, activation)
+    if prefix + "bn1.weight" in sd:
+        y = batchnorm_eval(y, sd[prefix + "bn1.weight"], sd[prefix + "bn1.bias"], sd[prefix + "bn1.running_mean"],
+                           sd[prefix + "bn1.running_var"])
+    return y
+
+
+def softmax(x: np.ndarray, axis: int) -> np.ndarray:
+    m = np.max(x, axis=axis, keepdims=True)
+    e = np.exp(x - m)
+    return e / np.sum(e, axis=axis, keepdims=True, dtype=x.dtype)
+
+
+def attention_1(local_embs: np.ndarray, w: np.ndarray, c, with_ave: bool, mul: bool, omega: float = 1.0):
+    """Attention_1.forward (model/Attention.py:78-105). local_embs [B, L, d]; w [d]; c scalar.
+    Returns (new_global [B, d] unit norm, weights [B, L] as stored in self.weights)."""
+    dt = local_embs.dtype.type
+    raw_global = np.mean(local_embs, axis=1, dtype=local_embs.dtype)              # :81
+    common = local_embs
+    if mul:
+        common = local_embs * raw_global[:, None, :]                              # :83-86
+    logits = common @ w + dt(c)                                                   # :88
+    weights = softmax(logits, axis=1)                                             # :89
+    new_global = weights[:, :, None] * local_embs                                 # :93
+    stored = weights
+    if with_ave:
+        stored = weights + dt(omega) * dt(1.0) / dt(weights.shape[1])             # :97
+        new_global = new_global + dt(omega) * raw_global[:, None, :]              # :99
+    new_global = np.sum(new_global, axis=1, dtype=local_embs.dtype)               # :101
+    return l2norm(new_global, eps=0), stored                                      # :103
+
+
+def multi_head_attention(local_embs: np.ndarray, sd: Mapping[str, np.ndarray], prefix: str, heads: int,
+                         with_ave: bool, mul: bool):
+    """Multi_head_MyApply_Attention.forward with split_head=True (model/Attention.py:508-531).
+    local_embs [B, L, D] -> ([B, H, D/H], weights [B, H, L])."""
+    B, L, D = local_embs.shape
+    dh = D // heads
+    x = local_embs.reshape(B, L, heads, dh)                                       # :517
+    outs, atts = [], []
+    for h in range(heads):                                                        # :525-527
+        p = "%sattention_layer.%d." % (prefix, h)
+        w = sd[p + "embedding_common.0.weight"].reshape(-1)
+        c = sd[p + "embedding_common.0.bias"].reshape(-1)[0]
+        omega = float(sd[p + "global_emb_weight_net.weight"].reshape(-1)[0])
+        o, a = attention_1(np.ascontiguousarray(x[:, :, h, :]), w, c, with_ave, mul, omega)
+        outs.append(o)
+        atts.append(a)
+    return np.stack(outs, 1), np.stack(atts, 1)                                   # :529
+
+
+def vis_net_forward(vis_input: Mapping[str, np.ndarray], sd: Mapping[str, np.ndarray], no_transform: Sequence[str],
+                    heads: int, with_ave=False, mul=False, activation="tanh"):
+    """VisMutiTransformNetAddAttnetion.forward -> VisMutiTransformNet.forward, eval (model/model.py:1858-1876,
+    :1807-1827): per-feature TransformNet (no-transform features tiled x heads, :1822-1823), stack in dict order
+    (:1862), multi-head LAFF."""
+    feats = []
+    for name, x in vis_input.items():
+        if name in no_transform:
+            x = np.tile(x, (1, heads))
+        feats.append(transform_net(x, sd, "VisMutiTransformNet.%s." % name, activation))
+    return multi_head_attention(np.stack(feats, 1), sd, "attention_layer.", heads, with_ave, mul)
+
+
+TXT_ENCODER_ORDER = ("rnn_encoder", "bow_encoder", "w2v_encoder", "CLIP_encoder")  # model/model.py:573-620
+TXT_FEATURE_KEY = {"rnn_encoder": "gru", "bow_encoder": "bow", "w2v_encoder": "w2v", "CLIP_encoder": "clip"}
+
+
+def txt_net_forward(txt_feats: Mapping[str, np.ndarray], sd: Mapping[str, np.ndarray], no_transform: Sequence[str],
+                    heads: int, with_ave=False, mul=False, activation="tanh"):
+    """MultiScaleTxtEncoderAttention.forward, eval (model/model.py:1663-1705) with the encoder outputs given as
+    features {'gru','bow','w2v','clip'}: tile no-transform (:1675-1676), per-encoder TransformNet (:1678), stack in
+    encoder_name_list order (:1683), multi-head LAFF (:1703)."""
+    feats = []
+    for enc in TXT_ENCODER_ORDER:
+        key = TXT_FEATURE_KEY[enc]
+        if key not in txt_feats:
+            continue
+        x = txt_feats[key]
+        if enc in no_transform:
+            x = np.tile(x, (1, heads))
+        feats.append(transform_net(x, sd, "transform_layer.%s_transform." % enc, activation))
+    return multi_head_attention(np.stack(feats, 1), sd, "attention_layer.", heads, with_ave, mul)
+
+
+def frame_attention_forward(frames: np.ndarray, sd: Mapping[str, np.ndarray], frame_feat: str):
+    """The frame-level stage of VisMutiTransformNetPlusFrameFeat.forward (model/model.py:2160-2173): Attention_1(dim,
+    with_ave=False, mul=False) over the frame axis of each video; the mask slice acts on the batch axis and is a no-op,
+    so zero-padded frames take part in the softmax.  frames [B, F, dim] -> [B, dim]."""
+    p = "frame_attention.%s.0." % frame_feat
+    w = sd[p + "embedding_common.0.weight"].reshape(-1)
+    c = sd[p + "embedding_common.0.bias"].reshape(-1)[0]
+    out, _ = attention_1(frames, w, c, with_ave=False, mul=False)
+    return out
+
+
+def frame_vis_net_forward(vis_input: Mapping[str, np.ndarray], frames: np.ndarray, frame_feat: str,
+                          sd: Mapping[str, np.ndarray], no_transform: Sequence[str], heads: int, activation="tanh"):
+    """VisMutiTransformNetPlusFrameFeat.forward, eval (model/model.py:2147-2190): the pooled frame feature joins the
+    video-level features (appended last), no-transform ones are tiled (:2182-2184), TransformNet each, stack, LAFF."""
+    feats_in = dict(vis_input)
+    feats_in[frame_feat] = frame_attention_forward(frames, sd, frame_feat)
+    feats = []
+    for name, x in feats_in.items():
+        if name in no_transform:
+            x = np.tile(x, (1, heads))
+        feats.append(transform_net(x, sd, "%s." % name, activation))
+    return multi_head_attention(np.stack(feats, 1), sd, "vis_attention_layer.", heads, False, False)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# ranking and metrics
+# ----------------------------------------------------------------------------------------------------------------
+def argsort_rank(scores: np.ndarray, gt: np.ndarray) -> np.ndarray:
+    """predictor.py:232-244 / evaluation.py:71-79 — inds = np.argsort(row)[::-1]; rank = position of the ground truth.
+    numpy's default sort is not stable, so exact ties are resolved however numpy resolves them."""
+    inds = np.argsort(scores, axis=1)
+    return np.array([np.where(inds[i][::-1] == gt[i])[0][0] for i in range(scores.shape[0])], dtype=np.int64)
+
+
+def tie_rule_rank(scores: np.ndarray, gt: np.ndarray) -> np.ndarray:
+    """The documented convention = np.argsort(kind='stable')[::-1]: order by (score desc, index desc):
+    rank0 = #{j != gt: s_j > s_gt} + #{j > gt: s_j == s_gt}."""
+    Q, V = scores.shape
+    sg = scores[np.arange(Q), gt][:, None]
+    cols = np.arange(V)[None, :]
+    beats = (scores > sg) | ((scores == sg) & (cols > gt[:, None]))
+    beats &= cols != gt[:, None]
+    return beats.sum(1).astype(np.int64)
+
+
+def rank_bounds(scores: np.ndarray, gt: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Every rank an argsort-based search can return: #{s_j > s_gt} <= rank0 <= #{s_j > s_gt} + #{j != gt: s_j == s_gt}.
+    numpy's default argsort (predictor.py:232) is not stable (introsort / SIMD quicksort depending on the build), so
+    on exact ties the reference's own answer is only pinned to this interval."""
+    Q, V = scores.shape
+    sg = scores[np.arange(Q), gt][:, None]
+    lo = (scores > sg).sum(1)
+    eq = (scores == sg).sum(1) - 1
+    return lo.astype(np.int64), (lo + eq).astype(np.int64)
+
+
+def tie_rule_topk(scores: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Top-k under the same order: np.argsort(kind='stable')[::-1][:k]."""
+    inds = np.argsort(scores, axis=1, kind="stable")[:, ::-1][:, :k]
+    return np.take_along_axis(scores, inds, 1), inds.astype(np.int64)
+
+
+def metrics_from_rank0(rank0: np.ndarray) -> Tuple[float, float, float, float, float, float]:
+    """evaluation.py:81-89 — from 0-based ranks: R@1/5/10 (%), MedR = floor(median)+1, MeanR = mean+1, MIR."""
+    ranks = np.asarray(rank0, dtype=np.float64)
+    n = len(ranks)
+    r1 = 100.0 * len(np.where(ranks < 1)[0]) / n
+    r5 = 100.0 * len(np.where(ranks < 5)[0]) / n
+    r10 = 100.0 * len(np.where(ranks < 10)[0]) / n
+    medr = np.floor(np.median(ranks)) + 1
+    meanr = ranks.mean() + 1
+    mir = (1.0 / (ranks + 1)).mean()
+    return (r1, r5, r10, medr, meanr, mir)
+
+
+def eval_qry2retro(qry2retro_sim: np.ndarray, n_qry: int = 1):
+    """evaluation.py:64-89 — ground truth of row i is column i / n_qry."""
+    assert qry2retro_sim.shape[0] / qry2retro_sim.shape[1] == n_qry, qry2retro_sim.shape
+    gt = (np.arange(qry2retro_sim.shape[0]) / n_qry).astype(np.int64)
+    return metrics_from_rank0(argsort_rank(qry2retro_sim, gt))
+
+
+def eval_label_matrix(label_matrix: np.ndarray):
+    """evaluation.py:92-109 — label_matrix[i, p] = 1 iff the item at sorted position p is a ground truth of query i.
+    Returns (r1, r5, r10, medr, meanr, mir, mAP) from 1-based ranks."""
+    label_matrix = label_matrix.astype(int)
+    n = label_matrix.shape[0]
+    ranks = np.zeros(n)
+    aps = np.zeros(n)
+    for i in range(n):
+        pos = np.where(label_matrix[i] == 1)[0] + 1
+        ranks[i] = pos[0]
+        aps[i] = np.mean([(j + 1.0) / pos[j] for j in range(len(pos))])
+    r1, r5, r10 = [100.0 * np.mean([x <= k for x in ranks]) for k in (1, 5, 10)]
+    return (r1, r5, r10, np.floor(np.median(ranks)), ranks.mean(), (1.0 / ranks).mean(), aps.mean())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# loss
+# ----------------------------------------------------------------------------------------------------------------
+def _hinge(scores: np.ndarray, margin, max_violation: bool, cost_style: str, direction: str, want_grad: bool):
+    """Shared by MarginRankingLoss (loss.py:99-135) and MarginRankingLossWithScore (loss.py:164-200).
+    Returns (loss, dLoss/dscores)."""
+    dt = scores.dtype.type
+    B = scores.shape[0]
+    diag = np.diag(scores).reshape(B, 1)
+    eye = np.eye(B, dtype=bool)
+    loss = dt(0)
+    g = np.zeros_like(scores)
+    parts = []
+    if direction in ("i2t", "bidir"):
+        parts.append(("s", np.where(eye, 0, np.maximum(dt(margin) + scores - diag, 0))))        # d1: diag[i] per row
+    if direction in ("t2i", "bidir"):
+        parts.append(("im", np.where(eye, 0, np.maximum(dt(margin) + scores - diag.T, 0))))     # d2: diag[j] per col
+    for kind, cost in parts:
+        if max_violation:
+            red = cost.max(1) if kind == "s" else cost.max(0)                                      # loss.py:121-125
+            arg = cost.argmax(1) if kind == "s" else cost.argmax(0)
+            denom = dt(B) if cost_style != "sum" else dt(1)
+            loss = loss + red.sum(dtype=scores.dtype) / denom
+            if want_grad:
+                for t in range(B):
+                    if red[t] > 0:
+                        if kind == "s":
+                            g[t, arg[t]] += 1 / denom
+                            g[t, t] -= 1 / denom
+                        else:
+                            g[arg[t], t] += 1 / denom
+                            g[t, t] -= 1 / denom
+        else:
+            denom = dt(B * B) if cost_style != "sum" else dt(1)
+            loss = loss + cost.sum(dtype=scores.dtype) / denom
+            if want_grad:
+                viol = (cost > 0).astype(scores.dtype) / denom
+                g += viol
+                if kind == "s":
+                    g[np.arange(B), np.arange(B)] -= viol.sum(1)
+                else:
+                    g[np.arange(B), np.arange(B)] -= viol.sum(0)
+    return loss, g
+
+
+def _l2norm_backward(x: np.ndarray, ghat: np.ndarray, eps) -> np.ndarray:
+    """d/dx of x / (||x|| + eps) contracted with ghat (autograd of loss.py:11-12)."""
+    n = np.sqrt((x * x).sum(1, keepdims=True))
+    den = n + eps
+    xhat = x / den
+    dot = (xhat * ghat).sum(1, keepdims=True)
+    return ghat / den - xhat * dot / np.where(n > 0, n, 1)
+
+
+def margin_ranking_loss(s: np.ndarray, im: np.ndarray, margin=0.0, max_violation=False, cost_style="sum",
+                        direction="bidir", want_grad: bool = False):
+    """MarginRankingLoss.forward(s, im) (loss.py:95-135): scores = cosine_sim(im, s) so rows = images/videos and
+    columns = sentences.  Returns loss or (loss, d_s, d_im)."""
+    dt = s.dtype.type
+    eps = dt(1e-13) + dt(1e-14)
+    s_hat, im_hat = l2norm(s), l2norm(im)
+    scores = im_hat @ s_hat.T
+    loss, g = _hinge(scores, margin, max_violation, cost_style, direction, want_grad)
+    if not want_grad:
+        return loss
+    d_im_hat = g @ s_hat
+    d_s_hat = g.T @ im_hat
+    return loss, _l2norm_backward(s, d_s_hat, eps), _l2norm_backward(im, d_im_hat, eps)
+
+
+def multi_head_loss(txt_embs: np.ndarray, vis_embs: np.ndarray, margin=0.2, max_violation=True, cost_style="sum",
+                    direction="t2i", want_grad: bool = False):
+    """W2VVPP.compute_loss 3-D branch / W2VVPP_MultiHeadAttention.compute_loss multi_space branch
+    (model/model.py:852-862, :2036-2038): sum over heads of criterion(txt[:, h, :], vis[:, h, :])."""
+    total = txt_embs.dtype.type(0)
+    d_txt = np.zeros_like(txt_embs)
+    d_vis = np.zeros_like(vis_embs)
+    for h in range(vis_embs.shape[1]):
+        r = margin_ranking_loss(np.ascontiguousarray(txt_embs[:, h, :]), np.ascontiguousarray(vis_embs[:, h, :]), margin,
+                                max_violation, cost_style, direction, want_grad)
+        if want_grad:
+            total = total + r[0]
+            d_txt[:, h, :], d_vis[:, h, :] = r[1], r[2]
+        else:
+            total = total + r
+    return (total, d_txt, d_vis) if want_grad else total
+
+
+def margin_ranking_loss_with_score(score: np.ndarray, margin=0.0, max_violation=False, cost_style="sum",
+                                   direction="bidir", want_grad: bool = False):
+    """MarginRankingLossWithScore.forward(score) (loss.py:161-200)."""
+    loss, g = _hinge(score, margin, max_violation, cost_style, direction, want_grad)
+    return (loss, g) if want_grad else loss
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# whole-path driver used as the CPU baseline (bench.py) — the reference's predictor path on embeddings
+# ----------------------------------------------------------------------------------------------------------------
+def retrieve_cpu(q_emb: np.ndarray, g_emb: np.ndarray, gt: np.ndarray, heads: int, k: int = 10, chunk: int = 100000,
+                 threads: int = 1):
+    """Reference evaluation path for Q queries against a V-video gallery of fused embeddings, restated for bounded
+    memory: get_txt2vis_matrix (model/model.py:1003-1016) per gallery chunk, np.argsort per row (predictor.py:232),
+    ground-truth position (predictor.py:239-244), metrics (evaluation.py:81-89).  The gallery is processed in
+    `chunk`-video pieces (the reference's predict() tiles by loader batch, model/model.py:1064-1073) and rows are
+    sorted on `threads` host threads.  Returns (rank0 [Q], topk_idx [Q, k], metrics)."""
+    Q = q_emb.shape[0]
+    V = g_emb.shape[0]
+    H = heads
+    q3 = q_emb.reshape(Q, H, -1)
+    scores = np.empty((Q, V), dtype=np.float32)
+    for s in range(0, V, chunk):
+        e = min(V, s + chunk)
+        scores[:, s:e] = txt2vis_matrix(q3, g_emb[s:e].reshape(e - s, H, -1))
+    rank0 = np.empty(Q, dtype=np.int64)
+    topk = np.empty((Q, k), dtype=np.int64)
+
+    def work(lo, hi):
+        inds = np.argsort(scores[lo:hi], axis=1)
+        for i in range(lo, hi):
+            ind = inds[i - lo][::-1]
+            rank0[i] = np.where(ind == gt[i])[0][0]
+            topk[i] = ind[:k]
+
+    step = max(1, (Q + threads - 1) // threads)
+    if threads <= 1:
+        work(0, Q)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda lo: work(lo, min(Q, lo + step)), range(0, Q, step)))
+    return rank0, topk, metrics_from_rank0(rank0)

@@ -326,6 +326,8 @@ SECTIONS = {
     "rank_cg1": lambda: sec_rank(1, 1000, 5000, 4096, 10, 4, 3),
     "rank_cg2": lambda: sec_rank(2, 1000, 5000, 4096, 10, 4, 3),
     "rank_cg2_b": lambda: sec_rank(2, 2990, 2990, 4096, 16, 16, 10),
+    "rank_cg2_k1": lambda: sec_rank(2, 700, 9000, 4096, 1, 2, 2),
+    "rank_cg2_c": lambda: sec_rank(2, 1000, 70001, 4096, 10, 16, 10),
     "fuse": sec_fuse,
     "loss": sec_loss,
     "perf_cg1": lambda: sec_perf(1, 10000, 200000, 16, 10, 3),
