@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — queries/sec ranked against a 1M-video gallery (BASELINE.json metric, config C5) on N B200s.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's CPU path (oracle port) on the host cores
+
+A step = one pass of the hot path over one batch of synthetic queries: fuse the text features of Q = 10 000 queries
+(gru + bow + w2v FC projections, CLIP tiled, LAFF pooling), then rank them against the V = 1 000 000-video gallery of
+fused embeddings resident in HBM (tensor-core similarity sweep fused with exact rank counting and top-10, metrics on
+device).  With N > 1 the gallery is sharded across the ranks (strong scaling: total work fixed) and the per-shard
+results are merged with NCCL.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+Q_FULL, V_FULL, HEADS, HEAD_DIM, TOPK = 10000, 1000000, 8, 512, 10
+D = HEADS * HEAD_DIM
+METRIC = "queries/sec ranked vs 1M-video gallery"
+UNIT = "queries/s"
+FLOP_PER_PAIR = 2 * D            # 8192 FLOP per (query, video) similarity
+FLOP_PER_QUERY_FUSE = 45.10e6    # 2*4096*(1024+3981+500)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tensor_tflops": float(d["bf16_tflops_sustained"]), "hbm_gbs": float(d["hbm_gbs"]), "source": "measured"}
+    return {"tensor_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}  # B200_PROFILING.md fallback (sustained)
+
+
+def recorded_traffic():
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("rank_sweep_dram_bytes_per_launch_1gpu")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+                power.append(float(p[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            busy = [s for s, w in zip(sm, power) if w >= 0.5 * max(power)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# synthetic workload
+# --------------------------------------------------------------------------------------------------------------------
+def build_txt_net(device):
+    from laff_b200 import config as cfg, model as M, synth
+    c = cfg.laff_config(D, HEADS, synth.DIMS)
+    net = M.MultiScaleTxtEncoderAttention(c)
+    sd = {k: torch.from_numpy(np.asarray(synth.param(1234, k, tuple(v.shape)))).to(v.dtype).reshape(v.shape)
+          for k, v in net.state_dict().items()}
+    net.load_state_dict(sd)
+    return net.to(device).eval()
+
+
+def query_features(Q, pinned: bool):
+    """Synthetic per-encoder text features of Q queries on the host (optionally pinned)."""
+    g = torch.Generator().manual_seed(1234 + 5)
+    from laff_b200 import synth
+    feats = {"gru": torch.randn(Q, synth.DIMS["gru"], generator=g),
+             "w2v": torch.randn(Q, synth.DIMS["w2v"], generator=g),
+             "clip": torch.randn(Q, synth.DIMS["clip"], generator=g)}
+    bow = torch.zeros(Q, synth.DIMS["bow"])
+    ids = torch.randint(0, synth.DIMS["bow"], (Q, 8), generator=g)
+    bow.scatter_add_(1, ids, torch.ones(Q, 8))
+    feats["bow"] = bow
+    if pinned:
+        feats = {k: v.pin_memory() for k, v in feats.items()}
+    return feats
+
+
+def unit_rows(n, gen, device, dtype=torch.float32):
+    x = torch.randn(n, HEADS, HEAD_DIM, generator=gen, device=device)
+    return (x / x.norm(dim=2, keepdim=True)).reshape(n, D).to(dtype)
+
+
+def build_gallery_shard(lo, hi, q_emb, gt, sigma, device):
+    """Rows [lo, hi) of the synthetic gallery: unit-norm noise per head; row gt(i) = normalise(q_i + sigma * noise) so
+    that R@1 is ~30 %.  Deterministic in the global row index, independent of the sharding."""
+    n = hi - lo
+    g16 = torch.empty(n, D, dtype=torch.bfloat16, device=device)
+    block = 65536
+    for s in range(lo - lo % block, hi, block):
+        gen = torch.Generator(device=device).manual_seed(9000 + s // block)
+        rows = unit_rows(block, gen, device)
+        a, b = max(s, lo), min(s + block, hi)
+        g16[a - lo:b - lo] = rows[a - s:b - s].to(torch.bfloat16)
+    own = ((gt >= lo) & (gt < hi)).nonzero().flatten()
+    if own.numel():
+        gen = torch.Generator(device=device).manual_seed(777)
+        noise = unit_rows(gt.numel(), gen, device)[own]
+        planted = q_emb[own].float() + sigma * noise
+        planted = planted.view(-1, HEADS, HEAD_DIM)
+        planted = (planted / planted.norm(dim=2, keepdim=True)).reshape(-1, D)
+        g16[gt[own] - lo] = planted.to(torch.bfloat16)
+    return g16
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# arms
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(q_emb, g_host, gt, sample, steps, warmup, threads):
+    """The reference's evaluation path restated on the host (oracle port): per step `sample` queries against the whole
+    gallery — get_txt2vis_matrix per 100k-video chunk, np.argsort per row, ground-truth search, metrics."""
+    from oracle import laff_oracle as O
+    torch.set_num_threads(threads)
+    times = []
+    Q = q_emb.shape[0]
+    for it in range(warmup + steps):
+        lo = (it * sample) % max(1, Q - sample + 1)
+        t0 = time.perf_counter()
+        O.retrieve_cpu(q_emb[lo:lo + sample], g_host, gt[lo:lo + sample], HEADS, k=TOPK, chunk=100000, threads=threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample
+    V = args.videos
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    g_host = np.empty((V, D), dtype=np.float32)
+    for s in range(0, V, 65536):
+        n = min(65536, V - s)
+        g_host[s:s + n] = unit_rows(n, gen, dev).cpu().numpy()
+    Qr = max(sample * 2, 256)
+    gt = (np.arange(Qr, dtype=np.int64) * 97) % V
+    from laff_b200 import synth
+    noise = unit_rows(Qr, gen, dev).cpu().numpy()
+    q = synth.unit_heads(g_host[gt] + synth.sigma_for_recall(V, D) * noise, HEADS)
+    times = cpu_reference_steps(q, g_host, gt, sample, args.steps, args.warmup, cores)
+    ms = 1e3 * sum(times) / len(times)
+    val = sample / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5: %d-query samples ranked against a %d-video gallery of fused LAFF embeddings "
+                                   "(8 heads x 512), top-%d + rank + R@K/MedR" % (sample, V, TOPK),
+                       "queries_per_step": sample, "gallery": V},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d queries x %d videos per step, gallery in 100k-video chunks, numpy/BLAS + "
+                                       "threaded argsort (oracle port of model.py:1003-1016, predictor.py:232-244, "
+                                       "evaluation.py:81-89)" % (sample, V)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from laff_b200 import _capi, ops, synth
+    from laff_b200.retrieval import GalleryIndex, Retriever, shard_bounds
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    Q, V = args.queries, args.videos
+    lib = _capi.lib()
+
+    txt_net = build_txt_net(dev)
+    feats_host = query_features(Q, pinned=True)
+    feats_dev = {k: v.to(dev) for k, v in feats_host.items()}
+    gt = ((torch.arange(Q, dtype=torch.int64) * 97) % V)
+    gt_host = gt.to(torch.int32).pin_memory()
+    gt_dev = gt.to(dev)
+    with torch.no_grad():
+        _, q16 = txt_net.encode(feats_dev, out16_dtype=torch.bfloat16)
+    sigma = synth.sigma_for_recall(V, D)
+    lo, hi = shard_bounds(V, world, rank)
+    g16 = build_gallery_shard(lo, hi, q16.reshape(Q, D), gt_dev, sigma, dev)
+    index = GalleryIndex(g16, V, HEADS, rank, world)
+    retr = Retriever(txt_net, index)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return retr.rank(feats_dev, gt_dev, TOPK)
+
+    def step_e2e():
+        res = retr.rank(feats_host, gt_host, TOPK)      # pinned host -> device copies inside
+        return res.rank0.cpu(), res.topk_val.cpu(), res.topk_idx.cpu(), res.metrics.cpu()
+
+    # ---- device-resident inputs: `value` ------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        res = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.laff_launch_count(1)
+    index.timers = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        res = step_device()
+        ev[i + 1].record()
+    barrier()
+    launches = int(lib.laff_launch_count(0))
+    total_ms = ev[0].elapsed_time(ev[-1])
+    sweep_ms = [a.elapsed_time(b) for a, b in index.timers]
+    index.timers = None
+    # ---- host buffers through the public API: `e2e` -------------------------------------------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        out = step_e2e()
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    times = torch.tensor([total_ms, e2e_ms, sum(sweep_ms) / max(1, len(sweep_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, sweep_avg_ms = [float(x) for x in times.cpu()]
+    metrics = res.metrics.cpu().tolist()
+
+    if rank != 0:
+        return
+    pk = peaks()
+    ms_per_step = total_ms / args.steps
+    value = Q / (ms_per_step * 1e-3)
+    e2e_value = Q / (e2e_ms / args.steps * 1e-3)
+    n_local = hi - lo
+    achieved = Q * n_local * FLOP_PER_PAIR / (sweep_avg_ms * 1e-3) / 1e12
+    h2d = sum(v.numel() * v.element_size() for v in feats_host.values()) + gt_host.numel() * 4
+    d2h = Q * 4 + Q * TOPK * 8 + 8 * 8
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "C5: %d queries (gru1024+bow3981+w2v500 FC -> 4096, CLIP512 tiled, LAFF pooling, 8x512) "
+                               "ranked against a %d-video gallery of fused embeddings resident in HBM: similarity "
+                               "sweep + exact rank + top-%d + R@K/MedR" % (Q, V, TOPK),
+                   "queries": Q, "gallery": V, "gallery_per_gpu": n_local, "topk": TOPK, "sharding": "gallery rows / %d" % world,
+                   "l2": "inputs exceed L2 (gallery shard %.1f GB)" % (n_local * D * 2 / 1e9),
+                   "recall": {"r1": metrics[0], "r5": metrics[1], "r10": metrics[2], "medr": metrics[3]}},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_kernel<2, EpiRank<16>> (similarity sweep + rank + top-k)",
+                     "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tensor_tflops"],
+                     "peak_source": pk["source"] + " (bf16 dense sustained)",
+                     "flop_per_launch": Q * n_local * FLOP_PER_PAIR, "avg_launch_ms": sweep_avg_ms,
+                     "traffic": recorded_traffic() if world == 1 and V == V_FULL and Q == Q_FULL else None},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample
+        g_host = np.empty((V, D), dtype=np.float32)
+        for s in range(0, V, 131072):
+            g_host[s:s + 131072] = g16[s:s + 131072].float().cpu().numpy()
+        q_host = q16.reshape(Q, D)[: max(2 * sample, 256)].float().cpu().numpy()
+        tms = cpu_reference_steps(q_host, g_host, gt.numpy()[: len(q_host)], sample, 2, 1, cores)
+        cval = sample / (sum(tms) / len(tms))
+        line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d queries x %d videos per step (2 steps after 1 warm-up), same embeddings as "
+                                          "the GPU arm, oracle port of the reference's sim + argsort + metrics path" % (sample, V)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--queries", type=int, default=Q_FULL)
+    ap.add_argument("--videos", type=int, default=V_FULL)
+    ap.add_argument("--cpu-sample", type=int, default=64, help="queries per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

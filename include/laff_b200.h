@@ -51,6 +51,9 @@ extern "C" {
 const char* laff_last_error(void);
 int laff_abi_version(void);
 
+/* Number of CUDA kernels this library has launched since the last reset (bench.py's gpu_launches). */
+long long laff_launch_count(int reset);
+
 /* Tuning knobs of the tcgen05 GEMM engine (0 keeps the current value).
  *   cta_group   1: one CTA per 128x256 tile, 2: CTA pair per 256x256 tile (cta_group::2 MMA).
  *   chunk_tiles number of consecutive 256-column gallery tiles one work unit sweeps with per-row top-k state.

@@ -53,6 +53,7 @@ _vp, _i, _ll, _f, _d, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_do
 SIGNATURES = {
     "laff_last_error": (C.c_char_p, []),
     "laff_abi_version": (_i, []),
+    "laff_launch_count": (C.c_longlong, [_i]),
     "laff_set_tuning": (_i, [_i, _i, _i]),
     "laff_get_tuning": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "laff_l2norm_quantize": (_i, [_vp, _ll, _i, _i, _ll, _d, _i, _vp, _ll, _vp]),

@@ -371,7 +371,7 @@ int laff_l2norm_quantize(const float* x, long long rows, int heads, int head_dim
   const long long blocks = (warps * 32 + block - 1) / block;
   LAFF_REQUIRE(blocks < (1LL << 31), LAFF_ENOTSUP, "laff_l2norm_quantize: too many rows");
   l2norm_quantize_kernel<<<static_cast<unsigned>(blocks), block, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rows, heads, head_dim, ldx, static_cast<float>(eps < 0 ? 0.0 : eps), eps >= 0 ? 1 : 0, out_dtype, out, ld_out);
+      x, rows, heads, head_dim, ldx, static_cast<float>(eps < 0 ? 0.0 : eps), eps >= 0 ? 1 : 0, out_dtype, out, ld_out); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }
@@ -385,7 +385,7 @@ int laff_cast_pad_16(const float* x, long long rows, int cols, long long ldx, in
   int rc = get_device_info(&di);
   if (rc) return rc;
   cast_pad_kernel<<<grid_for(rows * cols_pad, 256, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rows, cols, ldx, out_dtype, static_cast<uint16_t*>(out), cols_pad, ld_out);
+      x, rows, cols, ldx, out_dtype, static_cast<uint16_t*>(out), cols_pad, ld_out); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }
@@ -399,7 +399,7 @@ int laff_split3_16(const float* x, long long rows, int cols, long long ldx, int 
   int rc = get_device_info(&di);
   if (rc) return rc;
   split3_kernel<<<grid_for(rows * cols_pad, 256, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rows, cols, ldx, side, out_dtype, static_cast<uint16_t*>(out), cols_pad, ld_out);
+      x, rows, cols, ldx, side, out_dtype, static_cast<uint16_t*>(out), cols_pad, ld_out); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }
@@ -411,7 +411,7 @@ int laff_bn_fold(const float* weight, const float* bias, const float* running_me
   int rc = get_device_info(&di);
   if (rc) return rc;
   bn_fold_kernel<<<(D + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(weight, bias, running_mean, running_var,
-                                                                                static_cast<float>(eps), D, scale, shift);
+                                                                                static_cast<float>(eps), D, scale, shift); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }
@@ -488,7 +488,7 @@ int laff_attention_pool(const laff_pool_desc* desc, long long rows, float* out, 
 #define LAFF_POOL_CASE(V)                                                                                              \
   case V:                                                                                                              \
     attention_pool_kernel<V><<<static_cast<unsigned>(blocks), block, 0, st>>>(*desc, rows, out, ld_out, out16,          \
-                                                                              out16_dtype, ld_out16, att);             \
+                                                                              out16_dtype, ld_out16, att); laff::count_launch();             \
     break;
   LAFF_REQUIRE(dh % 32 == 0, LAFF_ENOTSUP, "laff_attention_pool: head_dim %d must be a multiple of 32", dh);
   switch (dh / 32) {
@@ -521,7 +521,7 @@ int laff_frame_pool(const float* frames, long long B, int F, int dim, const floa
   case V:                                                                                                            \
     frame_pool_kernel<V><<<static_cast<unsigned>(blocks), block, 0, st>>>(frames, B, F, dim, att_weight, att_bias,    \
                                                                           with_ave, mul, omega,                      \
-                                                                          static_cast<float>(norm_eps), out, ld_out); \
+                                                                          static_cast<float>(norm_eps), out, ld_out); laff::count_launch(); \
     break;
   switch (dim / 32) {
     LAFF_FRAME_CASE(1)

@@ -18,6 +18,9 @@
 #pragma once
 #include "ptx.cuh"
 
+#define LAFF_COUNT_LAUNCH_DECLARED
+namespace laff { void count_launch(int n = 1); }
+
 namespace laff {
 
 constexpr int kBlockM = 128;  // accumulator rows per CTA (TMEM lanes)
@@ -293,6 +296,7 @@ inline cudaError_t launch_gemm_kernel(const CUtensorMap& tmA, const CUtensorMap&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  count_launch();
   return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, num_kb, idesc, s, hintA, hintB, ep);
 }
 

@@ -2,6 +2,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 #include <mutex>
 
 namespace laff {
@@ -43,7 +44,15 @@ int get_device_info(DeviceInfo* info) {
   return LAFF_OK;
 }
 
-static Tuning g_tuning = {2, 16, 10};
+// Measured on B200 (profiles/): single-tile units in n-major order with ~10 query row-tiles per group keep the query
+// block L2-resident and let the CTA pairs that share a gallery tile run within a fraction of a tile of each other.
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count(bool reset) {
+  return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
+}
+
+static Tuning g_tuning = {2, 1, 10};
 static std::mutex g_tuning_mu;
 
 Tuning get_tuning() {
@@ -90,11 +99,15 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, int dtype, uint64_t rows, ui
 
 }  // namespace laff
 
+namespace laff { long long launch_count(bool reset); }
+
 extern "C" {
 
 const char* laff_last_error(void) { return laff::g_err; }
 
 int laff_abi_version(void) { return 1; }
+
+long long laff_launch_count(int reset) { return laff::launch_count(reset != 0); }
 
 int laff_set_tuning(int cta_group, int chunk_tiles, int m_group) {
   if ((cta_group != 0 && cta_group != 1 && cta_group != 2) || chunk_tiles < 0 || m_group < 0) {

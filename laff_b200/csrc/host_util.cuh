@@ -30,6 +30,12 @@ Tuning get_tuning();
 int make_tmap_2d(CUtensorMap* tm, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                  uint32_t box_rows);
 
+// Number of kernels this library has launched (bench.py reports it as gpu_launches).
+// (declared with its default argument in gemm_engine.cuh when that header is included first)
+#ifndef LAFF_COUNT_LAUNCH_DECLARED
+void count_launch(int n = 1);
+#endif
+
 inline bool is16(int dtype) { return dtype == LAFF_F16 || dtype == LAFF_BF16; }
 
 }  // namespace laff

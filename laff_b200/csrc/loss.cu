@@ -235,19 +235,19 @@ int laff_mrl_forward_backward(const float* txt, const float* vis, int B, int H, 
   const float eps = 1e-13f + 1e-14f;  // loss.py:8, :11 (default eps + 1e-14)
   const long long items = static_cast<long long>(B) * H;
   const int nblk = static_cast<int>((items * 32 + 255) / 256);
-  mrl_normalize_kernel<<<nblk, 256, 0, st>>>(txt, items, dh, eps, txt_hat, txt_nrm);
-  mrl_normalize_kernel<<<nblk, 256, 0, st>>>(vis, items, dh, eps, vis_hat, vis_nrm);
+  mrl_normalize_kernel<<<nblk, 256, 0, st>>>(txt, items, dh, eps, txt_hat, txt_nrm); laff::count_launch();
+  mrl_normalize_kernel<<<nblk, 256, 0, st>>>(vis, items, dh, eps, vis_hat, vis_nrm); laff::count_launch();
   dim3 grid((B + 31) / 32, (B + 31) / 32, H), block(32, 8);
-  mrl_scores_kernel<<<grid, block, 0, st>>>(vis_hat, txt_hat, B, H, dh, S);
+  mrl_scores_kernel<<<grid, block, 0, st>>>(vis_hat, txt_hat, B, H, dh, S); laff::count_launch();
   const bool need_grad = d_txt != nullptr || d_vis != nullptr;
   if (need_grad) LAFF_CUDA(cudaMemsetAsync(dS, 0, static_cast<size_t>(H) * B * B * 4, st));
   const int hthreads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
   mrl_hinge_kernel<<<H, hthreads, 0, st>>>(S, B, B, static_cast<long long>(B) * B, margin, max_violation, direction,
-                                           cost_mean, head_loss, need_grad ? dS : nullptr);
-  mrl_sum_heads_kernel<<<1, 32, 0, st>>>(head_loss, H, loss);
+                                           cost_mean, head_loss, need_grad ? dS : nullptr); laff::count_launch();
+  mrl_sum_heads_kernel<<<1, 32, 0, st>>>(head_loss, H, loss); laff::count_launch();
   const size_t gsm = static_cast<size_t>(dh + 32) * 4;
-  if (d_vis) mrl_grad_kernel<<<dim3(B, H), 128, gsm, st>>>(dS, txt_hat, vis_hat, vis_nrm, B, H, dh, eps, 0, d_vis);
-  if (d_txt) mrl_grad_kernel<<<dim3(B, H), 128, gsm, st>>>(dS, vis_hat, txt_hat, txt_nrm, B, H, dh, eps, 1, d_txt);
+  if (d_vis) mrl_grad_kernel<<<dim3(B, H), 128, gsm, st>>>(dS, txt_hat, vis_hat, vis_nrm, B, H, dh, eps, 0, d_vis); laff::count_launch();
+  if (d_txt) mrl_grad_kernel<<<dim3(B, H), 128, gsm, st>>>(dS, vis_hat, txt_hat, txt_nrm, B, H, dh, eps, 1, d_txt); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }
@@ -263,7 +263,7 @@ int laff_mrl_score_forward_backward(const float* score, int B, long long ld, flo
   if (d_score) LAFF_CUDA(cudaMemset2DAsync(d_score, static_cast<size_t>(ld) * 4, 0, static_cast<size_t>(B) * 4, B, st));
   const int hthreads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
   // head_loss[0] is written straight into *loss (H = 1)
-  mrl_hinge_kernel<<<1, hthreads, 0, st>>>(score, B, ld, 0, margin, max_violation, direction, cost_mean, loss, d_score);
+  mrl_hinge_kernel<<<1, hthreads, 0, st>>>(score, B, ld, 0, margin, max_violation, direction, cost_mean, loss, d_score); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }

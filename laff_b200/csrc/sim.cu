@@ -626,7 +626,7 @@ int laff_sim_gt_scores(const void* q, const void* g, int Q, int V, int D, long l
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > op.sms * 8) blocks = op.sms * 8;
   gather_rows16_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint4*>(g), ldg / 8, gt_local, Q, vec_per_row,
-                                               static_cast<uint4*>(ggt));
+                                               static_cast<uint4*>(ggt)); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   const Sched s = make_sched(Q, Q, op.cg, 1, 1, 1);
   EpiDiag::Params ep{sgt_raw, gt_local, Q};
@@ -661,13 +661,13 @@ int laff_sim_rank_topk(const void* q, const void* g, int Q, int V, int D, long l
   long long* slots = reinterpret_cast<long long*>(wp);
   int32_t* thr_key = reinterpret_cast<int32_t*>(wp + static_cast<size_t>(Q) * LAFF_MAX_TOPK * 8);
   const int init_n = Q * LAFF_MAX_TOPK;
-  rank_init_kernel<<<(init_n + 255) / 256, 256, 0, st>>>(count, thr_key, slots, Q, LAFF_MAX_TOPK);
+  rank_init_kernel<<<(init_n + 255) / 256, 256, 0, st>>>(count, thr_key, slots, Q, LAFF_MAX_TOPK); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   EpiRank<LAFF_MAX_TOPK>::Params ep{sgt_raw, gt_global, count, thr_key, slots, Q, V, col_offset, k};
   rc = launch_gemm<EpiRank<LAFF_MAX_TOPK>>(op, s, ep, st);
   if (rc) return rc;
   if (k > 0) {
-    topk_finalize_kernel<<<(Q + 127) / 128, 128, 0, st>>>(slots, Q, LAFF_MAX_TOPK, k, scale, topk_val, topk_idx);
+    topk_finalize_kernel<<<(Q + 127) / 128, 128, 0, st>>>(slots, Q, LAFF_MAX_TOPK, k, scale, topk_val, topk_idx); laff::count_launch();
     LAFF_CUDA(cudaGetLastError());
   }
   return LAFF_OK;
@@ -683,7 +683,7 @@ int laff_topk_merge(const float* vals, const int32_t* idx, int n_lists, int Q, i
   const int threads = 128;
   const int blocks = (Q * 32 + threads - 1) / threads;
   topk_merge_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(vals, idx, n_lists, Q, k_in, list_stride,
-                                                                              k_in, k_out, in_scale, out_val, out_idx);
+                                                                              k_in, k_out, in_scale, out_val, out_idx); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }
@@ -697,7 +697,7 @@ int laff_rank_from_scores(const float* scores, int Q, int V, long long ld, const
   int rc = get_device_info(&di);
   if (rc) return rc;
   rank_from_scores_kernel<<<Q, 256, 0, static_cast<cudaStream_t>(stream)>>>(scores, V, ld, gt, k, rank0, topk_val,
-                                                                           topk_idx);
+                                                                           topk_idx); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }
@@ -710,9 +710,9 @@ int laff_label_metrics(const uint8_t* label, int Q, int V, long long ld, int32_t
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int threads = 128;
-  label_metrics_kernel<<<(Q * 32 + threads - 1) / threads, threads, 0, st>>>(label, Q, V, ld, rank0, ap);
-  rank_metrics_kernel<<<1, 1024, 0, st>>>(rank0, Q, out8);
-  mean_double_kernel<<<1, 1024, 0, st>>>(ap, Q, out8 + 6);  // mAP over the per-query APs
+  label_metrics_kernel<<<(Q * 32 + threads - 1) / threads, threads, 0, st>>>(label, Q, V, ld, rank0, ap); laff::count_launch();
+  rank_metrics_kernel<<<1, 1024, 0, st>>>(rank0, Q, out8); laff::count_launch();
+  mean_double_kernel<<<1, 1024, 0, st>>>(ap, Q, out8 + 6); laff::count_launch();  // mAP over the per-query APs
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }
@@ -722,7 +722,7 @@ int laff_rank_metrics(const int32_t* rank0, int Q, double* out8, void* stream) {
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
-  rank_metrics_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(rank0, Q, out8);
+  rank_metrics_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(rank0, Q, out8); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }

@@ -107,3 +107,20 @@ class GalleryIndex:
             dist.all_gather(idxs, ti.contiguous(), group=self.group)
             tv, ti = be.merge(torch.stack(vals, 0), torch.stack(idxs, 0), k)
         return SearchResult(count, tv, ti, be.metrics(count))
+
+
+class Retriever:
+    """The whole query path behind one call: fuse the text features of a batch of queries (txt_net, F1-F6), then rank
+    them against the resident gallery shard(s) (S2 + E2 + E3).  This is the public API bench.py's e2e leg times."""
+
+    def __init__(self, txt_net, index: GalleryIndex, out16_dtype=torch.bfloat16):
+        self.txt_net = txt_net
+        self.index = index
+        self.out16_dtype = out16_dtype
+
+    @torch.no_grad()
+    def rank(self, caption_feat_dict, gt_global, k: int = 10) -> SearchResult:
+        """caption_feat_dict: per-encoder text features (host or device tensors); gt_global: int [Q]."""
+        _, q16 = self.txt_net.encode(caption_feat_dict, out16_dtype=self.out16_dtype)
+        dev = q16.device
+        return self.index.search(q16.reshape(q16.shape[0], -1), gt_global.to(dev, non_blocking=True), k)

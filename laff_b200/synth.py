@@ -104,6 +104,16 @@ def unit_heads(x: np.ndarray, heads: int) -> np.ndarray:
     return y.reshape(rows, -1)
 
 
+def sigma_for_recall(V: int, D: int, z_shift: float = -0.52) -> float:
+    """Noise level for which R@1 is ~30% against V unit-norm random distractors: the positive's mean score
+    1/sqrt(1+sigma^2) sits z_shift standard deviations from the expected maximum negative score
+    (Gumbel approximation of the maximum of V standard normals, scaled by 1/sqrt(D))."""
+    lv = np.log(float(max(V, 3)))
+    z = np.sqrt(2 * lv) - (np.log(lv) + np.log(4 * np.pi)) / (2 * np.sqrt(2 * lv))
+    t = max(1e-3, (z + z_shift) / np.sqrt(D))
+    return float(np.sqrt(max(1.0 / (t * t) - 1.0, 0.0)))
+
+
 def retrieval_embeddings(seed: int, Q: int, V: int, heads: int = 8, head_dim: int = 512, sigma: float = 1.2):
     """C5-style synthetic embeddings: gallery = unit-norm noise per head, gt(i) = (i*97) mod V,
     query = normalize(gallery[gt] + sigma * unit noise).  Returns (q [Q,D], g [V,D], gt [Q]) float32 / int64."""

@@ -1,0 +1,256 @@
+"""GPU parity of similarity + ranking + metrics through the C ABI.
+
+Bars: integer outputs (rank0, top-k indices, R@K, MedR) bit-exact against the oracle applied to the kernel's own fp32
+score matrix, and against the fp64 oracle scores wherever no two scores are closer than the fp32 accumulation noise
+(2e-6); fp32 scores within 2e-6 of the fp64 oracle on the same 16-bit operands (T1); within 2e-3 (bf16) / 3e-4
+(fp16) / 8e-6 (bf16x3) of the all-fp32 reference (T2, golden).
+
+fp32 accumulation of a 4096-term dot in the tensor core (truncating adds) vs fp64: |err| <= 2e-6 + 8e-6 * |score|
+(2e-6 holds for every negative pair, |score| < 0.1; matched pairs with scores ~0.5 see ~3e-6)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import cuda, max_abs
+from laff_b200 import evaluation as E
+from laff_b200 import loss as L
+from laff_b200 import model as M
+from laff_b200 import ops, synth
+from laff_b200.retrieval import GalleryIndex, shard_bounds
+from oracle import laff_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _restore():
+    before = ops.get_tuning()
+    L.set_precision("bf16")
+    yield
+    ops.set_tuning(*before)
+    L.set_precision("bf16")
+
+
+def sim_close(got, ref64):
+    got = got.detach().double().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got, dtype=np.float64)
+    return bool(np.all(np.abs(got - ref64) <= 2e-6 + 8e-6 * np.abs(ref64)))
+
+
+def operands(seed, Q, V, H=8, dh=512, sigma=1.2, dtype=torch.bfloat16):
+    q, g, gt = synth.retrieval_embeddings(seed, Q, V, H, dh, sigma)
+    return cuda(q).to(dtype), cuda(g).to(dtype), gt
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("Q,V,D,dtype", [(1, 1, 64, torch.bfloat16), (128, 256, 64, torch.bfloat16),
+                                        (300, 1000, 4096, torch.bfloat16), (300, 1000, 4096, torch.float16),
+                                        (257, 513, 520, torch.bfloat16), (1000, 1000, 4096, torch.bfloat16)])
+def test_sim_dense_vs_oracle(cg, Q, V, D, dtype):
+    ops.set_tuning(cta_group=cg)
+    r = synth.rng_for(1, "dense%d%d%d" % (Q, V, D))
+    q = cuda(r.standard_normal((Q, D)).astype(np.float32) / np.sqrt(D)).to(dtype)
+    g = cuda(r.standard_normal((V, D)).astype(np.float32) / np.sqrt(D)).to(dtype)
+    out = ops.sim_dense(q, g, 0.125)
+    ref = O.mm_mean_heads(q.float().cpu().numpy(), g.float().cpu().numpy(), 8)
+    assert out.shape == (Q, V)
+    assert sim_close(out, ref)
+
+
+def test_get_txt2vis_matrix_vs_reference_golden(golden):
+    d = golden("sim_eval.npz")
+    Q, H = 64, 8
+    model = M.W2VVPP(None)
+    t, v = cuda(d["q"]).view(Q, H, -1), cuda(d["g"]).view(Q, H, -1)
+    for prec, tol in (("bf16x3", 8e-6), ("fp16", 3e-4), ("bf16", 2e-3)):
+        L.set_precision(prec)
+        s = model.get_txt2vis_matrix(t, v)
+        assert max_abs(s, d["scores_fp32"]) <= tol, prec
+    # T1: bf16-representable embeddings in -> only accumulation order differs from the reference's fp32 mm.  The
+    # reference re-normalises the rounded vectors (loss.py:32); do the same normalisation in fp32 then compare.
+    L.set_precision("bf16x3")
+    s = model.get_txt2vis_matrix(cuda(d["q_bf16"]).view(Q, H, -1), cuda(d["g_bf16"]).view(Q, H, -1))
+    assert max_abs(s, d["scores_bf16"]) <= 8e-6
+    # 2-D embeddings and the static compute_sim + its error behaviour (model/model.py:1567-1578)
+    s2 = M.W2VVPP.compute_sim(t[:, 0, :].contiguous(), v[:, 0, :].contiguous(), "cosine")
+    assert max_abs(s2, O.cosine_sim(d["q"].reshape(Q, H, -1)[:, 0], d["g"].reshape(Q, H, -1)[:, 0])) <= 8e-6
+    with pytest.raises(Exception, match="invalid"):
+        M.W2VVPP.compute_sim(t, v, "nope")
+    with pytest.raises(Exception, match="Not implemented"):
+        M.W2VVPP.compute_sim(t, v, "euclidean")
+    # numpy-facing evaluation.cosine_sim / l2norm (evaluation.py:11-16, :44-50)
+    assert max_abs(E.cosine_sim(d["q"], d["g"]), d["np_cosine"]) <= 8e-6
+    assert max_abs(E.l2norm(d["l2_in"]), d["l2_numpy"]) <= 2e-7
+    assert max_abs(L.l2norm(cuda(d["l2_in"])), d["l2_torch"]) <= 2e-7
+    assert max_abs(L.l2norm(cuda(d["l2_in"]), eps=0), d["l2_torch_eps0"]) <= 2e-7
+
+
+def check_rank_against_dense(q16, g16, gt, k, col_offset=0):
+    """Fused sweep == tie rule applied (by the oracle, on CPU) to the kernel's own dense fp32 scores. Bit exact."""
+    gt_t = torch.from_numpy(gt).cuda()
+    dense = ops.sim_dense(q16, g16, 0.125)
+    sgt = ops.sim_gt_scores(q16, g16, gt_t.to(torch.int32))
+    assert torch.equal(sgt * 0.125, dense[torch.arange(len(gt), device="cuda"), gt_t]), "s_gt must be bit-identical to the sweep's score"
+    cnt, tv, ti = ops.sim_rank_topk(q16, g16, sgt, gt_t + col_offset, k, scale=0.125, col_offset=col_offset)
+    s = dense.cpu().numpy()
+    np.testing.assert_array_equal(cnt.cpu().numpy(), O.tie_rule_rank(s, gt))
+    if k:
+        ov, oi = O.tie_rule_topk(s, k)
+        kk = min(k, s.shape[1])
+        np.testing.assert_array_equal(ti.cpu().numpy()[:, :kk], oi[:, :kk] + col_offset)
+        np.testing.assert_array_equal(tv.cpu().numpy()[:, :kk], ov[:, :kk])
+        assert bool((ti[:, kk:] == -1).all()) and bool(torch.isinf(tv[:, kk:]).all())
+    r2, tv2, ti2 = ops.rank_from_scores(dense, gt_t, k)   # the materialised-matrix kernel obeys the same rule
+    np.testing.assert_array_equal(r2.cpu().numpy(), O.tie_rule_rank(s, gt))
+    if k:
+        np.testing.assert_array_equal(ti2.cpu().numpy()[:, :kk], oi[:, :kk])
+    return cnt, tv, ti, s
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("Q,V,k,chunk,mgroup", [(1000, 1000, 10, 1, 10), (2990, 2990, 10, 1, 10), (130, 5001, 16, 4, 3),
+                                               (64, 7, 10, 1, 1), (1, 300, 1, 2, 2), (700, 9000, 0, 16, 10)])
+def test_fused_rank_topk_exact(cg, Q, V, k, chunk, mgroup):
+    ops.set_tuning(cta_group=cg, chunk_tiles=chunk, m_group=mgroup)
+    q16, g16, gt = operands(5, Q, V)
+    if V > 600:  # plant exact ties with ground truths inside a tile, across tiles and at the last column
+        g16[5] = g16[int(gt[0])]
+        g16[V - 1] = g16[int(gt[1])]
+        g16[int(gt[2]) + 300] = g16[int(gt[2])]
+    cnt, tv, ti, s = check_rank_against_dense(q16, g16, gt, k)
+    lo, hi = O.rank_bounds(s, gt)
+    if V > 600:
+        assert (hi > lo).sum() >= 3  # the planted ties are real
+
+
+def test_rank_vs_fp64_oracle_scores():
+    """Against the oracle's own (fp64) scores on the same bf16 operands: identical ranks except where another score
+    lies within the fp32 accumulation noise of s_gt; those rows are enumerated and must stay inside the tie interval."""
+    Q, V = 500, 20000
+    q16, g16, gt = operands(6, Q, V, sigma=synth.sigma_for_recall(V, 4096))  # R@1 ~ 30%: ranks are non-trivial
+    gt_t = torch.from_numpy(gt).cuda()
+    sgt = ops.sim_gt_scores(q16, g16, gt_t.to(torch.int32))
+    cnt, tv, ti = ops.sim_rank_topk(q16, g16, sgt, gt_t, 10, scale=0.125)
+    s64 = O.mm_mean_heads(q16.float().cpu().numpy(), g16.float().cpu().numpy(), 8)
+    sg = s64[np.arange(Q), gt][:, None]
+    win = 2 * (2e-6 + 8e-6 * np.abs(sg))  # both s_gt and the competitor carry accumulation noise
+    near = (np.abs(s64 - sg) < win).sum(1) - 1
+    exact_rows = near == 0
+    assert exact_rows.mean() > 0.5 and 5 < (got_r1 := float((cnt == 0).float().mean()) * 100) < 95
+    ref = O.tie_rule_rank(s64, gt)
+    got = cnt.cpu().numpy()
+    np.testing.assert_array_equal(got[exact_rows], ref[exact_rows])
+    assert np.all(np.abs(got[~exact_rows] - ref[~exact_rows]) <= near[~exact_rows])
+    assert sim_close(tv, np.sort(s64, axis=1)[:, ::-1][:, :10])
+
+
+def test_metrics_kernels_vs_oracle_and_golden(golden):
+    d = golden("sim_eval.npz")
+    for name in ("odd", "even", "zeros", "big"):
+        rk = d["metrics_%s/rank0" % name]
+        m = ops.rank_metrics(cuda(rk.astype(np.int32))).cpu().numpy()
+        ref = O.metrics_from_rank0(rk)
+        np.testing.assert_array_equal(m[:4], ref[:4])                      # R@1/5/10, MedR: identical
+        np.testing.assert_allclose(m[4:6], ref[4:6], rtol=1e-13)           # MeanR, MIR
+        gold = d["metrics_%s/eval" % name]                                 # evaluation.eval on the label matrix
+        np.testing.assert_allclose([m[0], m[1], m[2], m[3], m[4], m[5]], gold[:6], rtol=1e-12)
+    r = synth.rng_for(2, "ranks").randint(0, 1000000, size=10000)
+    m = ops.rank_metrics(cuda(r.astype(np.int32))).cpu().numpy()
+    ref = O.metrics_from_rank0(r)
+    np.testing.assert_array_equal(m[:4], ref[:4])
+    np.testing.assert_allclose(m[4:6], ref[4:6], rtol=1e-13)
+    # drop-in evaluation.eval_qry2retro / eval on the reference's own score matrix
+    s = d["scores_bf16"]
+    got = E.eval_qry2retro(s, n_qry=1)
+    untied = np.array_equal(O.tie_rule_rank(s, np.arange(64)), d["rank0"])
+    exp = O.metrics_from_rank0(O.tie_rule_rank(s, np.arange(64)))
+    np.testing.assert_allclose(got, exp, rtol=1e-12)
+    if untied:
+        np.testing.assert_allclose(got, d["eval_qry2retro"], rtol=1e-12)
+    label = np.zeros_like(s)
+    label[np.arange(64), d["rank0"]] = 1
+    np.testing.assert_allclose(E.eval(label), d["eval_label"], rtol=1e-12)
+    multi = np.zeros((3, 50))
+    multi[0, [2, 5, 40]] = 1
+    multi[1, [0]] = 1
+    multi[2, [49, 10]] = 1
+    np.testing.assert_allclose(E.eval(multi), O.eval_label_matrix(multi), rtol=1e-12)
+    with pytest.raises(IndexError):
+        E.eval(np.zeros((2, 5)))
+
+
+def test_gallery_sharding_is_exact_on_one_gpu():
+    """Two and three gallery shards evaluated one after the other on this GPU and combined the way the NCCL path
+    combines them (sum of s_gt, sum of counts, k-way merge) == the single-shard answer, bit for bit."""
+    Q, V, k = 300, 7001, 10
+    q16, g16, gt = operands(8, Q, V)
+    g16[V - 1] = g16[int(gt[3])]
+    gt_t = torch.from_numpy(gt).cuda().to(torch.int32)
+    single = GalleryIndex(g16, V, 8).search(q16, gt_t, k)
+    for W in (2, 3):
+        sgt = torch.zeros(Q, device="cuda")
+        parts = []
+        for r in range(W):
+            lo, hi = shard_bounds(V, W, r)
+            owned = (gt_t >= lo) & (gt_t < hi)
+            sgt += ops.sim_gt_scores(q16, g16[lo:hi], torch.where(owned, gt_t - lo, torch.full_like(gt_t, -1)))
+        cnt = torch.zeros(Q, dtype=torch.int32, device="cuda")
+        for r in range(W):
+            lo, hi = shard_bounds(V, W, r)
+            c, tv, ti = ops.sim_rank_topk(q16, g16[lo:hi], sgt, gt_t, k, scale=0.125, col_offset=lo)
+            cnt += c
+            parts.append((tv, ti))
+        mv, mi = ops.topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
+        assert torch.equal(cnt, single.rank0)
+        assert torch.equal(mi, single.topk_idx) and torch.equal(mv, single.topk_val)
+    m = single.metrics.cpu().numpy()
+    np.testing.assert_array_equal(m[:4], O.metrics_from_rank0(single.rank0.cpu().numpy())[:4])
+
+
+@pytest.mark.parametrize("V", [1000000])
+def test_full_size_properties(V):
+    """BASELINE config C5 (10 000 queries x 1 000 000 videos): properties that do not need the 40 GB score matrix."""
+    Q, k = 10000, 10
+    H, dh = 8, 512
+    gen = torch.Generator(device="cuda").manual_seed(123)
+    g16 = torch.empty(V, H * dh, dtype=torch.bfloat16, device="cuda")
+    for s in range(0, V, 131072):
+        n = min(131072, V - s)
+        x = torch.randn(n, H, dh, generator=gen, device="cuda")
+        g16[s:s + n] = (x / x.norm(dim=2, keepdim=True)).reshape(n, -1).to(torch.bfloat16)
+    gt = (torch.arange(Q, device="cuda") * 97) % V
+    x = torch.randn(Q, H, dh, generator=gen, device="cuda")
+    sigma = synth.sigma_for_recall(V, H * dh)   # R@1 ~ 30%
+    qf = g16[gt].float().view(Q, H, dh) + sigma * x / x.norm(dim=2, keepdim=True)
+    q16 = (qf / qf.norm(dim=2, keepdim=True)).reshape(Q, -1).to(torch.bfloat16)
+    g16[V - 1] = g16[gt[11]]  # exact tie at the far end of the gallery
+    res = GalleryIndex(g16, V, H).search(q16, gt.to(torch.int32), k)
+    rank0, tv, ti = res.rank0, res.topk_val, res.topk_idx
+    # (1) top-k lists are ordered by the tie rule, indices unique and in range
+    assert bool((tv[:, :-1] >= tv[:, 1:]).all())
+    assert int(ti.min()) >= 0 and int(ti.max()) < V
+    assert bool((torch.sort(ti, 1).values[:, 1:] != torch.sort(ti, 1).values[:, :-1]).all())
+    # (2) rank0 and top-k agree: rank0 < k  <=>  the ground truth sits at position rank0 of the list
+    pos = (ti == gt[:, None].to(torch.int32)).float().argmax(1)
+    has = (ti == gt[:, None].to(torch.int32)).any(1)
+    assert torch.equal(has, rank0 < k)
+    assert torch.equal(pos[has].to(torch.int32), rank0[has])
+    assert int(rank0[11]) >= 1  # the planted tie has the higher index, so it outranks the ground truth
+    # (3) a subsample checked exactly against the dense kernel + oracle tie rule
+    sub = torch.arange(0, Q, 157, device="cuda")[:64]
+    dense = ops.sim_dense(q16[sub], g16, 1.0 / H)
+    r_sub, _, ti_sub = ops.rank_from_scores(dense, gt[sub].to(torch.int32), k)
+    assert torch.equal(r_sub, rank0[sub]) and torch.equal(ti_sub, ti[sub])
+    s = dense[:8].cpu().numpy()
+    np.testing.assert_array_equal(rank0[sub][:8].cpu().numpy(), O.tie_rule_rank(s, gt[sub][:8].cpu().numpy()))
+    # (4) sharding invariance at full size: two halves combine to the same answer
+    sgt = ops.sim_gt_scores(q16, g16, gt.to(torch.int32))
+    half = V // 2
+    c0, v0, i0 = ops.sim_rank_topk(q16, g16[:half], sgt, gt.to(torch.int32), k, scale=1.0 / H, col_offset=0)
+    c1, v1, i1 = ops.sim_rank_topk(q16, g16[half:], sgt, gt.to(torch.int32), k, scale=1.0 / H, col_offset=half)
+    assert torch.equal(c0 + c1, rank0)
+    mv, mi = ops.topk_merge(torch.stack([v0, v1]), torch.stack([i0, i1]), k)
+    assert torch.equal(mi, ti) and torch.equal(mv, tv)
+    # (5) metrics are consistent with the ranks
+    m = res.metrics.cpu().numpy()
+    np.testing.assert_array_equal(m[:4], O.metrics_from_rank0(rank0.cpu().numpy())[:4])
+    assert 5.0 < m[0] < 95.0 and m[0] <= m[1] <= m[2]

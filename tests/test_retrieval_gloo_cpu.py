@@ -1,0 +1,109 @@
+"""Host-side logic of the gallery-sharded search on CPU: shard arithmetic and the three collectives over gloo with
+world_size 2 and 3, with a numpy stand-in for the CUDA kernels (built from the oracle — test infrastructure only)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from laff_b200 import synth
+from laff_b200.retrieval import GalleryIndex, shard_bounds
+from oracle import laff_oracle as O
+
+
+class NumpyBackend:
+    """CPU stand-in with the same contract as laff_b200.retrieval.CudaBackend."""
+
+    def gt_scores(self, q16, g16, gt_local):
+        q, g, gl = q16.float().numpy().astype(np.float64), g16.float().numpy().astype(np.float64), gt_local.numpy()
+        s = np.where(gl >= 0, np.einsum("ij,ij->i", q, g[np.maximum(gl, 0)]), 0.0)
+        return torch.from_numpy(s.astype(np.float32))
+
+    def rank_topk(self, q16, g16, sgt_raw, gt_global, k, scale, col_offset, workspace=None):
+        s = (q16.float().numpy().astype(np.float64) @ g16.float().numpy().astype(np.float64).T).astype(np.float32)
+        sg = sgt_raw.numpy()[:, None]
+        cols = np.arange(s.shape[1])[None, :] + col_offset
+        gt = gt_global.numpy()[:, None]
+        beats = ((s > sg) | ((s == sg) & (cols > gt))) & (cols != gt)
+        count = torch.from_numpy(beats.sum(1).astype(np.int32))
+        order = np.lexsort((-cols.repeat(s.shape[0], 0), -s), axis=1)[:, :k]  # score desc, index desc
+        tv = np.take_along_axis(s, order, 1) * scale
+        ti = order + col_offset
+        if tv.shape[1] < k:
+            pad = k - tv.shape[1]
+            tv = np.concatenate([tv, np.full((s.shape[0], pad), -np.inf, np.float32)], 1)
+            ti = np.concatenate([ti, np.full((s.shape[0], pad), -1)], 1)
+        return count, torch.from_numpy(tv.astype(np.float32)), torch.from_numpy(ti.astype(np.int32))
+
+    def merge(self, vals, idx, k):
+        v = vals.numpy().transpose(1, 0, 2).reshape(vals.shape[1], -1)
+        i = idx.numpy().transpose(1, 0, 2).reshape(vals.shape[1], -1)
+        order = np.lexsort((-i, -v), axis=1)[:, :k]
+        return torch.from_numpy(np.take_along_axis(v, order, 1)), torch.from_numpy(np.take_along_axis(i, order, 1))
+
+    def metrics(self, rank0):
+        m = O.metrics_from_rank0(rank0.numpy())
+        return torch.tensor(list(m) + [m[5], float(len(rank0))], dtype=torch.float64)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _problem(Q=48, V=301, H=4, dh=16):
+    q, g, gt = synth.retrieval_embeddings(77, Q, V, H, dh, sigma=1.5)
+    g[13] = g[gt[5]]  # exact tie with a ground truth, across shard boundaries for W >= 2
+    g[V - 1] = g[gt[7]]
+    return synth.bf16_round(q), synth.bf16_round(g), gt, H
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q, g, gt, H = _problem()
+        lo, hi = shard_bounds(g.shape[0], world, rank)
+        idx = GalleryIndex(torch.from_numpy(g[lo:hi]).to(torch.bfloat16), g.shape[0], H, rank, world, backend=NumpyBackend())
+        res = idx.search(torch.from_numpy(q).to(torch.bfloat16), torch.from_numpy(gt), k=7)
+        if rank == 0:
+            torch.save({"rank0": res.rank0, "tv": res.topk_val, "ti": res.topk_idx, "m": res.metrics}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_search_equals_single_shard(world, tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got = torch.load(out)
+    q, g, gt, H = _problem()
+    single = GalleryIndex(torch.from_numpy(g).to(torch.bfloat16), g.shape[0], H, backend=NumpyBackend())
+    ref = single.search(torch.from_numpy(q).to(torch.bfloat16), torch.from_numpy(gt), k=7)
+    assert torch.equal(got["rank0"], ref.rank0)
+    assert torch.equal(got["ti"], ref.topk_idx)
+    assert torch.allclose(got["tv"], ref.topk_val, atol=0, rtol=0)
+    assert torch.equal(got["m"], ref.metrics)
+    # and the single-shard answer is the oracle's tie-rule answer on the same operands
+    s = (O.mm_mean_heads(q, g, H)).astype(np.float32)
+    np.testing.assert_array_equal(ref.rank0.numpy(), O.tie_rule_rank(s, gt))
+    np.testing.assert_array_equal(ref.topk_idx.numpy(), O.tie_rule_topk(s, 7)[1])
+
+
+def test_shard_bounds_cover_the_gallery():
+    for V in (0, 1, 7, 8, 1000000):
+        for W in (1, 2, 3, 8):
+            spans = [shard_bounds(V, W, r) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == V
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            assert all(lo <= hi for lo, hi in spans)
+
+
+def test_gallery_index_rejects_wrong_shard():
+    with pytest.raises(ValueError):
+        GalleryIndex(torch.zeros(5, 8), 100, 2, rank=0, world_size=2, backend=NumpyBackend())
