@@ -73,6 +73,7 @@ class GalleryIndex:
         self.lo, self.hi = lo, hi
         self.backend = backend or CudaBackend()
         self._ws = None
+        self.timers = None  # set to a list to collect (start, end) CUDA events around every sweep launch
 
     def _all_reduce(self, t):
         if self.world_size > 1:
@@ -93,7 +94,13 @@ class GalleryIndex:
             sgt = torch.zeros(q16.shape[0], dtype=torch.float32, device=q16.device)
         sgt = self._all_reduce(sgt)
         if n_local > 0:
+            if self.timers is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             count, tv, ti = be.rank_topk(q16, self.g16, sgt, gt_global, k, scale, self.lo, self._ws)
+            if self.timers is not None:
+                e1.record()
+                self.timers.append((e0, e1))
         else:
             Q = q16.shape[0]
             count = torch.zeros(Q, dtype=torch.int32, device=q16.device)
