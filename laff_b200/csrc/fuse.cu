@@ -108,15 +108,24 @@ __global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restr
 // ------------------------------------------------------------------------------------------------------------
 // F1: projection epilogue  y = BN(act(acc + bias))
 // ------------------------------------------------------------------------------------------------------------
+// tanh(z) = 1 - 2 / (exp(2z) + 1) with the hardware ex2 / rcp approximations: |error| < 3e-7 absolute over the whole
+// range (the reference's tanh output feeds a unit-norm embedding compared at 2e-6), 5 instructions instead of ~40.
+__device__ __forceinline__ float tanh_fast(float z) {
+  const float e = __expf(2.0f * z);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
 __device__ __forceinline__ float activate(float z, int act) {
   switch (act) {
-    case LAFF_ACT_TANH: return tanhf(z);
+    case LAFF_ACT_TANH: return tanh_fast(z);
     case LAFF_ACT_RELU: return fmaxf(z, 0.f);
-    case LAFF_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));
+    case LAFF_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-z));
     default: return z;
   }
 }
 
+// Projection epilogue.  The accumulator arrives one row per thread (TMEM lane = row); each warp transposes its
+// 32 x 32 chunk through a padded shared-memory tile so that a lane owns one output column: the per-column bias / BN
+// parameters become three registers per lane and every global store is a fully coalesced 128-byte row segment.
 struct EpiProject {
   struct Params {
     float* y;
@@ -128,40 +137,65 @@ struct EpiProject {
     const float* bn_shift;
     int act;
   };
-  static constexpr int kSmemBytes = 0;
+  static constexpr int kTile = 32 * 33;
+  static constexpr int kSmemBytes = kEpiWarps * kTile * 4;
   Params p;
-  __device__ EpiProject(const Params& p_, uint8_t*, int) : p(p_) {}
+  float* tile;
+  int lane;
+  __device__ EpiProject(const Params& p_, uint8_t* smem, int epi_tid) : p(p_) {
+    tile = reinterpret_cast<float*>(smem) + (epi_tid >> 5) * kTile;
+    lane = epi_tid & 31;
+  }
   __device__ __forceinline__ void unit_begin(int, const Unit&) {}
   __device__ __forceinline__ void unit_end(int, const Unit&) {}
   __device__ __forceinline__ void chunk(const uint32_t (&r)[32], int row, int col0) {
-    if (row >= p.M || col0 >= p.N) return;
-    float* dst = p.y + static_cast<long long>(row) * p.ldy + col0;
-    const bool full = (col0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-    float o[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int c = min(col0 + j, p.N - 1);
-      float z = __uint_as_float(r[j]);
-      if (p.bias) z += __ldg(p.bias + c);
+    for (int j = 0; j < 32; ++j) tile[j * 33 + lane] = __uint_as_float(r[j]);  // tile[col][row]
+    __syncwarp();
+    const int col = col0 + lane;
+    const bool cok = col < p.N;
+    const float b = (cok && p.bias) ? __ldg(p.bias + col) : 0.f;
+    const float sc = (cok && p.bn_scale) ? __ldg(p.bn_scale + col) : 1.f;
+    const float sh = (cok && p.bn_shift) ? __ldg(p.bn_shift + col) : 0.f;
+    const int row0 = row - lane;
+    float* dst = p.y + static_cast<long long>(row0) * p.ldy + col;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      float z = tile[lane * 33 + i] + b;
       z = activate(z, p.act);
-      if (p.bn_scale) z = fmaf(z, __ldg(p.bn_scale + c), __ldg(p.bn_shift + c));
-      o[j] = z;
+      z = fmaf(z, sc, sh);
+      if (cok && row0 + i < p.M) dst[static_cast<long long>(i) * p.ldy] = z;
     }
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) dst[j] = o[j];
-    }
+    __syncwarp();
   }
 };
 
 // ------------------------------------------------------------------------------------------------------------
-// F5/F6: LAFF block.  One warp per (row, head); lane owns elements d = lane + 32*t of the head.
+// F5/F6: LAFF block.  One warp per (row, head).  A lane owns VPL elements of the head:
+//   VEC  : 4 consecutive elements at 4*lane + 128*q (128-bit loads / stores; head_dim % 128 == 0, 16-byte aligned rows)
+//   !VEC : elements lane + 32*t (any head_dim % 32 == 0)
+// All L feature slices of the head are held in registers (LMAX * VPL values), so every input byte is read once.
 // ------------------------------------------------------------------------------------------------------------
-template <int VPL>  // values per lane = head_dim / 32
+template <int VPL, bool VEC>
+__device__ __forceinline__ int pool_elem(int lane, int t) {
+  return VEC ? (4 * lane + 128 * (t >> 2) + (t & 3)) : (lane + 32 * t);
+}
+
+template <int VPL, bool VEC>
+__device__ __forceinline__ void pool_load(const float* __restrict__ p, int lane, float (&v)[VPL]) {
+  if constexpr (VEC) {
+#pragma unroll
+    for (int q = 0; q < VPL / 4; ++q) {
+      const float4 x = *reinterpret_cast<const float4*>(p + 4 * lane + 128 * q);
+      v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) v[t] = p[lane + 32 * t];
+  }
+}
+
+template <int VPL, int LMAX, bool VEC>
 __global__ void __launch_bounds__(128) attention_pool_kernel(laff_pool_desc d, long long rows, float* __restrict__ out,
                                                             long long ld_out, void* __restrict__ out16, int out16_dtype,
                                                             long long ld_out16, float* __restrict__ att) {
@@ -174,28 +208,37 @@ __global__ void __launch_bounds__(128) attention_pool_kernel(laff_pool_desc d, l
   const int dh = d.head_dim;
   const int L = d.n_features;
 
-  float y[LAFF_MAX_FEATURES][VPL];
-  float w[VPL];
+  float y[LMAX][VPL];
 #pragma unroll
-  for (int t = 0; t < VPL; ++t) w[t] = __ldg(d.att_weight + static_cast<long long>(h) * dh + lane + 32 * t);
-
-#pragma unroll
-  for (int l = 0; l < LAFF_MAX_FEATURES; ++l) {
+  for (int l = 0; l < LMAX; ++l) {
     if (l < L) {
       const laff_pool_source& s = d.src[l];
       if (s.kind == 0) {
-        const float* p = s.src + row * s.ld + static_cast<long long>(h) * dh;
-#pragma unroll
-        for (int t = 0; t < VPL; ++t) y[l][t] = p[lane + 32 * t];
+        pool_load<VPL, VEC>(s.src + row * s.ld + static_cast<long long>(h) * dh, lane, y[l]);
       } else {
         // "no-transform": x tiled along D (x.repeat(1, heads)), then BatchNorm1d(D)   model/model.py:1822-1823
         const float* p = s.src + row * s.ld;
+        if constexpr (VEC) {
 #pragma unroll
-        for (int t = 0; t < VPL; ++t) {
-          const int col = h * dh + lane + 32 * t;
-          float v = p[col % s.in_dim];
-          if (s.bn_scale) v = fmaf(v, __ldg(s.bn_scale + col), __ldg(s.bn_shift + col));
-          y[l][t] = v;
+          for (int q = 0; q < VPL / 4; ++q) {
+            const int col = h * dh + 4 * lane + 128 * q;
+            const float4 x = *reinterpret_cast<const float4*>(p + col % s.in_dim);  // in_dim % 4 == 0: never wraps
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s.bn_scale) {
+              sc = __ldg(reinterpret_cast<const float4*>(s.bn_scale + col));
+              sh = __ldg(reinterpret_cast<const float4*>(s.bn_shift + col));
+            }
+            y[l][4 * q] = fmaf(x.x, sc.x, sh.x); y[l][4 * q + 1] = fmaf(x.y, sc.y, sh.y);
+            y[l][4 * q + 2] = fmaf(x.z, sc.z, sh.z); y[l][4 * q + 3] = fmaf(x.w, sc.w, sh.w);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < VPL; ++t) {
+            const int col = h * dh + lane + 32 * t;
+            float v = p[col % s.in_dim];
+            if (s.bn_scale) v = fmaf(v, __ldg(s.bn_scale + col), __ldg(s.bn_shift + col));
+            y[l][t] = v;
+          }
         }
       }
     } else {
@@ -203,6 +246,8 @@ __global__ void __launch_bounds__(128) attention_pool_kernel(laff_pool_desc d, l
       for (int t = 0; t < VPL; ++t) y[l][t] = 0.f;
     }
   }
+  float w[VPL];
+  pool_load<VPL, VEC>(d.att_weight + static_cast<long long>(h) * dh, lane, w);
 
   // raw_global_emb = mean over features (Attention.py:81)
   float mean[VPL];
@@ -211,17 +256,17 @@ __global__ void __launch_bounds__(128) attention_pool_kernel(laff_pool_desc d, l
   for (int t = 0; t < VPL; ++t) {
     float s = 0.f;
 #pragma unroll
-    for (int l = 0; l < LAFF_MAX_FEATURES; ++l)
+    for (int l = 0; l < LMAX; ++l)
       if (l < L) s += y[l][t];
     mean[t] = s * invL;
   }
 
   // logits e_l = w_h . common_l + c_h  (Attention.py:88), common = local (* mean if mul, Attention.py:83-86)
-  float e[LAFF_MAX_FEATURES];
+  float e[LMAX];
   const float cb = __ldg(d.att_bias + h);
   float emax = -INFINITY;
 #pragma unroll
-  for (int l = 0; l < LAFF_MAX_FEATURES; ++l) {
+  for (int l = 0; l < LMAX; ++l) {
     if (l < L) {
       float s = 0.f;
 #pragma unroll
@@ -235,7 +280,7 @@ __global__ void __launch_bounds__(128) attention_pool_kernel(laff_pool_desc d, l
   // softmax over features (Attention.py:89)
   float z = 0.f;
 #pragma unroll
-  for (int l = 0; l < LAFF_MAX_FEATURES; ++l) {
+  for (int l = 0; l < LMAX; ++l) {
     if (l < L) {
       e[l] = expf(e[l] - emax);
       z += e[l];
@@ -249,7 +294,7 @@ __global__ void __launch_bounds__(128) attention_pool_kernel(laff_pool_desc d, l
   for (int t = 0; t < VPL; ++t) {
     float s = 0.f;
 #pragma unroll
-    for (int l = 0; l < LAFF_MAX_FEATURES; ++l)
+    for (int l = 0; l < LMAX; ++l)
       if (l < L) s = fmaf(e[l] * invz, y[l][t], s);
     if (d.with_ave) s = fmaf(d.omega, mean[t] * static_cast<float>(L), s);  // sum_l omega * raw_global_emb
     g[t] = s;
@@ -258,15 +303,31 @@ __global__ void __launch_bounds__(128) attention_pool_kernel(laff_pool_desc d, l
   ss = warp_sum(ss);
   const float den = sqrtf(ss) + static_cast<float>(d.norm_eps);  // l2norm(eps=0): + 0 + 1e-14  (Attention.py:103)
 #pragma unroll
-  for (int t = 0; t < VPL; ++t) {
-    const float v = g[t] / den;
-    const long long c = static_cast<long long>(h) * dh + lane + 32 * t;
-    if (out) out[row * ld_out + c] = v;
-    if (out16) static_cast<uint16_t*>(out16)[row * ld_out16 + c] = to16(v, out16_dtype);
+  for (int t = 0; t < VPL; ++t) g[t] = g[t] / den;
+  const long long c0 = static_cast<long long>(h) * dh;
+  if constexpr (VEC) {
+#pragma unroll
+    for (int q = 0; q < VPL / 4; ++q) {
+      const long long c = c0 + 4 * lane + 128 * q;
+      if (out) *reinterpret_cast<float4*>(out + row * ld_out + c) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+      if (out16) {
+        uint2 pk;
+        pk.x = static_cast<uint32_t>(to16(g[4 * q], out16_dtype)) | (static_cast<uint32_t>(to16(g[4 * q + 1], out16_dtype)) << 16);
+        pk.y = static_cast<uint32_t>(to16(g[4 * q + 2], out16_dtype)) | (static_cast<uint32_t>(to16(g[4 * q + 3], out16_dtype)) << 16);
+        *reinterpret_cast<uint2*>(static_cast<uint16_t*>(out16) + row * ld_out16 + c) = pk;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+      const long long c = c0 + lane + 32 * t;
+      if (out) out[row * ld_out + c] = g[t];
+      if (out16) static_cast<uint16_t*>(out16)[row * ld_out16 + c] = to16(g[t], out16_dtype);
+    }
   }
   if (att && lane == 0) {
 #pragma unroll
-    for (int l = 0; l < LAFF_MAX_FEATURES; ++l)
+    for (int l = 0; l < LMAX; ++l)
       if (l < L) {
         float a = e[l] * invz;
         if (d.with_ave) a += d.omega / static_cast<float>(L);  // Attention.py:97
@@ -485,12 +546,29 @@ int laff_attention_pool(const laff_pool_desc* desc, long long rows, float* out, 
   LAFF_REQUIRE(blocks < (1LL << 31), LAFF_ENOTSUP, "laff_attention_pool: too many rows");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int dh = desc->head_dim;
+  LAFF_REQUIRE(dh % 32 == 0, LAFF_ENOTSUP, "laff_attention_pool: head_dim %d must be a multiple of 32", dh);
+  // 128-bit path: head_dim % 128 == 0 and every pointer / pitch 16-byte aligned
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  bool vec = dh % 128 == 0 && al16(desc->att_weight) && (!out || (al16(out) && ld_out % 4 == 0)) &&
+             (!out16 || ((reinterpret_cast<uintptr_t>(out16) & 7) == 0 && ld_out16 % 4 == 0));
+  for (int l = 0; l < desc->n_features && vec; ++l) {
+    const laff_pool_source& s = desc->src[l];
+    vec = al16(s.src) && s.ld % 4 == 0;
+    if (s.kind == 1) vec = vec && s.in_dim % 4 == 0 && (!s.bn_scale || (al16(s.bn_scale) && al16(s.bn_shift)));
+  }
+  const int L = desc->n_features;
+#define LAFF_POOL_LAUNCH(V, LM, VE)                                                                                    \
+  attention_pool_kernel<V, LM, VE><<<static_cast<unsigned>(blocks), block, 0, st>>>(*desc, rows, out, ld_out, out16,     \
+                                                                                    out16_dtype, ld_out16, att)
 #define LAFF_POOL_CASE(V)                                                                                              \
   case V:                                                                                                              \
-    attention_pool_kernel<V><<<static_cast<unsigned>(blocks), block, 0, st>>>(*desc, rows, out, ld_out, out16,          \
-                                                                              out16_dtype, ld_out16, att); laff::count_launch();             \
+    if (vec && V >= 4) {                                                                                               \
+      if (L <= 4) LAFF_POOL_LAUNCH((V >= 4 ? V : 4), 4, true);                                                         \
+      else LAFF_POOL_LAUNCH((V >= 4 ? V : 4), 8, true);                                                                \
+    } else {                                                                                                           \
+      LAFF_POOL_LAUNCH(V, 8, false);                                                                                   \
+    }                                                                                                                  \
     break;
-  LAFF_REQUIRE(dh % 32 == 0, LAFF_ENOTSUP, "laff_attention_pool: head_dim %d must be a multiple of 32", dh);
   switch (dh / 32) {
     LAFF_POOL_CASE(1)
     LAFF_POOL_CASE(2)
@@ -500,6 +578,7 @@ int laff_attention_pool(const laff_pool_desc* desc, long long rows, float* out, 
     default:
       LAFF_REQUIRE(false, LAFF_ENOTSUP, "laff_attention_pool: head_dim %d not in {32,64,128,256,512}", dh);
   }
+#undef LAFF_POOL_LAUNCH
 #undef LAFF_POOL_CASE
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
