@@ -451,34 +451,63 @@ __global__ void rank_from_scores_kernel(const float* __restrict__ scores, int V,
   }
 }
 
-// Single block.  Order statistics by a 31-step bitwise descent (ranks are non-negative int32), sums in fp64.
-__device__ int block_kth_smallest(const int32_t* __restrict__ x, int n, int kth, int* s_red) {
-  // returns the value v such that #(x < v) <= kth < #(x <= v)
-  int prefix = 0;
-  int remaining = kth;  // index among the elements that match the prefix so far
+// Single block.  Two order statistics at once by a 31-step bitwise descent (ranks are non-negative int32); each thread
+// keeps up to kMetricCache of its elements in registers so a pass costs two warp reductions and one barrier pair.
+constexpr int kMetricCache = 16;
+__device__ void block_two_order_stats(const int32_t* __restrict__ x, int n, int kth_a, int kth_b, int* s_red, int& out_a,
+                                      int& out_b) {
+  int cache[kMetricCache];
+  const bool cached = n <= kMetricCache * static_cast<int>(blockDim.x);
+#pragma unroll
+  for (int j = 0; j < kMetricCache; ++j) {
+    const int i = threadIdx.x + j * blockDim.x;
+    cache[j] = (cached && i < n) ? x[i] : -1;  // -1 never matches a prefix of non-negative values
+  }
+  int pa = 0, pb = 0, ra = kth_a, rb = kth_b;
+  const int nw = blockDim.x >> 5;
   for (int bit = 30; bit >= 0; --bit) {
     const int mask_hi = static_cast<int>(~((1u << (bit + 1)) - 1u));  // bits above `bit`
-    int c0 = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int v = x[i];
-      c0 += (((v & mask_hi) == (prefix & mask_hi)) && !((v >> bit) & 1)) ? 1 : 0;
+    int ca = 0, cb = 0;
+    if (cached) {
+#pragma unroll
+      for (int j = 0; j < kMetricCache; ++j) {
+        const int v = cache[j];
+        const bool zero = v >= 0 && !((v >> bit) & 1);
+        ca += (zero && (v & mask_hi) == (pa & mask_hi)) ? 1 : 0;
+        cb += (zero && (v & mask_hi) == (pb & mask_hi)) ? 1 : 0;
+      }
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int v = x[i];
+        const bool zero = !((v >> bit) & 1);
+        ca += (zero && (v & mask_hi) == (pa & mask_hi)) ? 1 : 0;
+        cb += (zero && (v & mask_hi) == (pb & mask_hi)) ? 1 : 0;
+      }
     }
-    for (int off = 16; off > 0; off >>= 1) c0 += __shfl_xor_sync(0xffffffffu, c0, off);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = c0;
-    __syncthreads();
-    int tot = 0;
-    for (int i = 0; i < (blockDim.x >> 5); ++i) tot += s_red[i];
-    if (remaining >= tot) {
-      remaining -= tot;
-      prefix |= (1 << bit);
+    for (int off = 16; off > 0; off >>= 1) {
+      ca += __shfl_xor_sync(0xffffffffu, ca, off);
+      cb += __shfl_xor_sync(0xffffffffu, cb, off);
     }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      s_red[threadIdx.x >> 5] = ca;
+      s_red[32 + (threadIdx.x >> 5)] = cb;
+    }
+    __syncthreads();
+    int ta = 0, tb = 0;
+    for (int i = 0; i < nw; ++i) {
+      ta += s_red[i];
+      tb += s_red[32 + i];
+    }
+    if (ra >= ta) { ra -= ta; pa |= (1 << bit); }
+    if (rb >= tb) { rb -= tb; pb |= (1 << bit); }
   }
-  return prefix;
+  out_a = pa;
+  out_b = pb;
 }
 
 __global__ void rank_metrics_kernel(const int32_t* __restrict__ rank0, int Q, double* __restrict__ out) {
-  __shared__ int s_red[32];
+  __shared__ int s_red[64];
   __shared__ double s_d[32][4];
   int c1 = 0, c5 = 0, c10 = 0;
   double sum_r = 0.0, sum_inv = 0.0;
@@ -503,8 +532,8 @@ __global__ void rank_metrics_kernel(const int32_t* __restrict__ rank0, int Q, do
     tot[t] = a;
   }
   // np.median: middle element (odd Q) or the mean of the two middle elements (even Q)
-  const int lo = block_kth_smallest(rank0, Q, (Q - 1) / 2, s_red);
-  const int hi = block_kth_smallest(rank0, Q, Q / 2, s_red);
+  int lo, hi;
+  block_two_order_stats(rank0, Q, (Q - 1) / 2, Q / 2, s_red, lo, hi);
   if (threadIdx.x == 0) {
     const double q = static_cast<double>(Q);
     const double med = 0.5 * (static_cast<double>(lo) + static_cast<double>(hi));

@@ -126,8 +126,30 @@ class Retriever:
         self.out16_dtype = out16_dtype
 
     @torch.no_grad()
+    def encode_queries(self, caption_feat_dict) -> torch.Tensor:
+        """Fused 16-bit query embeddings [Q, H*d_h], replicated on every rank.  With W > 1 ranks each rank fuses only
+        its 1/W slice of the queries (the fusion is data-parallel per item) and the slices are all-gathered over
+        NVLink, so the replicated part of a step shrinks with W."""
+        idx = self.index
+        W, r = idx.world_size, idx.rank
+        if W == 1:
+            _, q16 = self.txt_net.encode(caption_feat_dict, out16_dtype=self.out16_dtype)
+            return q16.reshape(q16.shape[0], -1)
+        Q = next(iter(caption_feat_dict.values())).shape[0]
+        per = (Q + W - 1) // W
+        lo, hi = min(Q, r * per), min(Q, (r + 1) * per)
+        part = {k: v[lo:hi] for k, v in caption_feat_dict.items()}
+        _, q16 = self.txt_net.encode(part, out16_dtype=self.out16_dtype)
+        q16 = q16.reshape(hi - lo, -1)
+        D = q16.shape[1]
+        buf = torch.zeros((per, D), dtype=q16.dtype, device=q16.device)
+        buf[: hi - lo] = q16
+        out = torch.empty((W * per, D), dtype=q16.dtype, device=q16.device)
+        dist.all_gather_into_tensor(out, buf, group=idx.group)
+        return out[:Q]
+
+    @torch.no_grad()
     def rank(self, caption_feat_dict, gt_global, k: int = 10) -> SearchResult:
         """caption_feat_dict: per-encoder text features (host or device tensors); gt_global: int [Q]."""
-        _, q16 = self.txt_net.encode(caption_feat_dict, out16_dtype=self.out16_dtype)
-        dev = q16.device
-        return self.index.search(q16.reshape(q16.shape[0], -1), gt_global.to(dev, non_blocking=True), k)
+        q16 = self.encode_queries(caption_feat_dict)
+        return self.index.search(q16, gt_global.to(q16.device, non_blocking=True), k)

@@ -1,0 +1,54 @@
+"""Multi-GPU parity of the gallery-sharded search (run under torchrun on 2/4/8 GPUs of one box):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 \
+        tools/check_multigpu.py
+
+Every rank builds the same synthetic problem, holds its shard, and runs GalleryIndex.search over NCCL; rank 0 also runs
+the single-shard search on the whole gallery and requires bit-identical rank0 / top-k / metrics.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from laff_b200 import synth  # noqa: E402
+from laff_b200.retrieval import GalleryIndex, shard_bounds  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    Q, V, H, dh, k = 1500, 100003, 8, 512, 10
+    gen = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(V, H, dh, generator=gen, device=dev)
+    g16 = (x / x.norm(dim=2, keepdim=True)).reshape(V, -1).to(torch.bfloat16)
+    gt = (torch.arange(Q, device=dev) * 97) % V
+    n = torch.randn(Q, H, dh, generator=gen, device=dev)
+    qf = g16[gt].float().view(Q, H, dh) + synth.sigma_for_recall(V, H * dh) * n / n.norm(dim=2, keepdim=True)
+    q16 = (qf / qf.norm(dim=2, keepdim=True)).reshape(Q, -1).to(torch.bfloat16)
+    g16[V - 1] = g16[gt[3]]
+    g16[7] = g16[gt[9]]
+    lo, hi = shard_bounds(V, world, rank)
+    res = GalleryIndex(g16[lo:hi].contiguous(), V, H, rank, world).search(q16, gt.to(torch.int32), k)
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        ref = GalleryIndex(g16, V, H).search(q16, gt.to(torch.int32), k)
+        ok = (torch.equal(res.rank0, ref.rank0) and torch.equal(res.topk_idx, ref.topk_idx)
+              and torch.equal(res.topk_val, ref.topk_val) and torch.equal(res.metrics, ref.metrics))
+        print("multi-GPU parity world=%d: %s  R@1=%.2f R@10=%.2f MedR=%.0f" % (
+            world, "OK" if ok else "MISMATCH", ref.metrics[0].item(), ref.metrics[2].item(), ref.metrics[3].item()), flush=True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
