@@ -38,6 +38,8 @@ extern "C" {
 
 #define LAFF_MAX_FEATURES 8
 #define LAFF_MAX_TOPK 16
+#define LAFF_FUSE_MAX_FC 4
+#define LAFF_FUSE_MAX_TILED 2
 
 #define LAFF_ACT_NONE 0
 #define LAFF_ACT_TANH 1
@@ -190,6 +192,44 @@ typedef struct {
 
 int laff_attention_pool(const laff_pool_desc* desc, long long rows, float* out, long long ld_out, void* out16,
                         int out16_dtype, long long ld_out16, float* att, void* stream);
+
+/* F1-F6 in ONE kernel: every FC projection (tcgen05 GEMM) + bias + activation + eval-BN + per-head attention logits +
+ *     softmax over features + weighted sum + L2 normalise; the projected features never reach HBM.  Covers the shipped
+ *     LAFF / LAFF-ml settings: head_dim = 512, with_ave = mul = False (Attention.py:78-105 with the softmax denominator
+ *     cancelling under the final l2norm), up to LAFF_FUSE_MAX_FC projected and LAFF_FUSE_MAX_TILED "no-transform" features.
+ *     fc[l].x16 [rows, K] 16-bit (pitch % 8 == 0, zero padded), fc[l].w16 [H*512, K]; tiled[l].x fp32 [rows, in_dim].
+ *     out fp32 [rows, H*512] and / or out16; at least one.  Other settings: laff_project + laff_attention_pool. */
+typedef struct {
+  int n_fc;
+  int n_tiled;
+  int heads;
+  int head_dim;   /* must be 512 */
+  int dtype;      /* LAFF_F16 / LAFF_BF16 operands of the projection GEMMs */
+  double norm_eps; /* added to the L2 norm (reference: 1e-14) */
+  const float* att_weight; /* [heads, 512] */
+  const float* att_bias;   /* [heads] */
+  struct {
+    const void* x16;
+    long long ldx;
+    const void* w16;
+    long long ldw;
+    int K;
+    int activation;
+    const float* bias;
+    const float* bn_scale;
+    const float* bn_shift;
+  } fc[LAFF_FUSE_MAX_FC];
+  struct {
+    const float* x;
+    long long ld;
+    int in_dim;
+    const float* bn_scale;
+    const float* bn_shift;
+  } tiled[LAFF_FUSE_MAX_TILED];
+} laff_fuse_desc;
+
+int laff_fuse_forward(const laff_fuse_desc* desc, long long rows, float* out, long long ld_out, void* out16,
+                      int out16_dtype, long long ld_out16, void* stream);
 
 /* F7  frame-level LAFF (model/model.py:2160-2173 -> Attention_1(dim), model/Attention.py:78-105):
  *     frames fp32 [B, F, dim] (zero padded frames take part in the softmax exactly like the reference),

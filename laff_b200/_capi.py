@@ -47,6 +47,25 @@ class PoolDesc(C.Structure):
     ]
 
 
+FUSE_MAX_FC, FUSE_MAX_TILED = 4, 2
+
+
+class FuseFc(C.Structure):
+    _fields_ = [("x16", C.c_void_p), ("ldx", C.c_longlong), ("w16", C.c_void_p), ("ldw", C.c_longlong), ("K", C.c_int),
+                ("activation", C.c_int), ("bias", C.c_void_p), ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p)]
+
+
+class FuseTiled(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ld", C.c_longlong), ("in_dim", C.c_int), ("bn_scale", C.c_void_p),
+                ("bn_shift", C.c_void_p)]
+
+
+class FuseDesc(C.Structure):
+    _fields_ = [("n_fc", C.c_int), ("n_tiled", C.c_int), ("heads", C.c_int), ("head_dim", C.c_int), ("dtype", C.c_int),
+                ("norm_eps", C.c_double), ("att_weight", C.c_void_p), ("att_bias", C.c_void_p),
+                ("fc", FuseFc * FUSE_MAX_FC), ("tiled", FuseTiled * FUSE_MAX_TILED)]
+
+
 _vp, _i, _ll, _f, _d, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_size_t
 
 # name -> (restype, argtypes); every symbol declared in include/laff_b200.h
@@ -72,6 +91,7 @@ SIGNATURES = {
     "laff_project": (_i, [_vp, _vp, _ll, _i, _i, _ll, _ll, _i, _vp, _i, _vp, _vp, _vp, _ll, _vp]),
     "laff_bn_fold": (_i, [_vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _vp]),
     "laff_attention_pool": (_i, [C.POINTER(PoolDesc), _ll, _vp, _ll, _vp, _i, _ll, _vp, _vp]),
+    "laff_fuse_forward": (_i, [C.POINTER(FuseDesc), _ll, _vp, _ll, _vp, _i, _ll, _vp]),
     "laff_frame_pool": (_i, [_vp, _ll, _i, _i, _vp, _f, _i, _i, _f, _d, _vp, _ll, _vp]),
     "laff_mrl_workspace_bytes": (_sz, [_i, _i, _i]),
     "laff_mrl_forward_backward": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

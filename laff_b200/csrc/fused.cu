@@ -1,0 +1,558 @@
+// laff_fuse_forward — the whole LAFF fusion of one net in ONE kernel:
+//   per-feature FC projection (tcgen05 GEMM, TMA-fed) -> bias -> activation -> eval-BN -> per-head attention logit ->
+//   softmax over the features -> weighted sum -> L2 normalise, never writing the projected features to HBM.
+//   model/model.py:257-276 (TransformNet), :1807-1876 / :1663-1705 (nets), model/Attention.py:78-105, :508-531.
+//
+// Work unit = (128-row tile, head).  A cluster of 2 CTAs owns one unit; CTA c computes columns [256c, 256c+256) of the
+// head's 512.  Per FC feature the CTA runs a 128 x 256 x K_l GEMM into one of two TMEM accumulator buffers, so the
+// epilogue of feature l overlaps the MMAs of feature l+1.  Epilogue threads own (row, 128 columns):
+//   pass A  y = BN(act(acc + b)), partial logit  sum_c w_h[c] y[c]           (TMEM -> registers)
+//   exchange the 4 partial logits of a row (2 column halves x 2 CTAs) through shared memory / DSMEM + a cluster mbarrier
+//   pass B  re-read TMEM, recompute y, online-softmax update of the running weighted sum g[128] held in registers
+// The softmax denominator cancels under the final L2 normalisation (with_ave = False), so only exp(e - max) weights are
+// kept.  "No-transform" features (raw 512-d vector tiled over the heads + BN, model/model.py:1822-1823) take the same
+// two passes reading the raw feature from global memory.  Register budget: setmaxnreg moves registers from the
+// producer/MMA warpgroup to the two epilogue warpgroups (g[128] + a 32-column chunk per thread).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstring>
+
+#include "gemm_engine.cuh"
+#include "host_util.cuh"
+
+namespace laff {
+
+constexpr int kFuseStages = 4;
+constexpr int kFuseABytes = kBlockM * kBlockK * 2;    // 16 KB: 128 rows of x
+constexpr int kFuseBBytes = kBlockN * kBlockK * 2;    // 32 KB: 256 rows of W (= output columns)
+constexpr int kFuseStageBytes = kFuseABytes + kFuseBBytes;
+constexpr int kFuseBarBytes = 256;
+constexpr int kFuseParamBufs = 3;                          // see the staging protocol in the epilogue
+constexpr int kFuseParamFloats = kFuseParamBufs * 4 * kBlockN;  // per buffer: {bias, scale, shift, w_h} x 256 columns
+constexpr int kFuseXchgFloats = 2 * 4 * kBlockM;            // [parity][partial][row]
+constexpr int kFuseSmem = kFuseStages * kFuseStageBytes + kFuseBarBytes + (kFuseParamFloats + kFuseXchgFloats) * 4 + 1024;
+static_assert(kFuseSmem <= 227 * 1024, "fused kernel shared memory budget");
+
+struct FuseTmaps {
+  CUtensorMap x[LAFF_FUSE_MAX_FC];
+  CUtensorMap w[LAFF_FUSE_MAX_FC];
+};
+
+struct FuseParams {
+  int n_fc, n_tiled, heads;
+  long long rows;
+  int num_kb[LAFF_FUSE_MAX_FC];
+  int act[LAFF_FUSE_MAX_FC];
+  const float* bias[LAFF_FUSE_MAX_FC];
+  const float* bn_scale[LAFF_FUSE_MAX_FC];
+  const float* bn_shift[LAFF_FUSE_MAX_FC];
+  const float* tiled_x[LAFF_FUSE_MAX_TILED];
+  long long tiled_ld[LAFF_FUSE_MAX_TILED];
+  int tiled_in_dim[LAFF_FUSE_MAX_TILED];
+  const float* tiled_scale[LAFF_FUSE_MAX_TILED];
+  const float* tiled_shift[LAFF_FUSE_MAX_TILED];
+  const float* att_w;
+  const float* att_b;
+  float* out;
+  long long ld_out;
+  void* out16;
+  int out16_dtype;
+  long long ld_out16;
+  float norm_eps;
+  uint32_t idesc;
+  int total_units;
+};
+
+namespace fptx {
+__device__ __forceinline__ void setmaxnreg_dec56() { asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory"); }
+__device__ __forceinline__ void setmaxnreg_inc224() { asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory"); }
+// Remote (peer CTA) shared-memory store that reports its 4 bytes to an mbarrier in the same peer CTA: the receiver
+// needs no fence and the sender no separate arrive.
+__device__ __forceinline__ void st_async_f32(uint32_t cluster_addr, float v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr),
+               "r"(__float_as_uint(v)), "r"(cluster_mbar)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > LAFF_WATCHDOG_CYCLES) ptx::watchdog_fire(bar, parity, tag);
+  }
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+}  // namespace fptx
+
+// One code path for every activation (the per-row epilogue is unrolled 128x, so instruction-cache footprint matters):
+//   tanh(z) = 2 / (1 + 2^(-2 z log2e)) - 1,  sigmoid(z) = 1 / (1 + 2^(-z log2e)),  relu / none = max(z, floor)
+// with the hardware ex2 / rcp approximations (|error| < 3e-7 absolute).
+struct ActCoef {
+  float neg_s;   // -s * log2(e)   (sigmoidal branch)
+  float a, c;    // y = a / (1 + 2^(neg_s z)) + c
+  float floor;   // piecewise-linear branch: y = max(z, floor)
+  bool sigm;
+};
+__device__ __forceinline__ ActCoef make_act(int act) {
+  ActCoef k;
+  k.sigm = act == LAFF_ACT_TANH || act == LAFF_ACT_SIGMOID;
+  const float l2e = 1.4426950408889634f;
+  k.neg_s = act == LAFF_ACT_TANH ? -2.0f * l2e : -l2e;
+  k.a = act == LAFF_ACT_TANH ? 2.0f : 1.0f;
+  k.c = act == LAFF_ACT_TANH ? -1.0f : 0.0f;
+  k.floor = act == LAFF_ACT_RELU ? 0.0f : -INFINITY;
+  return k;
+}
+__device__ __forceinline__ float apply_act(float z, const ActCoef& k) {
+  float t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(k.neg_s * z));
+  const float sg = fmaf(k.a, __fdividef(1.0f, 1.0f + t), k.c);
+  return k.sigm ? sg : fmaxf(z, k.floor);
+}
+__device__ __forceinline__ uint16_t fuse_to16(float v, int dtype) {
+  if (dtype == LAFF_BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  return __half_as_ushort(__float2half_rn(v));
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+    laff_fuse_kernel(const __grid_constant__ FuseTmaps tm, const __grid_constant__ FuseParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+
+  const uint32_t sA = base;
+  const uint32_t sB = base + kFuseStages * kFuseABytes;
+  const uint32_t bar0 = base + kFuseStages * kFuseStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kFuseStages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kFuseStages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kFuseStages + 2 + a); };
+  auto xchg_bar = [&](int a) { return bar0 + 8u * (2 * kFuseStages + 4 + a); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * kFuseStages + 6);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + kFuseStages * kFuseStageBytes + 8 * (2 * kFuseStages + 6));
+  float* s_param = reinterpret_cast<float*>(smem + kFuseStages * kFuseStageBytes + kFuseBarBytes);
+  float* s_xchg = s_param + kFuseParamFloats;
+  const uint32_t s_xchg_addr = bar0 + kFuseBarBytes + kFuseParamFloats * 4;
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = static_cast<int>(ptx::lane_id());
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const int cluster_id = static_cast<int>(blockIdx.x) >> 1;
+  const int num_clusters = static_cast<int>(gridDim.x) >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < p.n_fc; ++l) {
+      ptx::prefetch_tensormap(&tm.x[l]);
+      ptx::prefetch_tensormap(&tm.w[l]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kFuseStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), kEpiWarps);
+      ptx::mbar_init(xchg_bar(a), kEpiWarps);  // local epilogue warps; the peer's partials arrive as transaction bytes
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<1>(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish<1>();
+  }
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    fptx::setmaxnreg_dec56();
+    if (warp == 0) {
+      // ========================================= TMA producer =========================================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int u = cluster_id; u < p.total_units; u += num_clusters) {
+          const int row_tile = u / p.heads, head = u - row_tile * p.heads;
+          const int m0 = row_tile * kBlockM;
+          const int n0 = head * 2 * kBlockN + static_cast<int>(cta_rank) * kBlockN;
+          for (int l = 0; l < p.n_fc; ++l) {
+            for (int kb = 0; kb < p.num_kb[l]; ++kb) {
+              ptx::mbar_wait_nocall(empty_bar(stage), phase ^ 1u);
+              ptx::mbar_arrive_expect_tx(full_bar(stage), kFuseStageBytes);
+              ptx::tma_load_2d(sA + stage * kFuseABytes, &tm.x[l], full_bar(stage), kb * kBlockK, m0, ptx::kEvictNormal);
+              ptx::tma_load_2d(sB + stage * kFuseBBytes, &tm.w[l], full_bar(stage), kb * kBlockK, n0, ptx::kEvictLast);
+              if (++stage == kFuseStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ========================================== MMA issuer ==========================================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int u = cluster_id; u < p.total_units; u += num_clusters) {
+          for (int l = 0; l < p.n_fc; ++l) {
+            ptx::mbar_wait_nocall(tempty_bar(acc), acc_phase ^ 1u);
+            ptx::tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kBlockN);
+            for (int kb = 0; kb < p.num_kb[l]; ++kb) {
+              ptx::mbar_wait_nocall(full_bar(stage), phase);
+              ptx::tcgen05_fence_after();
+              const uint64_t da = ptx::make_smem_desc_sw128(sA + stage * kFuseABytes);
+              const uint64_t db = ptx::make_smem_desc_sw128(sB + stage * kFuseBBytes);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                ptx::umma_f16<1>(d_tmem, da + 2u * k, db + 2u * k, p.idesc, static_cast<uint32_t>((kb | k) != 0));
+              ptx::umma_commit<1>(empty_bar(stage));
+              if (++stage == kFuseStages) { stage = 0; phase ^= 1u; }
+            }
+            ptx::umma_commit<1>(tfull_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================================ epilogue ============================================
+    fptx::setmaxnreg_inc224();
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row_in_cta = quad * 32 + lane;
+    const int epi_tid = half * kBlockM + row_in_cta;       // 0..255
+    const int my_part = half + 2 * static_cast<int>(cta_rank);
+    const uint32_t peer = cta_rank ^ 1u;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t xchg_count = 0;  // exchanges done so far: parity = count & 1, phase = (count >> 1) & 1
+
+    // All-to-all of one float per (row, partial) among the 4 owners of a row (2 column halves x 2 CTAs); returns the
+    // sum in a fixed order, identical in all four threads.  post() publishes, collect() waits: independent work placed
+    // between the two hides the cluster round trip.  Exchange n uses slot / barrier n & 1; a thread can only post n + 2
+    // after collecting n + 1, which needs every thread's post of n + 1, which they issue after reading slot n.
+    auto post = [&](float v) {
+      const int par = static_cast<int>(xchg_count & 1u);
+      const int off = (par * 4 + my_part) * kBlockM + row_in_cta;
+      s_xchg[off] = v;
+      fptx::st_async_f32(ptx::mapa(s_xchg_addr + 4u * off, peer), v, ptx::mapa(xchg_bar(par), peer));
+      __syncwarp();
+      if (lane == 0) {
+        if (warp == 4) ptx::mbar_arrive_expect_tx(xchg_bar(par), 2 * kBlockM * 4);  // the peer's 2 x 128 partials
+        else ptx::mbar_arrive(xchg_bar(par));
+      }
+    };
+    auto collect = [&]() -> float {
+      const int par = static_cast<int>(xchg_count & 1u);
+      const uint32_t ph = (xchg_count >> 1) & 1u;
+      fptx::mbar_wait_cluster(xchg_bar(par), ph, 14);
+      const float* sx = s_xchg + par * 4 * kBlockM + row_in_cta;
+      const float r = ((sx[0] + sx[kBlockM]) + sx[2 * kBlockM]) + sx[3 * kBlockM];
+      ++xchg_count;
+      return r;
+    };
+    // Per-column parameters {bias, BN scale, BN shift, w_h} of (feature f of head `hd`), one column per epilogue thread:
+    // loaded into registers before pass A of the current feature and stored to buffer (cur + 1) % 3 after it, i.e.
+    // before this thread's post(); collect() then orders every thread's stores before anybody's reads.  Three buffers:
+    // a slower warp may still read buffer cur - 1 (pass B of the previous feature) while a faster one writes cur + 1.
+    auto load_params = [&](int f, int hd, float (&v)[4]) {
+      const bool tl = f < p.n_tiled;
+      const int l = tl ? f : f - p.n_tiled;
+      const int col = hd * 2 * kBlockN + static_cast<int>(cta_rank) * kBlockN + epi_tid;
+      const float* bs = tl ? nullptr : p.bias[l];
+      const float* sc = tl ? p.tiled_scale[l] : p.bn_scale[l];
+      const float* sh = tl ? p.tiled_shift[l] : p.bn_shift[l];
+      v[0] = bs ? __ldg(bs + col) : 0.f;
+      v[1] = sc ? __ldg(sc + col) : 1.f;
+      v[2] = sh ? __ldg(sh + col) : 0.f;
+      v[3] = __ldg(p.att_w + col);
+    };
+    auto store_params = [&](int buf, const float (&v)[4]) {
+      float* sp = s_param + buf * 4 * kBlockN;
+      sp[epi_tid] = v[0];
+      sp[kBlockN + epi_tid] = v[1];
+      sp[2 * kBlockN + epi_tid] = v[2];
+      sp[3 * kBlockN + epi_tid] = v[3];
+    };
+
+    int stage_buf = 0;  // buffer holding the parameters of the feature about to be processed
+    if (cluster_id < p.total_units) {
+      float v[4];
+      load_params(0, cluster_id % p.heads, v);
+      store_params(0, v);
+    }
+    fptx::epi_bar_sync();
+    for (int u = cluster_id; u < p.total_units; u += num_clusters) {
+      const int row_tile = u / p.heads, head = u - row_tile * p.heads;
+      const long long row = static_cast<long long>(row_tile) * kBlockM + row_in_cta;
+      const bool row_ok = row < p.rows;
+      const int colbase = head * 2 * kBlockN + static_cast<int>(cta_rank) * kBlockN;  // first global column of this CTA
+      const int mycol = half * kEpiCols;                                             // first column (in CTA) of this thread
+
+      float g[kEpiCols];
+#pragma unroll
+      for (int j = 0; j < kEpiCols; ++j) g[j] = 0.f;
+      float m_run = -INFINITY;
+
+      const int n_feat = p.n_tiled + p.n_fc;
+      for (int f = 0; f < n_feat; ++f) {
+        const bool tiled = f < p.n_tiled;
+        const int l = tiled ? f : f - p.n_tiled;
+        const float* sp = s_param + stage_buf * 4 * kBlockN;
+        float nextp[4];
+        const bool has_next = (f + 1 < n_feat) || (u + num_clusters < p.total_units);
+        if (f + 1 < n_feat) load_params(f + 1, head, nextp);
+        else if (has_next) load_params(0, (u + num_clusters) % p.heads, nextp);
+        const float* pb = sp + mycol;
+        const float* psc = sp + kBlockN + mycol;
+        const float* psh = sp + 2 * kBlockN + mycol;
+        const float* pw = sp + 3 * kBlockN + mycol;
+        const ActCoef ak = make_act(tiled ? LAFF_ACT_NONE : p.act[l]);
+        const float* xrow = nullptr;
+        int xoff = 0;
+        if (tiled) {
+          xrow = p.tiled_x[l] + (row_ok ? row : 0) * p.tiled_ld[l];
+          xoff = (colbase + mycol) % p.tiled_in_dim[l];  // in_dim is a multiple of 128: 128 consecutive columns never wrap
+        }
+        uint32_t taddr = 0;
+        if (!tiled) {
+          ptx::mbar_wait(tfull_bar(acc), acc_phase, 15);
+          ptx::tcgen05_fence_after();
+          taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * kBlockN + mycol);
+        }
+        // ---- pass A: y = BN(act(acc + b)) (written back to TMEM in place), partial logit over my 128 columns ----
+        float part = 0.f;
+        if (tiled) {
+#pragma unroll 1
+          for (int c = 0; c < kEpiCols / 32; ++c) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int cc = c * 32 + j;
+              const float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(xrow + xoff + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 sc4 = *reinterpret_cast<const float4*>(psc + cc);
+              const float4 sh4 = *reinterpret_cast<const float4*>(psh + cc);
+              const float4 w4 = *reinterpret_cast<const float4*>(pw + cc);
+              part = fmaf(w4.x, fmaf(v.x, sc4.x, sh4.x), part);
+              part = fmaf(w4.y, fmaf(v.y, sc4.y, sh4.y), part);
+              part = fmaf(w4.z, fmaf(v.z, sc4.z, sh4.z), part);
+              part = fmaf(w4.w, fmaf(v.w, sc4.w, sh4.w), part);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < kEpiCols / 32; ++c) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int cc = c * 32 + j;
+              const float4 b4 = *reinterpret_cast<const float4*>(pb + cc);
+              const float4 sc4 = *reinterpret_cast<const float4*>(psc + cc);
+              const float4 sh4 = *reinterpret_cast<const float4*>(psh + cc);
+              const float4 w4 = *reinterpret_cast<const float4*>(pw + cc);
+              const float y0 = fmaf(apply_act(__uint_as_float(r[j]) + b4.x, ak), sc4.x, sh4.x);
+              const float y1 = fmaf(apply_act(__uint_as_float(r[j + 1]) + b4.y, ak), sc4.y, sh4.y);
+              const float y2 = fmaf(apply_act(__uint_as_float(r[j + 2]) + b4.z, ak), sc4.z, sh4.z);
+              const float y3 = fmaf(apply_act(__uint_as_float(r[j + 3]) + b4.w, ak), sc4.w, sh4.w);
+              part = fmaf(w4.x, y0, part);
+              part = fmaf(w4.y, y1, part);
+              part = fmaf(w4.z, y2, part);
+              part = fmaf(w4.w, y3, part);
+              r[j] = __float_as_uint(y0); r[j + 1] = __float_as_uint(y1); r[j + 2] = __float_as_uint(y2); r[j + 3] = __float_as_uint(y3);
+            }
+            ptx::tmem_st_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), r);  // pass B re-reads y, not the accumulator
+          }
+          ptx::tmem_st_wait();
+        }
+        if (has_next) store_params(stage_buf == kFuseParamBufs - 1 ? 0 : stage_buf + 1, nextp);
+        post(part);
+        const float e = collect() + __ldg(p.att_b + head);
+        // ---- pass B: online softmax-weighted accumulation (the denominator cancels under the final L2 norm) ----
+        const float m_new = fmaxf(m_run, e);
+        const float corr = __expf(m_run - m_new);  // 0 on the first feature
+        const float pe = __expf(e - m_new);
+        m_run = m_new;
+        if (tiled) {
+#pragma unroll
+          for (int cc = 0; cc < kEpiCols; cc += 4) {
+            const float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(xrow + xoff + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 sc4 = *reinterpret_cast<const float4*>(psc + cc);
+            const float4 sh4 = *reinterpret_cast<const float4*>(psh + cc);
+            g[cc] = fmaf(g[cc], corr, pe * fmaf(v.x, sc4.x, sh4.x));
+            g[cc + 1] = fmaf(g[cc + 1], corr, pe * fmaf(v.y, sc4.y, sh4.y));
+            g[cc + 2] = fmaf(g[cc + 2], corr, pe * fmaf(v.z, sc4.z, sh4.z));
+            g[cc + 3] = fmaf(g[cc + 3], corr, pe * fmaf(v.w, sc4.w, sh4.w));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kEpiCols / 32; ++c) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) g[c * 32 + j] = fmaf(g[c * 32 + j], corr, pe * __uint_as_float(r[j]));
+          }
+        }
+        if (!tiled) {
+          ptx::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        stage_buf = stage_buf == kFuseParamBufs - 1 ? 0 : stage_buf + 1;
+      }
+      // ---- L2 normalise over the whole head (4 partial sums of squares per row) and write ----
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < kEpiCols; ++j) ss = fmaf(g[j], g[j], ss);
+      post(ss);
+      const float den = sqrtf(collect()) + p.norm_eps;
+      const float inv = 1.0f / den;  // one IEEE division per row; x * (1/den) is within 1 ulp of x / den
+#pragma unroll
+      for (int j = 0; j < kEpiCols; ++j) g[j] *= inv;
+      if (row_ok) {
+        const long long c0 = colbase + mycol;
+        if (p.out) {
+          float* o = p.out + row * p.ld_out + c0;
+#pragma unroll
+          for (int j = 0; j < kEpiCols; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+        }
+        if (p.out16) {
+          uint16_t* o = static_cast<uint16_t*>(p.out16) + row * p.ld_out16 + c0;
+          if (p.out16_dtype == LAFF_BF16) {
+#pragma unroll
+            for (int j = 0; j < kEpiCols; j += 8) {
+              __nv_bfloat162 a0 = __floats2bfloat162_rn(g[j], g[j + 1]), a1 = __floats2bfloat162_rn(g[j + 2], g[j + 3]);
+              __nv_bfloat162 a2 = __floats2bfloat162_rn(g[j + 4], g[j + 5]), a3 = __floats2bfloat162_rn(g[j + 6], g[j + 7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
+              pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+              *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < kEpiCols; j += 8) {
+              __half2 a0 = __floats2half2_rn(g[j], g[j + 1]), a1 = __floats2half2_rn(g[j + 2], g[j + 3]);
+              __half2 a2 = __floats2half2_rn(g[j + 4], g[j + 5]), a3 = __floats2half2_rn(g[j + 6], g[j + 7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
+              pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+              *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 2) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace laff
+
+using namespace laff;
+
+extern "C" int laff_fuse_forward(const laff_fuse_desc* d, long long rows, float* out, long long ld_out, void* out16,
+                                 int out16_dtype, long long ld_out16, void* stream) {
+  LAFF_REQUIRE(d && rows > 0, LAFF_EINVAL, "laff_fuse_forward: bad arguments");
+  LAFF_REQUIRE(out || out16, LAFF_EINVAL, "laff_fuse_forward: no output buffer");
+  LAFF_REQUIRE(d->head_dim == 2 * kBlockN, LAFF_ENOTSUP, "laff_fuse_forward: head_dim must be 512 (got %d); use "
+               "laff_project + laff_attention_pool for other shapes", d->head_dim);
+  LAFF_REQUIRE(d->heads > 0 && d->n_fc >= 1 && d->n_fc <= LAFF_FUSE_MAX_FC && d->n_tiled >= 0 &&
+                   d->n_tiled <= LAFF_FUSE_MAX_TILED, LAFF_ENOTSUP, "laff_fuse_forward: n_fc=%d n_tiled=%d unsupported",
+               d->n_fc, d->n_tiled);
+  LAFF_REQUIRE(is16(d->dtype) && d->att_weight && d->att_bias, LAFF_EINVAL, "laff_fuse_forward: bad descriptor");
+  LAFF_REQUIRE(rows < (1LL << 31) - kBlockM, LAFF_ENOTSUP, "laff_fuse_forward: too many rows");
+  const int D = d->heads * d->head_dim;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  LAFF_REQUIRE(!out || (ld_out >= D && ld_out % 4 == 0 && al16(out)), LAFF_EINVAL, "laff_fuse_forward: out pitch/alignment");
+  LAFF_REQUIRE(!out16 || (ld_out16 >= D && ld_out16 % 8 == 0 && al16(out16) && is16(out16_dtype)), LAFF_EINVAL,
+               "laff_fuse_forward: out16 pitch/alignment");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  FuseTmaps tm;
+  FuseParams p;
+  memset(&tm, 0, sizeof(tm));
+  memset(&p, 0, sizeof(p));
+  p.n_fc = d->n_fc;
+  p.n_tiled = d->n_tiled;
+  p.heads = d->heads;
+  p.rows = rows;
+  for (int l = 0; l < d->n_fc; ++l) {
+    const auto& f = d->fc[l];
+    LAFF_REQUIRE(f.x16 && f.w16 && f.K > 0 && f.K % 8 == 0 && f.ldx % 8 == 0 && f.ldw % 8 == 0 && f.ldx >= f.K && f.ldw >= f.K,
+                 LAFF_EINVAL, "laff_fuse_forward: fc feature %d: K and pitches must be multiples of 8", l);
+    LAFF_REQUIRE((f.bn_scale == nullptr) == (f.bn_shift == nullptr) && f.activation >= 0 && f.activation <= 3, LAFF_EINVAL,
+                 "laff_fuse_forward: fc feature %d: bad bn/activation", l);
+    rc = make_tmap_2d(&tm.x[l], f.x16, d->dtype, static_cast<uint64_t>(rows), static_cast<uint64_t>(f.K), static_cast<uint64_t>(f.ldx), kBlockM);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tm.w[l], f.w16, d->dtype, static_cast<uint64_t>(D), static_cast<uint64_t>(f.K), static_cast<uint64_t>(f.ldw), kBlockN);
+    if (rc) return rc;
+    p.num_kb[l] = (f.K + kBlockK - 1) / kBlockK;
+    p.act[l] = f.activation;
+    p.bias[l] = f.bias;
+    p.bn_scale[l] = f.bn_scale;
+    p.bn_shift[l] = f.bn_shift;
+  }
+  for (int l = 0; l < d->n_tiled; ++l) {
+    const auto& t = d->tiled[l];
+    LAFF_REQUIRE(t.x && t.in_dim > 0 && t.in_dim % kEpiCols == 0 && D % t.in_dim == 0 && t.ld >= t.in_dim && t.ld % 4 == 0 && al16(t.x),
+                 LAFF_ENOTSUP, "laff_fuse_forward: tiled feature %d: in_dim must be a multiple of 128 dividing D, 16-byte aligned rows", l);
+    LAFF_REQUIRE((t.bn_scale == nullptr) == (t.bn_shift == nullptr), LAFF_EINVAL, "laff_fuse_forward: tiled feature %d: bn mismatch", l);
+    p.tiled_x[l] = t.x;
+    p.tiled_ld[l] = t.ld;
+    p.tiled_in_dim[l] = t.in_dim;
+    p.tiled_scale[l] = t.bn_scale;
+    p.tiled_shift[l] = t.bn_shift;
+  }
+  p.att_w = d->att_weight;
+  p.att_b = d->att_bias;
+  p.out = out;
+  p.ld_out = ld_out;
+  p.out16 = out16;
+  p.out16_dtype = out16_dtype;
+  p.ld_out16 = ld_out16;
+  p.norm_eps = static_cast<float>(d->norm_eps);
+  p.idesc = make_idesc_f16(d->dtype, kBlockM, kBlockN);
+  const long long row_tiles = (rows + kBlockM - 1) / kBlockM;
+  p.total_units = static_cast<int>(row_tiles * d->heads);
+  static bool configured = false;
+  if (!configured) {
+    LAFF_CUDA(cudaFuncSetAttribute(laff_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuseSmem));
+    configured = true;
+  }
+  int clusters = di.sms / 2;
+  if (clusters > p.total_units) clusters = p.total_units;
+  laff_fuse_kernel<<<clusters * 2, kNumThreads, kFuseSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
+  count_launch();
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}

@@ -237,9 +237,48 @@ def get_attention_layer(attention_type: str, common_space_dim, encoder_num, opt)
     raise NotImplementedError("attention type %r is an ablation variant outside the LAFF hot path" % attention_type)
 
 
+_SINGLE_KERNEL = True  # use laff_fuse_forward when the configuration allows it (set False to force the two-kernel path)
+
+
+def set_single_kernel_fusion(flag: bool) -> None:
+    global _SINGLE_KERNEL
+    _SINGLE_KERNEL = bool(flag)
+
+
+def _fuse_single_kernel(features, attention, precision, out16_dtype):
+    """All projections + pooling in one kernel (csrc/fused.cu)."""
+    fc, tiled = [], []
+    for x, tn in features:
+        c = tn.prepared(precision)
+        if tn.fc1 is not None:
+            x16 = ops.split3_16(x, 0, torch.bfloat16) if precision == "bf16x3" else ops.cast_pad_16(x, _op_dtype(precision))
+            fc.append({"x16": x16, "w16": c["w16"], "bias": c["bias"], "activation": tn.activation_name,
+                       "bn_scale": c.get("bn_scale"), "bn_shift": c.get("bn_shift")})
+        else:
+            tiled.append({"x": x, "bn_scale": c.get("bn_scale"), "bn_shift": c.get("bn_shift")})
+    w, b = attention.head_params()
+    return ops.fuse_forward(fc, tiled, w, b, attention.multi_heads, attention.dim_per_head, want_f32=True,
+                            out16_dtype=out16_dtype)
+
+
+def _single_kernel_ok(features, attention, want_att) -> bool:
+    if not _SINGLE_KERNEL or want_att or attention.with_ave or attention.mul or attention.dim_per_head != 512:
+        return False
+    n_fc = sum(1 for _, tn in features if tn.fc1 is not None)
+    n_tiled = len(features) - n_fc
+    if not (1 <= n_fc <= 4 and n_tiled <= 2):
+        return False
+    D = attention.multi_heads * 512
+    return all(tn.fc1 is not None or (x.shape[1] % 128 == 0 and D % x.shape[1] == 0) for x, tn in features)
+
+
 def _fuse(features: Sequence, attention: Multi_head_MyApply_Attention, device, precision, out16_dtype=None,
-          want_att=True):
-    """features: list of (x fp32 [B, d] device tensor, TransformNet). Projection GEMMs + LAFF pooling, chunked by rows."""
+          want_att=False):
+    """features: list of (x fp32 [B, d] device tensor, TransformNet).  One fused kernel when the configuration allows
+    (head_dim 512, with_ave = mul = False, attention weights not requested); otherwise projection GEMMs + pooling kernel,
+    chunked by rows."""
+    if _single_kernel_ok(features, attention, want_att):
+        return _fuse_single_kernel(features, attention, precision, out16_dtype)
     B = features[0][0].shape[0]
     D = attention.multi_heads * attention.dim_per_head
     outs, outs16 = [], []
@@ -258,7 +297,7 @@ def _fuse(features: Sequence, attention: Multi_head_MyApply_Attention, device, p
             else:
                 c = tn.prepared(precision)
                 srcs.append({"x": xs, "bn_scale": c.get("bn_scale"), "bn_shift": c.get("bn_shift")})
-        o, o16 = attention.pool(srcs, out16_dtype=out16_dtype, want_att=want_att and B <= _ROW_CHUNK)
+        o, o16 = attention.pool(srcs, out16_dtype=out16_dtype, want_att=B <= _ROW_CHUNK)  # Attention_1.weights, as the reference keeps
         outs.append(o)
         outs16.append(o16)
     out = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
@@ -312,20 +351,20 @@ class VisMutiTransformNetAddAttnetion(nn.Module):
         self.attention_layer = get_attention_layer(opt.vis_attention, self.common_space_dim, len(space_dict), opt)
         self.expert_embedding = None
 
-    def encode(self, vis_input, out16_dtype=None, precision=None):
+    def encode(self, vis_input, out16_dtype=None, precision=None, want_att=False):
         precision = precision or _loss.get_precision()
         dev = _cuda_device(self.attention_layer.layer_norm.weight.device)
         if self.training:
             raise NotImplementedError("train-mode forward of the fusion net is SURVEY §8f N4; call .eval()")
         mods = dict(self.VisMutiTransformNet.named_children())
         feats = [(vis_input[name].to(dev, non_blocking=True).float(), mods[name]) for name in self.vis_net_space_dict.keys()]
-        return _fuse(feats, self.attention_layer, dev, precision, out16_dtype)
+        return _fuse(feats, self.attention_layer, dev, precision, out16_dtype, want_att)
 
     def forward(self, vis_input, txt_emb=None, vis_frame_feat_dict_input=None):
         return self.encode(vis_input)[0]
 
     def get_attention_weight(self, vis_input, txt_emb=None):
-        self.forward(vis_input, txt_emb)
+        self.encode(vis_input, want_att=True)
         return self.attention_layer.get_attention_weight()
 
 
@@ -386,7 +425,7 @@ class MultiScaleTxtEncoderAttention(nn.Module):
                 return caption_feat_dict[key]
         raise KeyError("caption_feat_dict has no feature for %s (expected one of %s)" % (enc, dict(_TXT_ENCODERS)[enc]))
 
-    def encode(self, caption_feat_dict, out16_dtype=None, precision=None):
+    def encode(self, caption_feat_dict, out16_dtype=None, precision=None, want_att=False):
         precision = precision or _loss.get_precision()
         dev = _cuda_device(self.attention_layer.layer_norm.weight.device)
         if self.training:
@@ -394,13 +433,13 @@ class MultiScaleTxtEncoderAttention(nn.Module):
         mods = dict(self.transform_layer.named_children())
         feats = [(self._feature(caption_feat_dict, n).to(dev, non_blocking=True).float(), mods[n + "_transform"])
                  for n in self.encoder_name_list]
-        return _fuse(feats, self.attention_layer, dev, precision, out16_dtype)
+        return _fuse(feats, self.attention_layer, dev, precision, out16_dtype, want_att)
 
     def forward(self, caption_feat_dict, visual_emb=None, task3=False):
         return self.encode(caption_feat_dict)[0]
 
     def get_attention_weight(self, caption_feat_dict, visual_emb=None):
-        self.forward(caption_feat_dict, visual_emb)
+        self.encode(caption_feat_dict, want_att=True)
         return self.attention_layer.get_attention_weight()
 
 

@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _capi
-from ._capi import BF16, F16, F32, MAX_TOPK, LaffError, PoolDesc
+from ._capi import BF16, F16, F32, FUSE_MAX_FC, FUSE_MAX_TILED, MAX_TOPK, FuseDesc, LaffError, PoolDesc
 
 _DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 _TORCH_DT = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32, "fp16": torch.float16,
@@ -285,6 +285,65 @@ def attention_pool(sources: Sequence[dict], att_weight: torch.Tensor, att_bias: 
         _capi.call("laff_attention_pool", C.byref(desc), rows, _ptr(out), D, _ptr(out16), o16dt, D, _ptr(att),
                    _stream(keep[0]))
     return out.view(rows, heads, head_dim), (None if out16 is None else out16.view(rows, heads, head_dim)), att
+
+
+def fuse_forward(fc: Sequence[dict], tiled: Sequence[dict], att_weight: torch.Tensor, att_bias: torch.Tensor, heads: int,
+                 head_dim: int, want_f32: bool = True, out16_dtype=None, norm_eps: float = 1e-14):
+    """All projections + LAFF pooling in ONE kernel (laff_fuse_forward; head_dim 512, with_ave = mul = False).
+
+    fc:    [{'x16': [rows, K] 16-bit, 'w16': [D, K] 16-bit, 'bias': fp32 [D] or None, 'activation': name/int,
+             'bn_scale': fp32 [D] or None, 'bn_shift': ...}]
+    tiled: [{'x': fp32 [rows, in_dim], 'bn_scale': ..., 'bn_shift': ...}]
+    Returns (out fp32 [rows, heads, head_dim] or None, out16 or None)."""
+    if not (1 <= len(fc) <= FUSE_MAX_FC and len(tiled) <= FUSE_MAX_TILED):
+        raise LaffError("fuse_forward supports 1..%d projected and up to %d tiled features" % (FUSE_MAX_FC, FUSE_MAX_TILED))
+    d = FuseDesc()
+    d.n_fc, d.n_tiled, d.heads, d.head_dim = len(fc), len(tiled), heads, head_dim
+    d.norm_eps = float(norm_eps)
+    att_weight = att_weight.detach().float().contiguous()
+    att_bias = att_bias.detach().float().contiguous()
+    d.att_weight, d.att_bias = att_weight.data_ptr(), att_bias.data_ptr()
+    keep = [att_weight, att_bias]
+    rows = None
+    dt = None
+    for l, f in enumerate(fc):
+        x16, w16 = _check_operands(f["x16"], f["w16"])
+        keep += [x16, w16]
+        dt = x16.dtype if dt is None else dt
+        if x16.dtype != dt:
+            raise LaffError("all projected features must share one operand dtype")
+        rows = x16.shape[0] if rows is None else rows
+        e = d.fc[l]
+        e.x16, e.ldx, e.w16, e.ldw, e.K = x16.data_ptr(), x16.stride(0), w16.data_ptr(), w16.stride(0), x16.shape[1]
+        act = f.get("activation")
+        e.activation = act if isinstance(act, int) else _capi.ACT[act]
+        for name in ("bias", "bn_scale", "bn_shift"):
+            t = f.get(name)
+            if t is not None:
+                _need_cuda(t)
+                keep.append(t)
+                setattr(e, name, t.data_ptr())
+    for l, f in enumerate(tiled):
+        x = _rowmajor(f["x"].float() if f["x"].dtype != torch.float32 else f["x"])
+        _need_cuda(x)
+        keep.append(x)
+        e = d.tiled[l]
+        e.x, e.ld, e.in_dim = x.data_ptr(), x.stride(0), x.shape[1]
+        if f.get("bn_scale") is not None:
+            e.bn_scale, e.bn_shift = f["bn_scale"].data_ptr(), f["bn_shift"].data_ptr()
+    d.dtype = _DT[dt]
+    dev = keep[2].device
+    D = heads * head_dim
+    out = torch.empty((rows, D), dtype=torch.float32, device=dev) if want_f32 else None
+    out16 = None
+    o16 = 0
+    if out16_dtype is not None:
+        out16_dtype = torch_dtype(out16_dtype)
+        out16 = torch.empty((rows, D), dtype=out16_dtype, device=dev)
+        o16 = _DT[out16_dtype]
+    if rows:
+        _capi.call("laff_fuse_forward", C.byref(d), rows, _ptr(out), D, _ptr(out16), o16, D, _stream(keep[2]))
+    return (None if out is None else out.view(rows, heads, head_dim)), (None if out16 is None else out16.view(rows, heads, head_dim))
 
 
 def frame_pool(frames: torch.Tensor, att_weight: torch.Tensor, att_bias: float, with_ave: bool = False,

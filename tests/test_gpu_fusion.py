@@ -209,3 +209,66 @@ def test_train_mode_is_refused_not_faked():
         tn(torch.randn(4, 64))
     with pytest.raises(NotImplementedError):
         M.get_attention_layer("muti_head_attention_official", 256, 4, cfg.laff_config(256, 8))
+
+
+@pytest.mark.parametrize("kind", ["laff_txt", "laff_vis", "frame_vis"])
+def test_single_kernel_fusion_vs_two_kernel_path_and_oracle(kind):
+    """laff_fuse_forward (all projections + pooling in one kernel) against the two-kernel path and the oracle, at the
+    real dimensions, for ragged row counts, with and without BatchNorm (LAFF-ml has BN on every FC feature)."""
+    from laff_b200 import _capi
+    r = synth.rng_for(21, kind)
+    if kind == "frame_vis":
+        c = cfg.frame_laff_config(4096, 8, synth.DIMS)
+        net = M.VisMutiTransformNetPlusFrameFeat(c)
+    else:
+        c = cfg.laff_config(4096, 8, synth.DIMS)
+        net = M.MultiScaleTxtEncoderAttention(c) if kind == "laff_txt" else M.VisMutiTransformNetAddAttnetion(c, c.vis_fc_layers[0])
+    sd = {k: synth.bf16_round(synth.param(3, k, tuple(v.shape))) if k.endswith("fc1.weight") else synth.param(3, k, tuple(v.shape))
+          for k, v in net.state_dict().items()}
+    load_numpy_state(net, sd)
+    net = net.cuda().eval()
+    for rows in (1, 127, 129, 300):
+        if kind == "laff_txt":
+            feats = {"gru": synth.bf16_round(r.standard_normal((rows, 1024)).astype(np.float32)),
+                     "bow": r.randint(0, 3, (rows, 3981)).astype(np.float32),
+                     "w2v": synth.bf16_round(r.standard_normal((rows, 500)).astype(np.float32)),
+                     "clip": r.standard_normal((rows, 512)).astype(np.float32)}
+            ref, _ = O.txt_net_forward(feats, sd, ["CLIP_encoder"], 8)
+            run = lambda: net.encode({k: torch.from_numpy(v) for k, v in feats.items()}, out16_dtype=torch.bfloat16)
+        elif kind == "laff_vis":
+            feats = {k: (r.standard_normal((rows, d)).astype(np.float32) if k == synth.VIS_CLIP_FT else
+                         synth.bf16_round(np.maximum(r.standard_normal((rows, d)), 0).astype(np.float32)))
+                     for k, d in c.vis_fc_layers[0].items()}
+            ref, _ = O.vis_net_forward(feats, sd, [synth.VIS_CLIP_FT], 8)
+            run = lambda: net.encode({k: torch.from_numpy(v) for k, v in feats.items()}, out16_dtype=torch.bfloat16)
+        else:
+            feats = {k: synth.bf16_round(np.maximum(r.standard_normal((rows, d)), 0).astype(np.float32))
+                     for k, d in c.vis_fc_layers[0].items() if k != synth.VIS_FRAME}
+            frames = r.standard_normal((rows, 6, 512)).astype(np.float32)
+            ref, _ = O.frame_vis_net_forward(feats, frames, synth.VIS_FRAME, sd, [synth.VIS_FRAME], 8)
+            fd = {"mask_tensor": torch.ones(rows, 6), synth.VIS_FRAME: torch.from_numpy(frames)}
+            run = lambda: net.encode({k: torch.from_numpy(v) for k, v in feats.items()}, fd, out16_dtype=torch.bfloat16)
+        lib = _capi.lib()
+        M.set_single_kernel_fusion(True)
+        run()                                                     # first call casts / folds the weights (cached)
+        lib.laff_launch_count(1)
+        a32, a16 = run()
+        n_single = lib.laff_launch_count(1)
+        M.set_single_kernel_fusion(False)
+        b32, b16 = run()
+        n_two = lib.laff_launch_count(1)
+        M.set_single_kernel_fusion(True)
+        assert n_single < n_two                                   # the single-kernel path really is the one that ran
+        assert max_abs(a32, ref) <= 2e-6 and max_abs(b32, ref) <= 2e-6, (kind, rows)
+        assert max_abs(a32, b32) <= 5e-7
+        assert torch.equal(a16, a32.to(torch.bfloat16))
+        np.testing.assert_allclose(a32.norm(dim=2).cpu().numpy(), 1.0, atol=1e-6)
+
+
+def test_fuse_forward_rejects_unsupported_shapes():
+    from laff_b200 import LaffError
+    x16 = torch.zeros(4, 64, dtype=torch.bfloat16, device="cuda")
+    w16 = torch.zeros(256, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(LaffError, match="head_dim must be 512"):
+        ops.fuse_forward([{"x16": x16, "w16": w16, "bias": None, "activation": "tanh"}], [], torch.zeros(8, 32, device="cuda"),
+                         torch.zeros(8, device="cuda"), 8, 32)

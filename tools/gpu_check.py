@@ -257,6 +257,74 @@ def sec_fuse():
         print("frame_pool with_ave=%d mul=%d err %.3e" % (with_ave, mul, (o.double() - ref).abs().max().item()))
 
 
+def sec_fused():
+    """Single-kernel fusion vs the two-kernel path vs fp64 torch, LAFF dims, several row counts."""
+    torch = _t()
+    import numpy as np
+    from laff_b200 import config as cfg, loss as L, model as M, synth
+    dev = "cuda"
+    c = cfg.laff_config(4096, 8, synth.DIMS)
+    for net_kind in ("txt", "vis"):
+        net = (M.MultiScaleTxtEncoderAttention(c) if net_kind == "txt" else M.VisMutiTransformNetAddAttnetion(c, c.vis_fc_layers[0]))
+        sd = {k: torch.from_numpy(np.asarray(synth.param(5, k, tuple(v.shape)))).to(v.dtype).reshape(v.shape) for k, v in net.state_dict().items()}
+        net.load_state_dict(sd)
+        net = net.to(dev).eval()
+        for rows in (1, 130, 1000, 2990):
+            g = torch.Generator(device=dev).manual_seed(rows)
+            if net_kind == "txt":
+                feats = {"gru": torch.randn(rows, 1024, generator=g, device=dev), "bow": torch.randint(0, 3, (rows, 3981), generator=g, device=dev).float(),
+                         "w2v": torch.randn(rows, 500, generator=g, device=dev), "clip": torch.randn(rows, 512, generator=g, device=dev)}
+            else:
+                feats = {k: torch.randn(rows, d, generator=g, device=dev).relu() for k, d in c.vis_fc_layers[0].items()}
+            for prec in ("bf16", "bf16x3"):
+                L.set_precision(prec)
+                M.set_single_kernel_fusion(True)
+                a32, a16 = net.encode(feats, out16_dtype=torch.bfloat16)
+                M.set_single_kernel_fusion(False)
+                b32, b16 = net.encode(feats, out16_dtype=torch.bfloat16)
+                torch.cuda.synchronize()
+                print("fused %s rows=%d %s: max|fused - two-kernel| = %.3e, out16 equal frac %.4f, norm err %.2e" % (
+                    net_kind, rows, prec, (a32 - b32).abs().max().item(), (a16 == b16).float().mean().item(),
+                    (a32.norm(dim=2) - 1).abs().max().item()))
+    M.set_single_kernel_fusion(True)
+    L.set_precision("bf16")
+    # throughput: 65536 videos, LAFF vis net
+    net = M.VisMutiTransformNetAddAttnetion(c, c.vis_fc_layers[0]).to(dev).eval()
+    rows = 65536
+    g = torch.Generator(device=dev).manual_seed(1)
+    feats = {k: torch.randn(rows, d, generator=g, device=dev).relu() for k, d in c.vis_fc_layers[0].items()}
+    for single in (True, False):
+        M.set_single_kernel_fusion(single)
+        for _ in range(2):
+            net.encode(feats, out16_dtype=torch.bfloat16)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            net.encode(feats, out16_dtype=torch.bfloat16)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print("encode %d videos single_kernel=%s: %.3f ms  %.1f TFLOP/s (39.85 MFLOP/video)  %.0f videos/s" % (
+            rows, single, ms, rows * 39.85e6 / (ms * 1e-3) / 1e12, rows / (ms * 1e-3)))
+    M.set_single_kernel_fusion(True)
+
+
+def sec_fusedprof():
+    torch = _t()
+    import numpy as np
+    from laff_b200 import config as cfg, model as M, synth
+    dev = "cuda"
+    c = cfg.laff_config(4096, 8, synth.DIMS)
+    net = M.VisMutiTransformNetAddAttnetion(c, c.vis_fc_layers[0]).to(dev).eval()
+    rows = 32768
+    g = torch.Generator(device=dev).manual_seed(1)
+    feats = {k: torch.randn(rows, d, generator=g, device=dev).relu() for k, d in c.vis_fc_layers[0].items()}
+    for _ in range(3):
+        net.encode(feats, out16_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+
+
 def sec_loss():
     torch = _t()
     from laff_b200 import ops
@@ -329,6 +397,8 @@ SECTIONS = {
     "rank_cg2_k1": lambda: sec_rank(2, 700, 9000, 4096, 1, 2, 2),
     "rank_cg2_c": lambda: sec_rank(2, 1000, 70001, 4096, 10, 16, 10),
     "fuse": sec_fuse,
+    "fused": sec_fused,
+    "fusedprof": sec_fusedprof,
     "loss": sec_loss,
     "perf_cg1": lambda: sec_perf(1, 10000, 200000, 16, 10, 3),
     "perf_cg2": lambda: sec_perf(2, 10000, 200000, 16, 10, 3),
