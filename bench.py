@@ -254,7 +254,7 @@ def run_ours(args, rank, world, local_rank):
         return retr.rank(feats_dev, gt_dev, TOPK)
 
     def step_e2e():
-        res = retr.rank(feats_host, gt_host, TOPK)      # pinned host -> device copies inside
+        res = retr.rank(feats_host, gt_host, TOPK, chunks=args.e2e_chunks)   # pinned host -> device copies inside
         return res.rank0.cpu(), res.topk_val.cpu(), res.topk_idx.cpu(), res.metrics.cpu()
 
     # ---- device-resident inputs: `value` ------------------------------------------------------------------------
@@ -350,6 +350,7 @@ def main():
     ap.add_argument("--videos", type=int, default=V_FULL)
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="query pieces whose H2D copies overlap the sweep (e2e leg)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -242,6 +242,8 @@ def attention_pool(sources: Sequence[dict], att_weight: torch.Tensor, att_bias: 
     Each source: {'y': fp32 [rows, D]} (projected) or {'x': fp32 [rows, in_dim], 'bn_scale':..., 'bn_shift':...}
     (no-transform, tiled + BN).  Returns (out fp32 [rows, heads, head_dim], out16 or None, att [rows, heads, L] or None).
     """
+    if not 1 <= len(sources) <= _capi.MAX_FEATURES:
+        raise LaffError("attention_pool: n_features=%d outside [1, %d]" % (len(sources), _capi.MAX_FEATURES))
     desc = PoolDesc()
     desc.n_features = len(sources)
     desc.heads, desc.head_dim = heads, head_dim

@@ -149,7 +149,42 @@ class Retriever:
         return out[:Q]
 
     @torch.no_grad()
-    def rank(self, caption_feat_dict, gt_global, k: int = 10) -> SearchResult:
-        """caption_feat_dict: per-encoder text features (host or device tensors); gt_global: int [Q]."""
-        q16 = self.encode_queries(caption_feat_dict)
-        return self.index.search(q16, gt_global.to(q16.device, non_blocking=True), k)
+    def rank(self, caption_feat_dict, gt_global, k: int = 10, chunks: int = 1) -> SearchResult:
+        """caption_feat_dict: per-encoder text features (host or device tensors); gt_global: int [Q].
+
+        chunks > 1 with host (pinned) inputs: the queries are cut into `chunks` pieces whose host->device copies are
+        issued up front on a copy stream; piece i is fused and swept while pieces i+1.. are still in flight, so only
+        the first piece's copy is exposed.  Results are identical to chunks = 1 (queries are independent)."""
+        first = next(iter(caption_feat_dict.values()))
+        Q = first.shape[0]
+        if chunks <= 1 or first.is_cuda or Q < 2 * chunks:
+            q16 = self.encode_queries(caption_feat_dict)
+            return self.index.search(q16, gt_global.to(q16.device, non_blocking=True), k)
+        dev = self.index.g16.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cs = self._copy_stream
+        cs.wait_stream(main)
+        per = (Q + chunks - 1) // chunks
+        staged = []
+        with torch.cuda.stream(cs):
+            for lo in range(0, Q, per):
+                hi = min(Q, lo + per)
+                part = {name: v[lo:hi].to(dev, non_blocking=True) for name, v in caption_feat_dict.items()}
+                g = gt_global[lo:hi].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                staged.append((part, g, ev))
+        outs = []
+        for part, g, ev in staged:
+            main.wait_event(ev)
+            for t in list(part.values()) + [g]:
+                t.record_stream(main)
+            q16 = self.encode_queries(part)
+            be = self.index.backend
+            res = self.index.search(q16, g, k)
+            outs.append(res)
+        rank0 = torch.cat([r.rank0 for r in outs])
+        return SearchResult(rank0, torch.cat([r.topk_val for r in outs]), torch.cat([r.topk_idx for r in outs]),
+                            self.index.backend.metrics(rank0))
