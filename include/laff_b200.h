@@ -63,6 +63,12 @@ long long laff_launch_count(int reset);
 int laff_set_tuning(int cta_group, int chunk_tiles, int m_group);
 int laff_get_tuning(int* cta_group, int* chunk_tiles, int* m_group);
 
+/* Which variant of the single-kernel fusion (laff_fuse_forward) runs: 0 = chosen per call from the row count,
+ * 1 = cta_group::1 MMAs in 2-CTA clusters (all SMs), 2 = cta_group::2 MMA pairs in 4-CTA clusters (fewer bytes per
+ * SM per k-block; 33 clusters fit a 148-SM B200).  Results are identical; only the speed differs. */
+int laff_set_fuse_variant(int cta_group);
+int laff_get_fuse_variant(void);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * S1  loss.l2norm (loss.py:8-13) applied per head, then rounding to the tensor-core operand type.
  *     x [rows, heads*head_dim] fp32, row stride ldx.  out[r, h, :] = x[r, h, :] / (||x[r, h, :]||_2 + eps)

@@ -3,11 +3,19 @@
 //   softmax over the features -> weighted sum -> L2 normalise, never writing the projected features to HBM.
 //   model/model.py:257-276 (TransformNet), :1807-1876 / :1663-1705 (nets), model/Attention.py:78-105, :508-531.
 //
-// Work unit = (128-row tile, head).  A cluster of 2 CTAs owns one unit; CTA c computes columns [256c, 256c+256) of the
-// head's 512.  Per FC feature the CTA runs a 128 x 256 x K_l GEMM into one of two TMEM accumulator buffers, so the
-// epilogue of feature l overlaps the MMAs of feature l+1.  Epilogue threads own (row, 128 columns):
+// Two variants of one kernel (template parameter CG = tcgen05 cta_group):
+//   CG = 1  work unit = (128-row tile, head), cluster of 2 CTAs; CTA c computes columns [256c, 256c+256) of the head's
+//           512 with cta_group::1 MMAs (128 x 256 x K_l).  All 148 SMs run, but each SM pulls 48 KB of operands per
+//           k-block (96 B/clk) and ends up L2->SM bound.
+//   CG = 2  work unit = (256-row tile, head), cluster of 4 CTAs = two MMA pairs; pair q computes columns
+//           [256q, 256q+256) with cta_group::2 MMAs (256 x 256 x K_l), each CTA holding 128 of the rows and loading
+//           half of the pair's W tile: 32 KB per k-block per SM (64 B/clk, as in the similarity sweep).  Only 33
+//           4-CTA clusters fit the 148 SMs (132 SMs busy), still the faster variant for large row counts.
+// Per FC feature the GEMM lands in one of two TMEM accumulator buffers, so the epilogue of feature l overlaps the
+// MMAs of feature l+1.  Epilogue threads own (row, 128 columns):
 //   pass A  y = BN(act(acc + b)), partial logit  sum_c w_h[c] y[c]           (TMEM -> registers)
-//   exchange the 4 partial logits of a row (2 column halves x 2 CTAs) through shared memory / DSMEM + a cluster mbarrier
+//   exchange the 4 partial logits of a row (2 column halves x the 2 CTAs that hold the row) through shared memory /
+//   DSMEM (st.async) + an mbarrier
 //   pass B  re-read TMEM, recompute y, online-softmax update of the running weighted sum g[128] held in registers
 // The softmax denominator cancels under the final L2 normalisation (with_ave = False), so only exp(e - max) weights are
 // kept.  "No-transform" features (raw 512-d vector tiled over the heads + BN, model/model.py:1822-1823) take the same
@@ -16,6 +24,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <atomic>
 #include <cstring>
 
 #include "gemm_engine.cuh"
@@ -23,16 +32,22 @@
 
 namespace laff {
 
-constexpr int kFuseStages = 4;
-constexpr int kFuseABytes = kBlockM * kBlockK * 2;    // 16 KB: 128 rows of x
-constexpr int kFuseBBytes = kBlockN * kBlockK * 2;    // 32 KB: 256 rows of W (= output columns)
-constexpr int kFuseStageBytes = kFuseABytes + kFuseBBytes;
 constexpr int kFuseBarBytes = 256;
 constexpr int kFuseParamBufs = 3;                          // see the staging protocol in the epilogue
 constexpr int kFuseParamFloats = kFuseParamBufs * 4 * kBlockN;  // per buffer: {bias, scale, shift, w_h} x 256 columns
 constexpr int kFuseXchgFloats = 2 * 4 * kBlockM;            // [parity][partial][row]
-constexpr int kFuseSmem = kFuseStages * kFuseStageBytes + kFuseBarBytes + (kFuseParamFloats + kFuseXchgFloats) * 4 + 1024;
-static_assert(kFuseSmem <= 227 * 1024, "fused kernel shared memory budget");
+template <int CG>
+struct FuseCfg {
+  static constexpr int kStages = (CG == 2) ? 6 : 4;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB: this CTA's 128 rows of x
+  static constexpr int kBRows = kBlockN / CG;                    // rows of W (= output columns) this CTA loads
+  static constexpr int kBBytes = kBRows * kBlockK * 2;           // 32 KB (CG 1) / 16 KB (CG 2)
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTxBytes = kStageBytes * CG;              // bytes landing per stage on the MMA issuer's barrier
+  static constexpr int kCluster = 2 * CG;
+  static constexpr int kSmem = kStages * kStageBytes + kFuseBarBytes + (kFuseParamFloats + kFuseXchgFloats) * 4 + 1024;
+  static_assert(kSmem <= 227 * 1024, "fused kernel shared memory budget");
+};
 
 struct FuseTmaps {
   CUtensorMap x[LAFF_FUSE_MAX_FC];
@@ -128,8 +143,14 @@ __device__ __forceinline__ uint16_t fuse_to16(float v, int dtype) {
   return __half_as_ushort(__float2half_rn(v));
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+template <int CG>
+__global__ void __launch_bounds__(kNumThreads, 1)
     laff_fuse_kernel(const __grid_constant__ FuseTmaps tm, const __grid_constant__ FuseParams p) {
+  using Cfg = FuseCfg<CG>;
+  constexpr int kFuseStages = Cfg::kStages;
+  constexpr int kFuseABytes = Cfg::kABytes;
+  constexpr int kFuseBBytes = Cfg::kBBytes;
+  constexpr int kFuseStageBytes = Cfg::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -153,8 +174,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = static_cast<int>(ptx::lane_id());
   const uint32_t cta_rank = ptx::cluster_ctarank();
-  const int cluster_id = static_cast<int>(blockIdx.x) >> 1;
-  const int num_clusters = static_cast<int>(gridDim.x) >> 1;
+  const int cluster_id = static_cast<int>(blockIdx.x) / Cfg::kCluster;
+  const int num_clusters = static_cast<int>(gridDim.x) / Cfg::kCluster;
+  // Which 256 columns of the head / which 128 rows of the unit this CTA holds, who issues its MMAs, and which CTA
+  // holds the other 256 columns of the same rows (the logit-exchange partner).
+  const int col_half = (CG == 2) ? static_cast<int>(cta_rank >> 1) : static_cast<int>(cta_rank);
+  const int row_sub = (CG == 2) ? static_cast<int>(cta_rank & 1u) : 0;
+  const uint32_t leader = (CG == 2) ? (cta_rank & ~1u) : cta_rank;
+  const bool is_leader = leader == cta_rank;
+  const uint32_t peer = (CG == 2) ? (cta_rank ^ 2u) : (cta_rank ^ 1u);
+  constexpr int kUnitRows = kBlockM * CG;
 
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < p.n_fc; ++l) {
@@ -169,14 +198,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), kEpiWarps);
+      ptx::mbar_init(tempty_bar(a), kEpiWarps * CG);  // every epilogue warp of the CTAs sharing the accumulator
       ptx::mbar_init(xchg_bar(a), kEpiWarps);  // local epilogue warps; the peer's partials arrive as transaction bytes
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc<1>(tmem_slot, kTmemCols);
-    ptx::tmem_relinquish<1>();
+    ptx::tmem_alloc<CG>(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish<CG>();
   }
   ptx::tcgen05_fence_before();
   ptx::cluster_sync_all();
@@ -192,14 +221,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
         uint32_t phase = 0;
         for (int u = cluster_id; u < p.total_units; u += num_clusters) {
           const int row_tile = u / p.heads, head = u - row_tile * p.heads;
-          const int m0 = row_tile * kBlockM;
-          const int n0 = head * 2 * kBlockN + static_cast<int>(cta_rank) * kBlockN;
+          const int m0 = row_tile * kUnitRows + row_sub * kBlockM;
+          const int n0 = head * 2 * kBlockN + col_half * kBlockN + row_sub * Cfg::kBRows;
           for (int l = 0; l < p.n_fc; ++l) {
             for (int kb = 0; kb < p.num_kb[l]; ++kb) {
               ptx::mbar_wait_nocall(empty_bar(stage), phase ^ 1u);
-              ptx::mbar_arrive_expect_tx(full_bar(stage), kFuseStageBytes);
-              ptx::tma_load_2d(sA + stage * kFuseABytes, &tm.x[l], full_bar(stage), kb * kBlockK, m0, ptx::kEvictNormal);
-              ptx::tma_load_2d(sB + stage * kFuseBBytes, &tm.w[l], full_bar(stage), kb * kBlockK, n0, ptx::kEvictLast);
+              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kTxBytes);
+              if constexpr (CG == 1) {
+                ptx::tma_load_2d(sA + stage * kFuseABytes, &tm.x[l], full_bar(stage), kb * kBlockK, m0, ptx::kEvictNormal);
+                ptx::tma_load_2d(sB + stage * kFuseBBytes, &tm.w[l], full_bar(stage), kb * kBlockK, n0, ptx::kEvictLast);
+              } else {
+                const uint32_t leader_full = ptx::mapa(full_bar(stage), leader);
+                ptx::tma_load_2d_pair(sA + stage * kFuseABytes, &tm.x[l], leader_full, kb * kBlockK, m0, ptx::kEvictNormal);
+                ptx::tma_load_2d_pair(sB + stage * kFuseBBytes, &tm.w[l], leader_full, kb * kBlockK, n0, ptx::kEvictLast);
+              }
               if (++stage == kFuseStages) { stage = 0; phase ^= 1u; }
             }
           }
@@ -207,11 +242,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
       }
     } else if (warp == 1) {
       // ========================================== MMA issuer ==========================================
-      if (lane == 0) {
+      if (is_leader && lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        const uint16_t pair_mask = static_cast<uint16_t>(3u << leader);
+        auto commit = [&](uint32_t bar) {
+          if constexpr (CG == 1) ptx::umma_commit<1>(bar);
+          else ptx::umma_commit_pair_mask(bar, pair_mask);
+        };
         for (int u = cluster_id; u < p.total_units; u += num_clusters) {
           for (int l = 0; l < p.n_fc; ++l) {
             ptx::mbar_wait_nocall(tempty_bar(acc), acc_phase ^ 1u);
@@ -224,11 +264,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
               const uint64_t db = ptx::make_smem_desc_sw128(sB + stage * kFuseBBytes);
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                ptx::umma_f16<1>(d_tmem, da + 2u * k, db + 2u * k, p.idesc, static_cast<uint32_t>((kb | k) != 0));
-              ptx::umma_commit<1>(empty_bar(stage));
+                ptx::umma_f16<CG>(d_tmem, da + 2u * k, db + 2u * k, p.idesc, static_cast<uint32_t>((kb | k) != 0));
+              commit(empty_bar(stage));
               if (++stage == kFuseStages) { stage = 0; phase ^= 1u; }
             }
-            ptx::umma_commit<1>(tfull_bar(acc));
+            commit(tfull_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
           }
         }
@@ -242,8 +282,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
     const int half = (warp - 4) >> 2;
     const int row_in_cta = quad * 32 + lane;
     const int epi_tid = half * kBlockM + row_in_cta;       // 0..255
-    const int my_part = half + 2 * static_cast<int>(cta_rank);
-    const uint32_t peer = cta_rank ^ 1u;
+    const int my_part = half + 2 * col_half;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t xchg_count = 0;  // exchanges done so far: parity = count & 1, phase = (count >> 1) & 1
@@ -279,7 +318,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
     auto load_params = [&](int f, int hd, float (&v)[4]) {
       const bool tl = f < p.n_tiled;
       const int l = tl ? f : f - p.n_tiled;
-      const int col = hd * 2 * kBlockN + static_cast<int>(cta_rank) * kBlockN + epi_tid;
+      const int col = hd * 2 * kBlockN + col_half * kBlockN + epi_tid;
       const float* bs = tl ? nullptr : p.bias[l];
       const float* sc = tl ? p.tiled_scale[l] : p.bn_scale[l];
       const float* sh = tl ? p.tiled_shift[l] : p.bn_shift[l];
@@ -305,9 +344,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
     fptx::epi_bar_sync();
     for (int u = cluster_id; u < p.total_units; u += num_clusters) {
       const int row_tile = u / p.heads, head = u - row_tile * p.heads;
-      const long long row = static_cast<long long>(row_tile) * kBlockM + row_in_cta;
+      const long long row = static_cast<long long>(row_tile) * kUnitRows + row_sub * kBlockM + row_in_cta;
       const bool row_ok = row < p.rows;
-      const int colbase = head * 2 * kBlockN + static_cast<int>(cta_rank) * kBlockN;  // first global column of this CTA
+      const int colbase = head * 2 * kBlockN + col_half * kBlockN;                   // first global column of this CTA
       const int mycol = half * kEpiCols;                                             // first column (in CTA) of this thread
 
       float g[kEpiCols];
@@ -418,7 +457,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
         if (!tiled) {
           ptx::tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
+            else ptx::mbar_arrive_remote(tempty_bar(acc), leader);
+          }
           if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
         stage_buf = stage_buf == kFuseParamBufs - 1 ? 0 : stage_buf + 1;
@@ -471,13 +513,73 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
   ptx::cluster_sync_all();
   if (warp == 2) {
     ptx::tcgen05_fence_after();
-    ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
+    ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
   }
 }
 
 }  // namespace laff
 
 using namespace laff;
+
+namespace {
+
+std::atomic<int> g_fuse_variant{0};  // 0 = choose per call, 1 / 2 = force the cta_group::1 / ::2 kernel
+
+// Co-resident clusters of the given variant (4-CTA clusters cannot straddle a GPC: 33 fit on a 148-SM B200).
+template <int CG>
+int fuse_max_clusters(int sms, int* out) {
+  static int cached = 0;
+  if (!cached) {
+    auto kern = laff_fuse_kernel<CG>;
+    LAFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FuseCfg<CG>::kSmem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(sms / FuseCfg<CG>::kCluster * FuseCfg<CG>::kCluster));
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = FuseCfg<CG>::kSmem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = FuseCfg<CG>::kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    LAFF_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    LAFF_REQUIRE(n > 0, LAFF_ENODEV, "laff_fuse_forward: no %d-CTA cluster of the fused kernel fits this device", FuseCfg<CG>::kCluster);
+    cached = n;
+  }
+  *out = cached;
+  return LAFF_OK;
+}
+
+template <int CG>
+int fuse_launch(const FuseTmaps& tm, const FuseParams& p, int clusters, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * FuseCfg<CG>::kCluster));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = FuseCfg<CG>::kSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = FuseCfg<CG>::kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LAFF_CUDA(cudaLaunchKernelEx(&cfg, laff_fuse_kernel<CG>, tm, p));
+  count_launch();
+  return LAFF_OK;
+}
+
+}  // namespace
+
+extern "C" int laff_set_fuse_variant(int cta_group) {
+  LAFF_REQUIRE(cta_group >= 0 && cta_group <= 2, LAFF_EINVAL, "laff_set_fuse_variant: cta_group must be 0 (auto), 1 or 2");
+  g_fuse_variant.store(cta_group);
+  return LAFF_OK;
+}
+
+extern "C" int laff_get_fuse_variant(void) { return g_fuse_variant.load(); }
 
 extern "C" int laff_fuse_forward(const laff_fuse_desc* d, long long rows, float* out, long long ld_out, void* out16,
                                  int out16_dtype, long long ld_out16, void* stream) {
@@ -498,6 +600,26 @@ extern "C" int laff_fuse_forward(const laff_fuse_desc* d, long long rows, float*
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
+  // Variant: wall time ~ waves x unit time; a cta_group::2 unit covers twice the rows in ~4/3 of the time, but only
+  // the clusters that fit the GPCs run at once.
+  int max1 = 0, max2 = 0;
+  rc = fuse_max_clusters<1>(di.sms, &max1);
+  if (rc) return rc;
+  rc = fuse_max_clusters<2>(di.sms, &max2);
+  if (rc) return rc;
+  const long long units1 = (rows + kBlockM - 1) / kBlockM * d->heads;
+  const long long units2 = (rows + 2 * kBlockM - 1) / (2 * kBlockM) * d->heads;
+  int cg = g_fuse_variant.load();
+  if (cg == 0) {
+    // Measured (profiles/README.md): the pair variant only wins when a wide feature (K >= 3072, the 3981-word BoW)
+    // makes the kernel operand-feed bound; otherwise running on all 148 SMs is worth more than the cheaper feed.
+    int kmax = 0;
+    for (int l = 0; l < d->n_fc; ++l) kmax = d->fc[l].K > kmax ? d->fc[l].K : kmax;
+    const long long waves1 = (units1 + max1 - 1) / max1;
+    const long long waves2 = (units2 + max2 - 1) / max2;
+    cg = (kmax >= 3072 && waves2 * 5 <= waves1 * 6) ? 2 : 1;  // a pair wave takes ~0.83 of a cta_group::1 wave there
+  }
+  const int b_rows = kBlockN / cg;
   FuseTmaps tm;
   FuseParams p;
   memset(&tm, 0, sizeof(tm));
@@ -514,7 +636,7 @@ extern "C" int laff_fuse_forward(const laff_fuse_desc* d, long long rows, float*
                  "laff_fuse_forward: fc feature %d: bad bn/activation", l);
     rc = make_tmap_2d(&tm.x[l], f.x16, d->dtype, static_cast<uint64_t>(rows), static_cast<uint64_t>(f.K), static_cast<uint64_t>(f.ldx), kBlockM);
     if (rc) return rc;
-    rc = make_tmap_2d(&tm.w[l], f.w16, d->dtype, static_cast<uint64_t>(D), static_cast<uint64_t>(f.K), static_cast<uint64_t>(f.ldw), kBlockN);
+    rc = make_tmap_2d(&tm.w[l], f.w16, d->dtype, static_cast<uint64_t>(D), static_cast<uint64_t>(f.K), static_cast<uint64_t>(f.ldw), static_cast<uint32_t>(b_rows));
     if (rc) return rc;
     p.num_kb[l] = (f.K + kBlockK - 1) / kBlockK;
     p.act[l] = f.activation;
@@ -541,18 +663,12 @@ extern "C" int laff_fuse_forward(const laff_fuse_desc* d, long long rows, float*
   p.out16_dtype = out16_dtype;
   p.ld_out16 = ld_out16;
   p.norm_eps = static_cast<float>(d->norm_eps);
-  p.idesc = make_idesc_f16(d->dtype, kBlockM, kBlockN);
-  const long long row_tiles = (rows + kBlockM - 1) / kBlockM;
-  p.total_units = static_cast<int>(row_tiles * d->heads);
-  static bool configured = false;
-  if (!configured) {
-    LAFF_CUDA(cudaFuncSetAttribute(laff_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuseSmem));
-    configured = true;
-  }
-  int clusters = di.sms / 2;
+  p.idesc = make_idesc_f16(d->dtype, kBlockM * cg, kBlockN);
+  const long long units = cg == 2 ? units2 : units1;
+  LAFF_REQUIRE(units < (1LL << 31), LAFF_ENOTSUP, "laff_fuse_forward: too many work units");
+  p.total_units = static_cast<int>(units);
+  int clusters = cg == 2 ? max2 : max1;
   if (clusters > p.total_units) clusters = p.total_units;
-  laff_fuse_kernel<<<clusters * 2, kNumThreads, kFuseSmem, static_cast<cudaStream_t>(stream)>>>(tm, p);
-  count_launch();
-  LAFF_CUDA(cudaGetLastError());
-  return LAFF_OK;
+  if (cg == 2) return fuse_launch<2>(tm, p, clusters, static_cast<cudaStream_t>(stream));
+  return fuse_launch<1>(tm, p, clusters, static_cast<cudaStream_t>(stream));
 }

@@ -192,6 +192,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   }
 }
 
+// cta_group::2 commit whose arrival is multicast to the CTAs named by `mask` (cluster ranks): for clusters that hold
+// more than one MMA pair.
+__device__ __forceinline__ void umma_commit_pair_mask(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns; thread t receives lane t's columns.
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -31,6 +31,7 @@ from . import loss as _loss
 from .loss import MarginRankingLoss, MarginRankingLossWithScore
 
 _ROW_CHUNK = 32768  # rows fused per pass: bounds the projected-feature scratch to L * 512 MB
+_FUSED_ROW_CHUNK = 131072  # rows per laff_fuse_forward launch: bounds the 16-bit input copies (1.3 GB for the video net)
 
 
 def _cuda_device(hint: Optional[torch.device] = None) -> torch.device:
@@ -245,20 +246,38 @@ def set_single_kernel_fusion(flag: bool) -> None:
     _SINGLE_KERNEL = bool(flag)
 
 
-def _fuse_single_kernel(features, attention, precision, out16_dtype):
-    """All projections + pooling in one kernel (csrc/fused.cu)."""
-    fc, tiled = [], []
-    for x, tn in features:
-        c = tn.prepared(precision)
-        if tn.fc1 is not None:
-            x16 = ops.split3_16(x, 0, torch.bfloat16) if precision == "bf16x3" else ops.cast_pad_16(x, _op_dtype(precision))
-            fc.append({"x16": x16, "w16": c["w16"], "bias": c["bias"], "activation": tn.activation_name,
-                       "bn_scale": c.get("bn_scale"), "bn_shift": c.get("bn_shift")})
-        else:
-            tiled.append({"x": x, "bn_scale": c.get("bn_scale"), "bn_shift": c.get("bn_shift")})
+def _fuse_single_kernel(features, attention, precision, out16_dtype, want_f32=True):
+    """All projections + pooling in one kernel (csrc/fused.cu), `_FUSED_ROW_CHUNK` rows per launch so the 16-bit copies
+    of the input features stay a bounded scratch (a 1 M-video gallery shard is fused in 8 launches)."""
+    B = features[0][0].shape[0]
+    dev = features[0][0].device
+    D = attention.multi_heads * attention.dim_per_head
     w, b = attention.head_params()
-    return ops.fuse_forward(fc, tiled, w, b, attention.multi_heads, attention.dim_per_head, want_f32=True,
-                            out16_dtype=out16_dtype)
+    prepared = [tn.prepared(precision) for _, tn in features]
+    out = torch.empty((B, D), dtype=torch.float32, device=dev) if want_f32 else None
+    out16 = torch.empty((B, D), dtype=ops.torch_dtype(out16_dtype), device=dev) if out16_dtype is not None else None
+    chunk = min(max(B, 1), _FUSED_ROW_CHUNK)
+    scratch: Dict[int, torch.Tensor] = {}
+    for s in range(0, B, chunk):
+        e = min(B, s + chunk)
+        fc, tiled = [], []
+        for i, ((x, tn), c) in enumerate(zip(features, prepared)):
+            xs = x[s:e]
+            if tn.fc1 is not None:
+                if precision == "bf16x3":
+                    x16 = ops.split3_16(xs, 0, torch.bfloat16)
+                else:
+                    if B > chunk and i not in scratch:
+                        scratch[i] = torch.empty((chunk, (x.shape[1] + 7) // 8 * 8), dtype=_op_dtype(precision), device=dev)
+                    x16 = ops.cast_pad_16(xs, _op_dtype(precision), out=scratch.get(i))
+                fc.append({"x16": x16, "w16": c["w16"], "bias": c["bias"], "activation": tn.activation_name,
+                           "bn_scale": c.get("bn_scale"), "bn_shift": c.get("bn_shift")})
+            else:
+                tiled.append({"x": xs, "bn_scale": c.get("bn_scale"), "bn_shift": c.get("bn_shift")})
+        ops.fuse_forward(fc, tiled, w, b, attention.multi_heads, attention.dim_per_head, want_f32=False,
+                         out=None if out is None else out[s:e], out16=None if out16 is None else out16[s:e])
+    H, dh = attention.multi_heads, attention.dim_per_head
+    return (None if out is None else out.view(B, H, dh)), (None if out16 is None else out16.view(B, H, dh))
 
 
 def _single_kernel_ok(features, attention, want_att) -> bool:
@@ -273,12 +292,12 @@ def _single_kernel_ok(features, attention, want_att) -> bool:
 
 
 def _fuse(features: Sequence, attention: Multi_head_MyApply_Attention, device, precision, out16_dtype=None,
-          want_att=False):
+          want_att=False, want_f32=True):
     """features: list of (x fp32 [B, d] device tensor, TransformNet).  One fused kernel when the configuration allows
     (head_dim 512, with_ave = mul = False, attention weights not requested); otherwise projection GEMMs + pooling kernel,
     chunked by rows."""
     if _single_kernel_ok(features, attention, want_att):
-        return _fuse_single_kernel(features, attention, precision, out16_dtype)
+        return _fuse_single_kernel(features, attention, precision, out16_dtype, want_f32 or out16_dtype is None)
     B = features[0][0].shape[0]
     D = attention.multi_heads * attention.dim_per_head
     outs, outs16 = [], []
@@ -351,14 +370,16 @@ class VisMutiTransformNetAddAttnetion(nn.Module):
         self.attention_layer = get_attention_layer(opt.vis_attention, self.common_space_dim, len(space_dict), opt)
         self.expert_embedding = None
 
-    def encode(self, vis_input, out16_dtype=None, precision=None, want_att=False):
+    def encode(self, vis_input, out16_dtype=None, precision=None, want_att=False, want_f32=True):
+        """-> (fp32 [B, H, d_h] embeddings, 16-bit copy or None).  want_f32 = False with an out16_dtype skips the fp32
+        copy where the single-kernel path runs (gallery encoding keeps only the 16-bit rows)."""
         precision = precision or _loss.get_precision()
         dev = _cuda_device(self.attention_layer.layer_norm.weight.device)
         if self.training:
             raise NotImplementedError("train-mode forward of the fusion net is SURVEY §8f N4; call .eval()")
         mods = dict(self.VisMutiTransformNet.named_children())
         feats = [(vis_input[name].to(dev, non_blocking=True).float(), mods[name]) for name in self.vis_net_space_dict.keys()]
-        return _fuse(feats, self.attention_layer, dev, precision, out16_dtype, want_att)
+        return _fuse(feats, self.attention_layer, dev, precision, out16_dtype, want_att, want_f32)
 
     def forward(self, vis_input, txt_emb=None, vis_frame_feat_dict_input=None):
         return self.encode(vis_input)[0]
@@ -472,7 +493,7 @@ class VisMutiTransformNetPlusFrameFeat(nn.Module):
         return ops.frame_pool(frames, lin.weight, float(lin.bias.item()), att.with_ave, att.mul,
                               omega=float(att.global_emb_weight_net.weight.item()) if att.with_ave else 0.0)
 
-    def encode(self, vis_input, vis_frame_feat_dict_input, out16_dtype=None, precision=None):
+    def encode(self, vis_input, vis_frame_feat_dict_input, out16_dtype=None, precision=None, want_f32=True):
         precision = precision or _loss.get_precision()
         dev = _cuda_device(self.vis_attention_layer.layer_norm.weight.device)
         if self.training:
@@ -484,7 +505,7 @@ class VisMutiTransformNetPlusFrameFeat(nn.Module):
             feats_in[feat_name] = self.frame_pool(feat_name, fr.to(dev, non_blocking=True).float())
         mods = dict(self.named_children())
         feats = [(x.to(dev, non_blocking=True).float(), mods[name]) for name, x in feats_in.items()]
-        return _fuse(feats, self.vis_attention_layer, dev, precision, out16_dtype)
+        return _fuse(feats, self.vis_attention_layer, dev, precision, out16_dtype, False, want_f32)
 
     def forward(self, vis_input, vis_frame_feat_dict_input, txt_emb=None):
         return self.encode(vis_input, vis_frame_feat_dict_input)[0]

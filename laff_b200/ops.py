@@ -55,6 +55,15 @@ def get_tuning() -> tuple[int, int, int]:
     return a.value, b.value, c.value
 
 
+def set_fuse_variant(cta_group: int = 0) -> None:
+    """0 = per-call choice, 1 / 2 = force the cta_group::1 / ::2 single-kernel fusion (include/laff_b200.h)."""
+    _capi.call("laff_set_fuse_variant", cta_group)
+
+
+def get_fuse_variant() -> int:
+    return int(_capi.lib().laff_get_fuse_variant())
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # operand preparation
 # ----------------------------------------------------------------------------------------------------------------
@@ -75,14 +84,20 @@ def l2norm_quantize(x: torch.Tensor, heads: int, out_dtype=torch.bfloat16, eps: 
     return out.reshape(shape)
 
 
-def cast_pad_16(x: torch.Tensor, dtype=torch.bfloat16, multiple: int = 8) -> torch.Tensor:
-    """fp32 [rows, cols] -> 16-bit [rows, cols_pad] with zero padding so the row pitch is TMA-legal."""
+def cast_pad_16(x: torch.Tensor, dtype=torch.bfloat16, multiple: int = 8, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> 16-bit [rows, cols_pad] with zero padding so the row pitch is TMA-legal.  `out`: optional
+    16-bit scratch of at least [rows, cols_pad] to write into (its first `rows` rows are returned)."""
     _need_cuda(x)
     x2 = _rowmajor(x.float() if x.dtype != torch.float32 else x)
     rows, cols = x2.shape
     cols_pad = (cols + multiple - 1) // multiple * multiple
     dtype = torch_dtype(dtype)
-    out = torch.empty((rows, cols_pad), dtype=dtype, device=x.device)
+    if out is None:
+        out = torch.empty((rows, cols_pad), dtype=dtype, device=x.device)
+    else:
+        if out.dtype != dtype or out.dim() != 2 or out.shape[0] < rows or out.shape[1] != cols_pad or out.stride(1) != 1:
+            raise LaffError("cast_pad_16: out must be a %s [>=%d, %d] row-major tensor" % (dtype, rows, cols_pad))
+        out = out[:rows]
     if rows:
         _capi.call("laff_cast_pad_16", _ptr(x2), rows, cols, x2.stride(0), _DT[dtype], _ptr(out), cols_pad,
                    out.stride(0), _stream(x))
@@ -290,12 +305,14 @@ def attention_pool(sources: Sequence[dict], att_weight: torch.Tensor, att_bias: 
 
 
 def fuse_forward(fc: Sequence[dict], tiled: Sequence[dict], att_weight: torch.Tensor, att_bias: torch.Tensor, heads: int,
-                 head_dim: int, want_f32: bool = True, out16_dtype=None, norm_eps: float = 1e-14):
+                 head_dim: int, want_f32: bool = True, out16_dtype=None, norm_eps: float = 1e-14,
+                 out: Optional[torch.Tensor] = None, out16: Optional[torch.Tensor] = None):
     """All projections + LAFF pooling in ONE kernel (laff_fuse_forward; head_dim 512, with_ave = mul = False).
 
     fc:    [{'x16': [rows, K] 16-bit, 'w16': [D, K] 16-bit, 'bias': fp32 [D] or None, 'activation': name/int,
              'bn_scale': fp32 [D] or None, 'bn_shift': ...}]
     tiled: [{'x': fp32 [rows, in_dim], 'bn_scale': ..., 'bn_shift': ...}]
+    out / out16: optional preallocated [rows, heads*head_dim] destinations (row-major; fp32 / 16-bit).
     Returns (out fp32 [rows, heads, head_dim] or None, out16 or None)."""
     if not (1 <= len(fc) <= FUSE_MAX_FC and len(tiled) <= FUSE_MAX_TILED):
         raise LaffError("fuse_forward supports 1..%d projected and up to %d tiled features" % (FUSE_MAX_FC, FUSE_MAX_TILED))
@@ -336,15 +353,28 @@ def fuse_forward(fc: Sequence[dict], tiled: Sequence[dict], att_weight: torch.Te
     d.dtype = _DT[dt]
     dev = keep[2].device
     D = heads * head_dim
-    out = torch.empty((rows, D), dtype=torch.float32, device=dev) if want_f32 else None
-    out16 = None
+    def _dest(t, dtype, what):
+        if t.dtype != dtype or t.dim() != 2 or tuple(t.shape) != (rows, D) or t.stride(1) != 1 or not t.is_cuda:
+            raise LaffError("fuse_forward: %s must be a CUDA %s [%d, %d] tensor with contiguous rows" % (what, dtype, rows, D))
+        return t
+
+    if out is not None:
+        out = _dest(out, torch.float32, "out")
+    elif want_f32:
+        out = torch.empty((rows, D), dtype=torch.float32, device=dev)
     o16 = 0
-    if out16_dtype is not None:
+    if out16 is not None:
+        out16 = _dest(out16, out16.dtype if out16_dtype is None else torch_dtype(out16_dtype), "out16")
+        o16 = _DT[out16.dtype]
+    elif out16_dtype is not None:
         out16_dtype = torch_dtype(out16_dtype)
         out16 = torch.empty((rows, D), dtype=out16_dtype, device=dev)
         o16 = _DT[out16_dtype]
+    if out is None and out16 is None:
+        raise LaffError("fuse_forward: nothing to write (want_f32 = False and no 16-bit output)")
     if rows:
-        _capi.call("laff_fuse_forward", C.byref(d), rows, _ptr(out), D, _ptr(out16), o16, D, _stream(keep[2]))
+        _capi.call("laff_fuse_forward", C.byref(d), rows, _ptr(out), 0 if out is None else out.stride(0), _ptr(out16), o16,
+                   0 if out16 is None else out16.stride(0), _stream(keep[2]))
     return (None if out is None else out.view(rows, heads, head_dim)), (None if out16 is None else out16.view(rows, heads, head_dim))
 
 

@@ -75,6 +75,22 @@ class GalleryIndex:
         self._ws = None
         self.timers = None  # set to a list to collect (start, end) CUDA events around every sweep launch
 
+    @classmethod
+    @torch.no_grad()
+    def from_features(cls, vis_net, vis_input, total: int, rank: int = 0, world_size: int = 1, group=None,
+                      backend=None, frame_input=None, out16_dtype=torch.bfloat16):
+        """Fuse this rank's shard of raw video features into the resident 16-bit gallery (the reference's
+        `vis_net(vis_input)` loop over the gallery loader, model/model.py:1036-1049, data-parallel over the shard; no
+        communication).  vis_input: dict name -> [rows of this shard, d_l] tensors (host or device); frame_input: the
+        LAFF-ml frame-feature dict."""
+        if frame_input is not None:
+            _, g16 = vis_net.encode(vis_input, frame_input, out16_dtype=out16_dtype, want_f32=False)
+        else:
+            _, g16 = vis_net.encode(vis_input, out16_dtype=out16_dtype, want_f32=False)
+        heads = g16.shape[1]
+        g16 = g16.reshape(g16.shape[0], -1)
+        return cls(g16, total, heads, rank, world_size, group, backend)
+
     def _all_reduce(self, t):
         if self.world_size > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -182,7 +198,6 @@ class Retriever:
             for t in list(part.values()) + [g]:
                 t.record_stream(main)
             q16 = self.encode_queries(part)
-            be = self.index.backend
             res = self.index.search(q16, g, k)
             outs.append(res)
         rank0 = torch.cat([r.rank0 for r in outs])

@@ -211,11 +211,21 @@ def test_train_mode_is_refused_not_faked():
         M.get_attention_layer("muti_head_attention_official", 256, 4, cfg.laff_config(256, 8))
 
 
+@pytest.fixture
+def fuse_variant(request):
+    ops.set_fuse_variant(request.param)
+    yield request.param
+    ops.set_fuse_variant(0)
+
+
+@pytest.mark.parametrize("fuse_variant", [1, 2], indirect=True)
 @pytest.mark.parametrize("kind", ["laff_txt", "laff_vis", "frame_vis"])
-def test_single_kernel_fusion_vs_two_kernel_path_and_oracle(kind):
-    """laff_fuse_forward (all projections + pooling in one kernel) against the two-kernel path and the oracle, at the
-    real dimensions, for ragged row counts, with and without BatchNorm (LAFF-ml has BN on every FC feature)."""
+def test_single_kernel_fusion_vs_two_kernel_path_and_oracle(kind, fuse_variant):
+    """laff_fuse_forward (all projections + pooling in one kernel; both the cta_group::1 / 2-CTA-cluster and the
+    cta_group::2 / 4-CTA-cluster variants) against the two-kernel path and the oracle, at the real dimensions, for
+    ragged row counts, with and without BatchNorm (LAFF-ml has BN on every FC feature)."""
     from laff_b200 import _capi
+    assert ops.get_fuse_variant() == fuse_variant
     r = synth.rng_for(21, kind)
     if kind == "frame_vis":
         c = cfg.frame_laff_config(4096, 8, synth.DIMS)
@@ -227,7 +237,7 @@ def test_single_kernel_fusion_vs_two_kernel_path_and_oracle(kind):
           for k, v in net.state_dict().items()}
     load_numpy_state(net, sd)
     net = net.cuda().eval()
-    for rows in (1, 127, 129, 300):
+    for rows in (1, 127, 129, 300, 700):
         if kind == "laff_txt":
             feats = {"gru": synth.bf16_round(r.standard_normal((rows, 1024)).astype(np.float32)),
                      "bow": r.randint(0, 3, (rows, 3981)).astype(np.float32),
