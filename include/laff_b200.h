@@ -137,6 +137,29 @@ int laff_topk_merge(const float* vals, const int32_t* idx, int n_lists, int Q, i
 int laff_rank_from_scores(const float* scores, int Q, int V, long long ld, const int32_t* gt, int k, int32_t* rank0,
                           float* topk_val, int32_t* topk_idx, void* stream);
 
+/* Ranked lists for the result writers (predictor.py:53-88 txt2video_write_to_file: `inds[index][::-1][0:TopK]`,
+ * TopK = 2000 for id.sent.score.txt, 500 for t2v.pkl): top-k of every row of a dense fp32 matrix scores[rows, cols]
+ * (row pitch ld), 1 <= k <= LAFF_MAX_TOPK_DENSE, ordered by the tie rule above (score desc, index desc).
+ *   idx_in == NULL: candidate j of a row has index j (any cols < 2^31).
+ *   idx_in != NULL: int32 [rows, cols] (pitch ld_idx) indices carried by the candidates, -1 = empty slot; cols <= 16384.
+ *                   Used to merge the all_gather'ed per-shard lists of a sharded gallery.
+ * out_val[i, r] = scale * score, out_idx[i, r] = index; slots past the number of candidates: -inf / -1. */
+#define LAFF_MAX_TOPK_DENSE 2048
+int laff_topk_dense(const float* scores, long long ld, const int32_t* idx_in, long long ld_idx, int rows, long long cols,
+                    int k, float scale, float* out_val, int32_t* out_idx, void* stream);
+
+/* Video -> text direction (predictor.py:262-270): a row has several ground-truth columns (the captions of the video),
+ * given as CSR lists gt_cols[gt_offsets[i] .. gt_offsets[i+1]).  rank0[e] = 0-based rank of ground truth e in its row
+ * under the tie rule (-1 for a column outside [0, cols)). */
+int laff_rank_multi_gt(const float* scores, long long ld, int rows, long long cols, const long long* gt_offsets,
+                       const int32_t* gt_cols, int32_t* rank0, void* stream);
+
+/* evaluation.eval (evaluation.py:92-109) from laff_rank_multi_gt's ranks: first[i] = rank of the best-ranked ground
+ * truth of row i, ap[i] = mean_t (t + 1) / (r_(t) + 1) over its ground truths sorted by rank; out8 as laff_rank_metrics
+ * with [6] = mAP = mean(ap).  Every row must own at least one ground truth (the reference raises IndexError). */
+int laff_multi_gt_metrics(const int32_t* rank0, const long long* gt_offsets, int rows, int32_t* first, double* ap,
+                          double* out8, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * E3  evaluation.eval_qry2retro metrics (evaluation.py:81-89) / evaluation.eval (evaluation.py:105-109) on device.
  *     rank0 int32 [Q] (0-based rank of the first ground truth).  out (device, 8 doubles):

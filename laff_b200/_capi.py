@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "liblaff_b200.so")
 F16, BF16, F32 = 0, 1, 2
 MAX_FEATURES = 8
 MAX_TOPK = 16
+MAX_TOPK_DENSE = 2048
 ACT = {None: 0, False: 0, "none": 0, "tanh": 1, "relu": 2, "sigmoid": 3}
 DIRECTION = {"t2i": 0, "i2t": 1, "bidir": 2}
 
@@ -88,6 +89,9 @@ SIGNATURES = {
     "laff_sim_rank_topk": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _f, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "laff_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _ll, _i, _f, _vp, _vp, _vp]),
     "laff_rank_from_scores": (_i, [_vp, _i, _i, _ll, _vp, _i, _vp, _vp, _vp, _vp]),
+    "laff_topk_dense": (_i, [_vp, _ll, _vp, _ll, _i, _ll, _i, _f, _vp, _vp, _vp]),
+    "laff_rank_multi_gt": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _vp, _vp]),
+    "laff_multi_gt_metrics": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "laff_rank_metrics": (_i, [_vp, _i, _vp, _vp]),
     "laff_label_metrics": (_i, [_vp, _i, _i, _ll, _vp, _vp, _vp, _vp]),
     "laff_project": (_i, [_vp, _vp, _ll, _i, _i, _ll, _ll, _i, _vp, _i, _vp, _vp, _vp, _ll, _vp]),

@@ -113,13 +113,15 @@ __device__ __forceinline__ void mbar_arrive_release_cluster_local(uint32_t bar) 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 }  // namespace fptx
 
-// One code path for every activation (the per-row epilogue is unrolled 128x, so instruction-cache footprint matters):
-//   tanh(z) = 2 / (1 + 2^(-2 z log2e)) - 1,  sigmoid(z) = 1 / (1 + 2^(-z log2e)),  relu / none = max(z, floor)
-// with the hardware ex2 / rcp approximations (|error| < 3e-7 absolute).
+// Activations in the epilogue, with every per-column constant folded on the host side of the loop (load_params):
+//   tanh(z) = 2 / (1 + 2^(-2 z log2e)) - 1,  sigmoid(z) = 1 / (1 + 2^(-z log2e))     ("sigm" family: a / (1 + 2^(n z)) + c)
+//   y = BN(act(acc + b)) = A' * rcp(1 + ex2(acc * n + n b)) + C'   with  A' = a * scale,  C' = c * scale + shift
+//   relu / none: y = max(acc + b, floor) * scale + shift
+// ex2.approx / rcp.approx: |error| < 3e-7 absolute on y.
 struct ActCoef {
-  float neg_s;   // -s * log2(e)   (sigmoidal branch)
-  float a, c;    // y = a / (1 + 2^(neg_s z)) + c
-  float floor;   // piecewise-linear branch: y = max(z, floor)
+  float neg_s;   // n = -s * log2(e)
+  float a, c;
+  float floor;   // piecewise-linear family: -inf for 'none', 0 for relu
   bool sigm;
 };
 __device__ __forceinline__ ActCoef make_act(int act) {
@@ -132,11 +134,57 @@ __device__ __forceinline__ ActCoef make_act(int act) {
   k.floor = act == LAFF_ACT_RELU ? 0.0f : -INFINITY;
   return k;
 }
-__device__ __forceinline__ float apply_act(float z, const ActCoef& k) {
+__device__ __forceinline__ float ex2_approx(float x) {
   float t;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(k.neg_s * z));
-  const float sg = fmaf(k.a, __fdividef(1.0f, 1.0f + t), k.c);
-  return k.sigm ? sg : fmaxf(z, k.floor);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+// One 16-column chunk of pass A: r holds the accumulators on entry and y on exit; returns the running partial logit.
+// p0/p1/p2 are the folded per-column constants described above, pw the attention weights w_h.
+constexpr int kFuseChunk = 16;
+__device__ __forceinline__ float pass_a_chunk(uint32_t (&r)[kFuseChunk], const float* p0, const float* p1, const float* p2,
+                                              const float* pw, const ActCoef& ak, float part) {
+  if (ak.sigm) {
+#pragma unroll
+    for (int j = 0; j < kFuseChunk; j += 4) {
+      const float4 n4 = *reinterpret_cast<const float4*>(p0 + j);
+      const float4 a4 = *reinterpret_cast<const float4*>(p1 + j);
+      const float4 c4 = *reinterpret_cast<const float4*>(p2 + j);
+      const float4 w4 = *reinterpret_cast<const float4*>(pw + j);
+      const float y0 = fmaf(a4.x, rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(r[j]), ak.neg_s, n4.x))), c4.x);
+      const float y1 = fmaf(a4.y, rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(r[j + 1]), ak.neg_s, n4.y))), c4.y);
+      const float y2 = fmaf(a4.z, rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(r[j + 2]), ak.neg_s, n4.z))), c4.z);
+      const float y3 = fmaf(a4.w, rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(r[j + 3]), ak.neg_s, n4.w))), c4.w);
+      part = fmaf(w4.x, y0, part);
+      part = fmaf(w4.y, y1, part);
+      part = fmaf(w4.z, y2, part);
+      part = fmaf(w4.w, y3, part);
+      r[j] = __float_as_uint(y0); r[j + 1] = __float_as_uint(y1); r[j + 2] = __float_as_uint(y2); r[j + 3] = __float_as_uint(y3);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kFuseChunk; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(p0 + j);
+      const float4 a4 = *reinterpret_cast<const float4*>(p1 + j);
+      const float4 c4 = *reinterpret_cast<const float4*>(p2 + j);
+      const float4 w4 = *reinterpret_cast<const float4*>(pw + j);
+      const float y0 = fmaf(fmaxf(__uint_as_float(r[j]) + b4.x, ak.floor), a4.x, c4.x);
+      const float y1 = fmaf(fmaxf(__uint_as_float(r[j + 1]) + b4.y, ak.floor), a4.y, c4.y);
+      const float y2 = fmaf(fmaxf(__uint_as_float(r[j + 2]) + b4.z, ak.floor), a4.z, c4.z);
+      const float y3 = fmaf(fmaxf(__uint_as_float(r[j + 3]) + b4.w, ak.floor), a4.w, c4.w);
+      part = fmaf(w4.x, y0, part);
+      part = fmaf(w4.y, y1, part);
+      part = fmaf(w4.z, y2, part);
+      part = fmaf(w4.w, y3, part);
+      r[j] = __float_as_uint(y0); r[j + 1] = __float_as_uint(y1); r[j + 2] = __float_as_uint(y2); r[j + 3] = __float_as_uint(y3);
+    }
+  }
+  return part;
 }
 __device__ __forceinline__ uint16_t fuse_to16(float v, int dtype) {
   if (dtype == LAFF_BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
@@ -322,9 +370,13 @@ __global__ void __launch_bounds__(kNumThreads, 1)
       const float* bs = tl ? nullptr : p.bias[l];
       const float* sc = tl ? p.tiled_scale[l] : p.bn_scale[l];
       const float* sh = tl ? p.tiled_shift[l] : p.bn_shift[l];
-      v[0] = bs ? __ldg(bs + col) : 0.f;
-      v[1] = sc ? __ldg(sc + col) : 1.f;
-      v[2] = sh ? __ldg(sh + col) : 0.f;
+      const float b = bs ? __ldg(bs + col) : 0.f;
+      const float scale = sc ? __ldg(sc + col) : 1.f;
+      const float shift = sh ? __ldg(sh + col) : 0.f;
+      const ActCoef k = make_act(tl ? LAFF_ACT_NONE : p.act[l]);
+      v[0] = k.sigm ? k.neg_s * b : b;                    // sigm family: n * b, else the bias itself
+      v[1] = k.sigm ? k.a * scale : scale;                // A'
+      v[2] = k.sigm ? fmaf(k.c, scale, shift) : shift;    // C'
       v[3] = __ldg(p.att_w + col);
     };
     auto store_params = [&](int buf, const float (&v)[4]) {
@@ -352,7 +404,21 @@ __global__ void __launch_bounds__(kNumThreads, 1)
       float g[kEpiCols];
 #pragma unroll
       for (int j = 0; j < kEpiCols; ++j) g[j] = 0.f;
-      float m_run = -INFINITY;
+      float m_ref = -INFINITY;  // reference logit of the row: weights are exp(e - m_ref)
+      // Weight of a feature with logit e.  The reference moves (and g is rescaled) only when exp() could overflow --
+      // always on the first feature (m_ref = -inf), practically never afterwards -- so the common case costs one FMA
+      // per element in pass B.  All four owners of a row see the same e and share their warp's row set, so they take
+      // the same decision and the row keeps one common scale.
+      auto rebase = [&](float e) -> float {
+        if (__any_sync(0xffffffffu, e - m_ref > 60.0f)) {
+          const float nm = fmaxf(m_ref, e);
+          const float corr = __expf(m_ref - nm);
+          m_ref = nm;
+#pragma unroll
+          for (int j = 0; j < kEpiCols; ++j) g[j] *= corr;
+        }
+        return __expf(e - m_ref);
+      };
 
       const int n_feat = p.n_tiled + p.n_fc;
       for (int f = 0; f < n_feat; ++f) {
@@ -363,34 +429,48 @@ __global__ void __launch_bounds__(kNumThreads, 1)
         const bool has_next = (f + 1 < n_feat) || (u + num_clusters < p.total_units);
         if (f + 1 < n_feat) load_params(f + 1, head, nextp);
         else if (has_next) load_params(0, (u + num_clusters) % p.heads, nextp);
-        const float* pb = sp + mycol;
-        const float* psc = sp + kBlockN + mycol;
-        const float* psh = sp + 2 * kBlockN + mycol;
+        const float* p0 = sp + mycol;                  // see load_params for the meaning of the four rows
+        const float* p1 = sp + kBlockN + mycol;
+        const float* p2 = sp + 2 * kBlockN + mycol;
         const float* pw = sp + 3 * kBlockN + mycol;
-        const ActCoef ak = make_act(tiled ? LAFF_ACT_NONE : p.act[l]);
-        const float* xrow = nullptr;
-        int xoff = 0;
+        const int next_buf = stage_buf == kFuseParamBufs - 1 ? 0 : stage_buf + 1;
+
         if (tiled) {
-          xrow = p.tiled_x[l] + (row_ok ? row : 0) * p.tiled_ld[l];
-          xoff = (colbase + mycol) % p.tiled_in_dim[l];  // in_dim is a multiple of 128: 128 consecutive columns never wrap
-        }
-        uint32_t taddr = 0;
-        if (!tiled) {
-          ptx::mbar_wait(tfull_bar(acc), acc_phase, 15);
-          ptx::tcgen05_fence_after();
-          taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * kBlockN + mycol);
-        }
-        // ---- pass A: y = BN(act(acc + b)) (written back to TMEM in place), partial logit over my 128 columns ----
-        float part = 0.f;
-        if (tiled) {
+          const float* xrow = p.tiled_x[l] + (row_ok ? row : 0) * p.tiled_ld[l];
+          const int xoff = (colbase + mycol) % p.tiled_in_dim[l];  // in_dim is a multiple of 128: 128 consecutive columns never wrap
+          float part = 0.f;
+          if (f == 0) {
+            // First feature of the row: its weight is exp(0) = 1 whatever its logit turns out to be, so y goes
+            // straight into g and no second pass is needed.
+#pragma unroll
+            for (int cc = 0; cc < kEpiCols; cc += 4) {
+              const float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(xrow + xoff + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 sc4 = *reinterpret_cast<const float4*>(p1 + cc);
+              const float4 sh4 = *reinterpret_cast<const float4*>(p2 + cc);
+              const float4 w4 = *reinterpret_cast<const float4*>(pw + cc);
+              g[cc] = fmaf(v.x, sc4.x, sh4.x);
+              g[cc + 1] = fmaf(v.y, sc4.y, sh4.y);
+              g[cc + 2] = fmaf(v.z, sc4.z, sh4.z);
+              g[cc + 3] = fmaf(v.w, sc4.w, sh4.w);
+              part = fmaf(w4.x, g[cc], part);
+              part = fmaf(w4.y, g[cc + 1], part);
+              part = fmaf(w4.z, g[cc + 2], part);
+              part = fmaf(w4.w, g[cc + 3], part);
+            }
+            if (has_next) store_params(next_buf, nextp);
+            post(part);
+            m_ref = collect() + __ldg(p.att_b + head);
+            stage_buf = next_buf;
+            continue;
+          }
 #pragma unroll 1
           for (int c = 0; c < kEpiCols / 32; ++c) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const int cc = c * 32 + j;
               const float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(xrow + xoff + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float4 sc4 = *reinterpret_cast<const float4*>(psc + cc);
-              const float4 sh4 = *reinterpret_cast<const float4*>(psh + cc);
+              const float4 sc4 = *reinterpret_cast<const float4*>(p1 + cc);
+              const float4 sh4 = *reinterpret_cast<const float4*>(p2 + cc);
               const float4 w4 = *reinterpret_cast<const float4*>(pw + cc);
               part = fmaf(w4.x, fmaf(v.x, sc4.x, sh4.x), part);
               part = fmaf(w4.y, fmaf(v.y, sc4.y, sh4.y), part);
@@ -398,72 +478,78 @@ __global__ void __launch_bounds__(kNumThreads, 1)
               part = fmaf(w4.w, fmaf(v.w, sc4.w, sh4.w), part);
             }
           }
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < kEpiCols / 32; ++c) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), r);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int cc = c * 32 + j;
-              const float4 b4 = *reinterpret_cast<const float4*>(pb + cc);
-              const float4 sc4 = *reinterpret_cast<const float4*>(psc + cc);
-              const float4 sh4 = *reinterpret_cast<const float4*>(psh + cc);
-              const float4 w4 = *reinterpret_cast<const float4*>(pw + cc);
-              const float y0 = fmaf(apply_act(__uint_as_float(r[j]) + b4.x, ak), sc4.x, sh4.x);
-              const float y1 = fmaf(apply_act(__uint_as_float(r[j + 1]) + b4.y, ak), sc4.y, sh4.y);
-              const float y2 = fmaf(apply_act(__uint_as_float(r[j + 2]) + b4.z, ak), sc4.z, sh4.z);
-              const float y3 = fmaf(apply_act(__uint_as_float(r[j + 3]) + b4.w, ak), sc4.w, sh4.w);
-              part = fmaf(w4.x, y0, part);
-              part = fmaf(w4.y, y1, part);
-              part = fmaf(w4.z, y2, part);
-              part = fmaf(w4.w, y3, part);
-              r[j] = __float_as_uint(y0); r[j + 1] = __float_as_uint(y1); r[j + 2] = __float_as_uint(y2); r[j + 3] = __float_as_uint(y3);
-            }
-            ptx::tmem_st_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), r);  // pass B re-reads y, not the accumulator
-          }
-          ptx::tmem_st_wait();
-        }
-        if (has_next) store_params(stage_buf == kFuseParamBufs - 1 ? 0 : stage_buf + 1, nextp);
-        post(part);
-        const float e = collect() + __ldg(p.att_b + head);
-        // ---- pass B: online softmax-weighted accumulation (the denominator cancels under the final L2 norm) ----
-        const float m_new = fmaxf(m_run, e);
-        const float corr = __expf(m_run - m_new);  // 0 on the first feature
-        const float pe = __expf(e - m_new);
-        m_run = m_new;
-        if (tiled) {
+          if (has_next) store_params(next_buf, nextp);
+          post(part);
+          const float pe = rebase(collect() + __ldg(p.att_b + head));
 #pragma unroll
           for (int cc = 0; cc < kEpiCols; cc += 4) {
             const float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(xrow + xoff + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 sc4 = *reinterpret_cast<const float4*>(psc + cc);
-            const float4 sh4 = *reinterpret_cast<const float4*>(psh + cc);
-            g[cc] = fmaf(g[cc], corr, pe * fmaf(v.x, sc4.x, sh4.x));
-            g[cc + 1] = fmaf(g[cc + 1], corr, pe * fmaf(v.y, sc4.y, sh4.y));
-            g[cc + 2] = fmaf(g[cc + 2], corr, pe * fmaf(v.z, sc4.z, sh4.z));
-            g[cc + 3] = fmaf(g[cc + 3], corr, pe * fmaf(v.w, sc4.w, sh4.w));
+            const float4 sc4 = *reinterpret_cast<const float4*>(p1 + cc);
+            const float4 sh4 = *reinterpret_cast<const float4*>(p2 + cc);
+            g[cc] = fmaf(pe, fmaf(v.x, sc4.x, sh4.x), g[cc]);
+            g[cc + 1] = fmaf(pe, fmaf(v.y, sc4.y, sh4.y), g[cc + 1]);
+            g[cc + 2] = fmaf(pe, fmaf(v.z, sc4.z, sh4.z), g[cc + 2]);
+            g[cc + 3] = fmaf(pe, fmaf(v.w, sc4.w, sh4.w), g[cc + 3]);
           }
-        } else {
-#pragma unroll
-          for (int c = 0; c < kEpiCols / 32; ++c) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), r);
+          stage_buf = next_buf;
+          continue;
+        }
+
+        // ---------------- projected feature: the accumulator of its GEMM is in TMEM buffer `acc` ----------------
+        const ActCoef ak = make_act(p.act[l]);
+        ptx::mbar_wait(tfull_bar(acc), acc_phase, 15);
+        ptx::tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * kBlockN + mycol);
+        // ---- pass A: y = BN(act(acc + b)) written back to TMEM in place, partial logit over my 128 columns.  The
+        //      TMEM load of chunk c + 1 is in flight while chunk c is computed. ----
+        float part = 0.f;
+        constexpr int kChunks = kEpiCols / kFuseChunk;
+        {
+          uint32_t ra[kFuseChunk], rb[kFuseChunk];
+          ptx::tmem_ld_32x32b_x16(taddr, ra);
+#pragma unroll 1
+          for (int c = 0; c < kChunks; c += 2) {
+            const int o0 = c * kFuseChunk, o1 = o0 + kFuseChunk;
             ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(o1), rb);
+            part = pass_a_chunk(ra, p0 + o0, p1 + o0, p2 + o0, pw + o0, ak, part);
+            ptx::tmem_st_32x32b_x16(taddr + static_cast<uint32_t>(o0), ra);  // pass B re-reads y, not the accumulator
+            ptx::tmem_ld_wait();
+            // (tcgen05.st consumed ra when it issued: reloading ra needs no wait::st)
+            if (c + 2 < kChunks) ptx::tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(o1 + kFuseChunk), ra);
+            part = pass_a_chunk(rb, p0 + o1, p1 + o1, p2 + o1, pw + o1, ak, part);
+            ptx::tmem_st_32x32b_x16(taddr + static_cast<uint32_t>(o1), rb);
+          }
+          ptx::tmem_st_wait();
+        }
+        if (has_next) store_params(next_buf, nextp);
+        post(part);
+        // ---- pass B: g += exp(e - m_ref) * y (the softmax denominator cancels under the final L2 norm) ----
+        const float pe = rebase(collect() + __ldg(p.att_b + head));
+        {
+          uint32_t ra[kFuseChunk], rb[kFuseChunk];
+          ptx::tmem_ld_32x32b_x16(taddr, ra);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) g[c * 32 + j] = fmaf(g[c * 32 + j], corr, pe * __uint_as_float(r[j]));
+          for (int c = 0; c < kChunks; c += 2) {
+            const int o0 = c * kFuseChunk, o1 = o0 + kFuseChunk;
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(o1), rb);
+#pragma unroll
+            for (int j = 0; j < kFuseChunk; ++j) g[o0 + j] = fmaf(pe, __uint_as_float(ra[j]), g[o0 + j]);
+            ptx::tmem_ld_wait();
+            if (c + 2 < kChunks) ptx::tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(o1 + kFuseChunk), ra);
+#pragma unroll
+            for (int j = 0; j < kFuseChunk; ++j) g[o1 + j] = fmaf(pe, __uint_as_float(rb[j]), g[o1 + j]);
           }
         }
-        if (!tiled) {
-          ptx::tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
-            else ptx::mbar_arrive_remote(tempty_bar(acc), leader);
-          }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        ptx::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
+          else ptx::mbar_arrive_remote(tempty_bar(acc), leader);
         }
-        stage_buf = stage_buf == kFuseParamBufs - 1 ? 0 : stage_buf + 1;
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        stage_buf = next_buf;
       }
       // ---- L2 normalise over the whole head (4 partial sums of squares per row) and write ----
       float ss = 0.f;

@@ -577,6 +577,12 @@ class W2VVPP(nn.Module):
         """Dense score matrix for small galleries; same return contract as the reference:
         (scores ndarray [Q, V] float32, txt_ids, vis_ids).  Video embeddings stay on the device (the reference parks
         them on the host and re-uploads them per text batch, model/model.py:1047, :1066)."""
+        scores, txt_ids, vis_ids = self.predict_device(txt_loader, vis_loader, measure, record_emb)
+        return scores.cpu().numpy(), txt_ids, vis_ids
+
+    def predict_device(self, txt_loader, vis_loader, measure, record_emb=False):
+        """predict() with the score matrix left on the device (CUDA fp32 [Q, V]) for laff_b200.predictor, which ranks,
+        evaluates and extracts the written lists there instead of argsorting on the host."""
         self.eval()
         if measure != "cosine":
             self.compute_sim(None, None, measure)
@@ -603,7 +609,7 @@ class W2VVPP(nn.Module):
                 rows.append(ops.sim_dense(q16, g16, 1.0 / H))
                 txt_ids.extend(batch_txt_ids)
             scores = torch.cat(rows, 0)
-        return scores.cpu().numpy(), txt_ids, self.vis_ids
+        return scores, txt_ids, self.vis_ids
 
 
 class W2VVPP_MultiHeadAttention(W2VVPP):

@@ -11,7 +11,8 @@ from typing import Optional, Sequence
 import torch
 
 from . import _capi
-from ._capi import BF16, F16, F32, FUSE_MAX_FC, FUSE_MAX_TILED, MAX_TOPK, FuseDesc, LaffError, PoolDesc
+from ._capi import (BF16, F16, F32, FUSE_MAX_FC, FUSE_MAX_TILED, MAX_TOPK, MAX_TOPK_DENSE, FuseDesc, LaffError,
+                    PoolDesc)
 
 _DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 _TORCH_DT = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32, "fp16": torch.float16,
@@ -208,6 +209,57 @@ def rank_from_scores(scores: torch.Tensor, gt: Optional[torch.Tensor], k: int = 
     _capi.call("laff_rank_from_scores", _ptr(scores), Q, V, scores.stride(0), _ptr(gt), int(k), _ptr(rank0), _ptr(tv),
                _ptr(ti), _stream(scores))
     return rank0, tv, ti
+
+
+def topk_dense(scores: torch.Tensor, k: int, idx_in: Optional[torch.Tensor] = None, scale: float = 1.0):
+    """Ranked list of every row of a dense fp32 matrix: (values [R, k], indices int32 [R, k]) ordered by the tie rule
+    (score desc, index desc), 1 <= k <= 2048 (laff_topk_dense).  idx_in: int32 [R, C] indices carried by the candidates
+    (-1 = empty), C <= 16384 -- merges per-shard lists.  Slots past the number of candidates hold -inf / -1."""
+    _need_cuda(scores, idx_in)
+    if not 1 <= k <= MAX_TOPK_DENSE:
+        raise LaffError("topk_dense: k must be in [1, %d] (got %d)" % (MAX_TOPK_DENSE, k))
+    scores = _rowmajor(scores.float() if scores.dtype != torch.float32 else scores)
+    R, Cn = scores.shape
+    ld_idx = 0
+    if idx_in is not None:
+        idx_in = _rowmajor(idx_in.to(torch.int32))
+        if tuple(idx_in.shape) != (R, Cn):
+            raise LaffError("topk_dense: idx_in must have the shape of scores")
+        ld_idx = idx_in.stride(0)
+    tv = torch.empty((R, k), dtype=torch.float32, device=scores.device)
+    ti = torch.empty((R, k), dtype=torch.int32, device=scores.device)
+    _capi.call("laff_topk_dense", _ptr(scores), scores.stride(0), _ptr(idx_in), ld_idx, R, Cn, int(k), float(scale), _ptr(tv),
+               _ptr(ti), _stream(scores))
+    return tv, ti
+
+
+def rank_multi_gt(scores: torch.Tensor, gt_offsets: torch.Tensor, gt_cols: torch.Tensor) -> torch.Tensor:
+    """0-based tie-rule rank of every ground-truth column of every row; CSR lists gt_cols[gt_offsets[i]:gt_offsets[i+1]]
+    (laff_rank_multi_gt, the video -> text direction of predictor.py:262-270)."""
+    _need_cuda(scores, gt_offsets, gt_cols)
+    scores = _rowmajor(scores.float() if scores.dtype != torch.float32 else scores)
+    R, Cn = scores.shape
+    gt_offsets = gt_offsets.to(torch.int64).contiguous()
+    gt_cols = gt_cols.to(torch.int32).contiguous()
+    if gt_offsets.numel() != R + 1:
+        raise LaffError("rank_multi_gt: gt_offsets must have rows + 1 entries")
+    rank0 = torch.empty(gt_cols.numel(), dtype=torch.int32, device=scores.device)
+    _capi.call("laff_rank_multi_gt", _ptr(scores), scores.stride(0), R, Cn, _ptr(gt_offsets), _ptr(gt_cols), _ptr(rank0),
+               _stream(scores))
+    return rank0
+
+
+def multi_gt_metrics(rank0: torch.Tensor, gt_offsets: torch.Tensor):
+    """evaluation.eval from multi-ground-truth ranks: (metrics double[8], first int32 [R], ap double [R])."""
+    _need_cuda(rank0, gt_offsets)
+    rank0 = rank0.to(torch.int32).contiguous()
+    gt_offsets = gt_offsets.to(torch.int64).contiguous()
+    R = gt_offsets.numel() - 1
+    first = torch.empty(R, dtype=torch.int32, device=rank0.device)
+    ap = torch.empty(R, dtype=torch.float64, device=rank0.device)
+    out = torch.empty(8, dtype=torch.float64, device=rank0.device)
+    _capi.call("laff_multi_gt_metrics", _ptr(rank0), _ptr(gt_offsets), R, _ptr(first), _ptr(ap), _ptr(out), _stream(rank0))
+    return out, first, ap
 
 
 def rank_metrics(rank0: torch.Tensor) -> torch.Tensor:

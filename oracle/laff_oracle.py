@@ -287,6 +287,67 @@ def eval_label_matrix(label_matrix: np.ndarray):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# predictor / validate: id-based ground truth, both directions, result writers  
+# ----------------------------------------------------------------------------------------------------------------
+def sorted_desc(scores: np.ndarray) -> np.ndarray:
+    """`inds[index][::-1]` of predictor.py:232-239 under the documented tie rule (stable argsort, reversed)."""
+    return np.argsort(scores, axis=1, kind="stable")[:, ::-1]
+
+
+def predictor_t2v_eval(t2i: np.ndarray, txt_ids: Sequence[str], vis_ids: Sequence[str]):
+    """predictor.py:236-246 / trainer.py:582-599 — label_matrix[i, p] = 1 where the p-th ranked video id equals
+    txt_id.split('#')[0]; metrics = evaluation.eval(label_matrix).  Returns (metrics7, label_matrix)."""
+    order = sorted_desc(t2i)
+    vis = np.array(vis_ids)
+    label = np.zeros(order.shape)
+    for i in range(order.shape[0]):
+        label[i][np.where(vis[order[i]] == txt_ids[i].split("#")[0])[0]] = 1
+    return eval_label_matrix(label), label
+
+
+def predictor_v2t_eval(t2i: np.ndarray, txt_ids: Sequence[str], vis_ids: Sequence[str]):
+    """predictor.py:262-270 — rows = videos of t2i.T, ground truths = every caption whose id prefix is the video id."""
+    i2t = t2i.T
+    order = sorted_desc(i2t)
+    cap_vid = np.array([t.split("#")[0] for t in txt_ids])
+    label = np.zeros(order.shape)
+    for v in range(order.shape[0]):
+        label[v][np.where(cap_vid[order[v]] == vis_ids[v])[0]] = 1
+    return eval_label_matrix(label), label
+
+
+def writer_topk(n_vis: int, threshold: int) -> int:
+    """predictor.py:55-58, :64 — `ind = inds[index][::-1][0:TopK]` with TopK = Threshold if len(vis_ids) >= Threshold
+    else -1: below the threshold the slice 0:-1 drops the last (lowest-ranked) video."""
+    return threshold if n_vis >= threshold else max(n_vis - 1, 0)
+
+
+def txt2video_lines(t2i: np.ndarray, txt_ids: Sequence[str], vis_ids: Sequence[str], threshold: int = 2000):
+    """The lines txt2video_write_to_file writes (predictor.py:62-67): '<txt_id> <vis_id> <score> <vis_id> <score> ...'
+    with scores printed by '%s' of the float32 matrix entry."""
+    order = sorted_desc(t2i)
+    k = writer_topk(len(vis_ids), threshold)
+    lines = []
+    for i in range(order.shape[0]):
+        ind = order[i][:k]
+        lines.append(txt_ids[i] + " " + " ".join([vis_ids[j] + " %s" % t2i[i][j] for j in ind]))
+    return lines
+
+
+def t2v_shot_dict(t2i: np.ndarray, txt_ids: Sequence[str], vis_ids: Sequence[str], captions: Mapping[str, str],
+                  threshold: int = 500):
+    """The dict pickled to t2v.pkl (predictor.py:68-86)."""
+    order = sorted_desc(t2i)
+    k = writer_topk(len(vis_ids), threshold)
+    out = {}
+    for i in range(order.shape[0]):
+        ind = order[i][:k]
+        out[txt_ids[i]] = {"query": captions[txt_ids[i]], "rank_list": [vis_ids[j] for j in ind],
+                           "sim_value": [t2i[i][j] for j in ind]}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # loss
 # ----------------------------------------------------------------------------------------------------------------
 def _hinge(scores: np.ndarray, margin, max_violation: bool, cost_style: str, direction: str, want_grad: bool):

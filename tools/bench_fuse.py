@@ -39,6 +39,7 @@ def timeit(fn, iters=7, warmup=2):
 
 def main():
     rows = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
+    quick = "--quick" in sys.argv  # one warm-up + one timed launch per variant: for runs under ncu (cycle counts)
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(0)
     out_path = os.path.join("gpurun_out", "fuse_bench.jsonl")
@@ -62,7 +63,7 @@ def main():
         for variant in (1, 2):
             ops.set_fuse_variant(variant)
             run = lambda: ops.fuse_forward(fc, tiled, aw, ab, 8, 512, want_f32=False, out16_dtype=torch.bfloat16)
-            ms = timeit(run)
+            ms = timeit(run, iters=1, warmup=1) if quick else timeit(run)
             outs[variant] = run()[1].float()
             rec = {"kernel": "laff_fuse_forward cta_group::%d, %s, rows=%d" % (variant, name, rows), "ms": ms,
                    "achieved": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s"}
