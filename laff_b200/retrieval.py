@@ -48,6 +48,16 @@ class CudaBackend:
     def metrics(self, rank0):
         return ops.rank_metrics(rank0)
 
+    def dense_topk(self, q16, g16, k, scale, col_offset):
+        """Ranked list of the k best local videos per query: dense scores of the chunk, then laff_topk_dense."""
+        s = ops.sim_dense(q16, g16, scale)
+        tv, ti = ops.topk_dense(s, k)
+        return tv, torch.where(ti >= 0, ti + col_offset, ti)
+
+    def merge_lists(self, vals, idx, k):
+        """vals/idx [Q, n] candidates carrying global indices (-1 = empty) -> the k best by the tie rule."""
+        return ops.topk_dense(vals, k, idx_in=idx)
+
 
 @dataclass
 class SearchResult:
@@ -131,6 +141,37 @@ class GalleryIndex:
             tv, ti = be.merge(torch.stack(vals, 0), torch.stack(idxs, 0), k)
         return SearchResult(count, tv, ti, be.metrics(count))
 
+    def ranked_lists(self, q16: torch.Tensor, k: int, query_chunk: int = 256):
+        """The k best videos of every query over the whole (sharded) gallery, k up to 2048: the lists the reference
+        writes to id.sent.score.txt (top 2000) and t2v.pkl (top 500), predictor.py:53-88.  Queries are processed
+        `query_chunk` at a time so the dense chunk of scores stays bounded (256 x 1 M fp32 = 1 GB); with W > 1 shards
+        every rank extracts its local lists and one all_gather + merge per chunk yields the global ones.
+        Returns (values fp32 [Q, k], global indices int32 [Q, k]) on the device, -inf / -1 beyond the gallery size."""
+        be = self.backend
+        scale = 1.0 / self.heads
+        Q = q16.shape[0]
+        n_local = self.hi - self.lo
+        out_v, out_i = [], []
+        for lo in range(0, Q, query_chunk):
+            qc = q16[lo:lo + query_chunk]
+            if n_local > 0:
+                tv, ti = be.dense_topk(qc, self.g16, k, scale, self.lo)
+            else:
+                tv = torch.full((qc.shape[0], k), float("-inf"), dtype=torch.float32, device=q16.device)
+                ti = torch.full((qc.shape[0], k), -1, dtype=torch.int32, device=q16.device)
+            if self.world_size > 1:
+                vals = [torch.empty_like(tv) for _ in range(self.world_size)]
+                idxs = [torch.empty_like(ti) for _ in range(self.world_size)]
+                dist.all_gather(vals, tv.contiguous(), group=self.group)
+                dist.all_gather(idxs, ti.contiguous(), group=self.group)
+                tv, ti = be.merge_lists(torch.cat(vals, 1), torch.cat(idxs, 1), k)
+            out_v.append(tv)
+            out_i.append(ti)
+        if not out_v:
+            return (torch.empty((0, k), dtype=torch.float32, device=q16.device),
+                    torch.empty((0, k), dtype=torch.int32, device=q16.device))
+        return torch.cat(out_v), torch.cat(out_i)
+
 
 class Retriever:
     """The whole query path behind one call: fuse the text features of a batch of queries (txt_net, F1-F6), then rank
@@ -163,6 +204,11 @@ class Retriever:
         out = torch.empty((W * per, D), dtype=q16.dtype, device=q16.device)
         dist.all_gather_into_tensor(out, buf, group=idx.group)
         return out[:Q]
+
+    @torch.no_grad()
+    def ranked_lists(self, caption_feat_dict, k: int, query_chunk: int = 256):
+        """Fuse the queries, then GalleryIndex.ranked_lists (the writer lists of predictor.py:53-88 at gallery scale)."""
+        return self.index.ranked_lists(self.encode_queries(caption_feat_dict), k, query_chunk)
 
     @torch.no_grad()
     def rank(self, caption_feat_dict, gt_global, k: int = 10, chunks: int = 1) -> SearchResult:

@@ -206,6 +206,24 @@ def test_gallery_sharding_is_exact_on_one_gpu():
     np.testing.assert_array_equal(m[:4], O.metrics_from_rank0(single.rank0.cpu().numpy())[:4])
 
 
+def test_ranked_lists_at_gallery_scale_match_stable_argsort():
+    """GalleryIndex.ranked_lists (dense chunk -> radix-select top-k, writer lists of predictor.py:53-88): indices equal
+    the stable-argsort order of the device's own dense scores, and agree with the fused sweep's top-16."""
+    from laff_b200.retrieval import GalleryIndex
+    Q, V, H, dh, k = 70, 40009, 8, 32, 777
+    q, g, gt = synth.retrieval_embeddings(91, Q, V, H, dh, sigma=1.0)
+    g[V - 1] = g[gt[0]]
+    g[5] = g[gt[1]]
+    q16, g16 = torch.from_numpy(synth.bf16_round(q)).cuda().to(torch.bfloat16), torch.from_numpy(synth.bf16_round(g)).cuda().to(torch.bfloat16)
+    idx = GalleryIndex(g16, V, H)
+    lv, li = idx.ranked_lists(q16, k, query_chunk=32)
+    s = ops.sim_dense(q16, g16, 1.0 / H).cpu().numpy()
+    rv, ri = O.tie_rule_topk(s, k)
+    assert np.array_equal(li.cpu().numpy().astype(np.int64), ri) and np.array_equal(lv.cpu().numpy(), rv)
+    res = idx.search(q16, torch.from_numpy(gt).cuda().to(torch.int32), 16)
+    assert torch.equal(res.topk_idx, li[:, :16])
+
+
 @pytest.mark.parametrize("V", [1000000])
 def test_full_size_properties(V):
     """BASELINE config C5 (10 000 queries x 1 000 000 videos): properties that do not need the 40 GB score matrix."""

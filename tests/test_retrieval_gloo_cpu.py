@@ -44,6 +44,19 @@ class NumpyBackend:
         order = np.lexsort((-i, -v), axis=1)[:, :k]
         return torch.from_numpy(np.take_along_axis(v, order, 1)), torch.from_numpy(np.take_along_axis(i, order, 1))
 
+    def dense_topk(self, q16, g16, k, scale, col_offset):
+        s = (q16.float().numpy().astype(np.float64) @ g16.float().numpy().astype(np.float64).T).astype(np.float32) * np.float32(scale)
+        v, i = O.tie_rule_topk(s, k)
+        pad = k - v.shape[1]
+        v = np.pad(v, ((0, 0), (0, pad)), constant_values=-np.inf)
+        i = np.pad(i + col_offset, ((0, 0), (0, pad)), constant_values=-1)
+        return torch.from_numpy(v.astype(np.float32)), torch.from_numpy(i.astype(np.int32))
+
+    def merge_lists(self, vals, idx, k):
+        v, i = vals.numpy(), idx.numpy().astype(np.int64)
+        order = np.lexsort((-i, -v), axis=1)[:, :k]  # empty slots (-inf, -1) sort last
+        return torch.from_numpy(np.take_along_axis(v, order, 1)), torch.from_numpy(np.take_along_axis(i, order, 1).astype(np.int32))
+
     def metrics(self, rank0):
         m = O.metrics_from_rank0(rank0.numpy())
         return torch.tensor(list(m) + [m[5], float(len(rank0))], dtype=torch.float64)
@@ -70,8 +83,9 @@ def _worker(rank, world, port, out):
         lo, hi = shard_bounds(g.shape[0], world, rank)
         idx = GalleryIndex(torch.from_numpy(g[lo:hi]).to(torch.bfloat16), g.shape[0], H, rank, world, backend=NumpyBackend())
         res = idx.search(torch.from_numpy(q).to(torch.bfloat16), torch.from_numpy(gt), k=7)
+        lv, li = idx.ranked_lists(torch.from_numpy(q).to(torch.bfloat16), k=150, query_chunk=20)
         if rank == 0:
-            torch.save({"rank0": res.rank0, "tv": res.topk_val, "ti": res.topk_idx, "m": res.metrics}, out)
+            torch.save({"rank0": res.rank0, "tv": res.topk_val, "ti": res.topk_idx, "m": res.metrics, "lv": lv, "li": li}, out)
     finally:
         dist.destroy_process_group()
 
@@ -88,6 +102,10 @@ def test_sharded_search_equals_single_shard(world, tmp_path):
     assert torch.equal(got["ti"], ref.topk_idx)
     assert torch.allclose(got["tv"], ref.topk_val, atol=0, rtol=0)
     assert torch.equal(got["m"], ref.metrics)
+    # writer lists (top-150 of a 301-video gallery, shards of 101..151 videos): sharded == single shard == oracle
+    sv, si = single.ranked_lists(torch.from_numpy(q).to(torch.bfloat16), k=150, query_chunk=48)
+    assert torch.equal(got["li"], si) and torch.equal(got["lv"], sv)
+    np.testing.assert_array_equal(si.numpy(), O.tie_rule_topk((O.mm_mean_heads(q, g, H)).astype(np.float32), 150)[1])
     # and the single-shard answer is the oracle's tie-rule answer on the same operands
     s = (O.mm_mean_heads(q, g, H)).astype(np.float32)
     np.testing.assert_array_equal(ref.rank0.numpy(), O.tie_rule_rank(s, gt))

@@ -36,12 +36,16 @@ def main():
     g16[7] = g16[gt[9]]
     lo, hi = shard_bounds(V, world, rank)
     res = GalleryIndex(g16[lo:hi].contiguous(), V, H, rank, world).search(q16, gt.to(torch.int32), k)
+    lv, li = GalleryIndex(g16[lo:hi].contiguous(), V, H, rank, world).ranked_lists(q16[:300], 500, query_chunk=128)
     torch.cuda.synchronize()
     ok = True
     if rank == 0:
-        ref = GalleryIndex(g16, V, H).search(q16, gt.to(torch.int32), k)
+        single = GalleryIndex(g16, V, H)
+        ref = single.search(q16, gt.to(torch.int32), k)
+        rv, ri = single.ranked_lists(q16[:300], 500, query_chunk=128)
         ok = (torch.equal(res.rank0, ref.rank0) and torch.equal(res.topk_idx, ref.topk_idx)
-              and torch.equal(res.topk_val, ref.topk_val) and torch.equal(res.metrics, ref.metrics))
+              and torch.equal(res.topk_val, ref.topk_val) and torch.equal(res.metrics, ref.metrics)
+              and torch.equal(li, ri) and torch.equal(lv, rv) and torch.equal(ri[:, :k], ref.topk_idx[:300]))
         print("multi-GPU parity world=%d: %s  R@1=%.2f R@10=%.2f MedR=%.0f" % (
             world, "OK" if ok else "MISMATCH", ref.metrics[0].item(), ref.metrics[2].item(), ref.metrics[3].item()), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
