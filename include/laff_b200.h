@@ -174,6 +174,28 @@ int laff_label_metrics(const uint8_t* label, int Q, int V, long long ld, int32_t
                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * N2  Text front-end after tokenisation (model/model.py:322-434, txt2vec.py:49-109).  Token lists are CSR:
+ *     ids[offsets[i] .. offsets[i+1]) belong to caption i; ids outside the table are skipped.
+ *   laff_bow_counts   BowVec._encoding: out[i, id] += 1 (rows are zeroed first).  out fp32 [rows, ndims].
+ *   laff_gather_mean  W2Vec._encoding: mean of table rows, summed in float64 in list order, rounded to fp32 once
+ *                     (numpy's np.array(vectors).mean(axis=0) on float64); no valid id -> zeros.  The caller passes the
+ *                     ids de-duplicated and sorted, as BigFile.read returns them (bigfile.py:204-211).
+ *   laff_gather_rows  nn.Embedding lookup: out[i] = table[ids[i]] (zeros for an id outside the table).
+ *   laff_gru_cell     one nn.GRU step for packed sequences: gi [B, 3H] = W_ih x_t + b_ih, gh [B, 3H] = W_hh h + b_hh
+ *                     (gate order r, z, n); sequences with lengths[b] <= t keep h.  sum += h_t (for 'mean' pooling) and
+ *                     last = h at t == len - 1 are optional outputs (model/model.py:361-383).
+ *   laff_mean_over_length  x[b, :] /= lengths[b]. */
+int laff_bow_counts(const long long* tok_offsets, const int32_t* tok_ids, int rows, int ndims, float* out, long long ld,
+                    void* stream);
+int laff_gather_mean(const float* table, long long ld_table, long long n_table, const long long* offsets,
+                     const int32_t* ids, int rows, int dim, float* out, long long ld, void* stream);
+int laff_gather_rows(const float* table, long long ld_table, long long n_table, const int32_t* ids, long long n, int dim,
+                     float* out, long long ld, void* stream);
+int laff_gru_cell(const float* gi, long long ld_gi, const float* gh, long long ld_gh, const float* h_prev,
+                  const int32_t* lengths, int t, int B, int H, float* h_out, float* sum, float* last, void* stream);
+int laff_mean_over_length(float* x, const int32_t* lengths, int B, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * F1  TransformNet.forward (model/model.py:257-276): y = BN(act(x W^T + b)), eval mode (dropout = identity,
  *     BatchNorm1d running stats, eps bn_eps).  x16 [rows, K] ldx, w16 [D, K] ldw (16-bit, K-major, pitches % 8 == 0).
  *     Eval-mode BatchNorm is the per-column affine map y*bn_scale + bn_shift produced by laff_bn_fold.

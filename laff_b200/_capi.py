@@ -93,6 +93,11 @@ SIGNATURES = {
     "laff_rank_multi_gt": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _vp, _vp]),
     "laff_multi_gt_metrics": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "laff_rank_metrics": (_i, [_vp, _i, _vp, _vp]),
+    "laff_bow_counts": (_i, [_vp, _vp, _i, _i, _vp, _ll, _vp]),
+    "laff_gather_mean": (_i, [_vp, _ll, _ll, _vp, _vp, _i, _i, _vp, _ll, _vp]),
+    "laff_gather_rows": (_i, [_vp, _ll, _ll, _vp, _ll, _i, _vp, _ll, _vp]),
+    "laff_gru_cell": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "laff_mean_over_length": (_i, [_vp, _vp, _i, _i, _vp]),
     "laff_label_metrics": (_i, [_vp, _i, _i, _ll, _vp, _vp, _vp, _vp]),
     "laff_project": (_i, [_vp, _vp, _ll, _i, _i, _ll, _ll, _i, _vp, _i, _vp, _vp, _vp, _ll, _vp]),
     "laff_bn_fold": (_i, [_vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _vp]),

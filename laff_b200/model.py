@@ -389,6 +389,89 @@ class VisMutiTransformNetAddAttnetion(nn.Module):
         return self.attention_layer.get_attention_weight()
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# text encoders: strings -> per-encoder features on the device
+# ----------------------------------------------------------------------------------------------------------------
+class TxtEncoder(nn.Module):
+    """model/model.py:311-320."""
+
+    def __init__(self, opt):
+        super().__init__()
+
+    def forward(self, caption_feat_dict, task3=False):
+        return {"text_features": caption_feat_dict["caption"]}
+
+
+class GruTxtEncoder(TxtEncoder):
+    """model/model.py:322-387: IndexVec token ids -> nn.Embedding -> 1-layer GRU -> mean / last / mean_last pooling.
+    Parameters live in `we` (nn.Embedding) and `rnn` (nn.GRU) so reference checkpoints load by name; the arithmetic is
+    laff_b200.text.gru_encode (device kernels), not torch's GRU."""
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.bigru = False
+        if int(opt.rnn_layer) != 1:
+            raise NotImplementedError("rnn_layer = %s: the shipped configs use one GRU layer (base_config.py:39)" % opt.rnn_layer)
+        self.pooling = opt.pooling
+        self.rnn_size = int(opt.rnn_size)
+        self.t2v_idx = opt.t2v_idx
+        self.we = nn.Embedding(len(self.t2v_idx.vocab), int(opt.we_dim))
+        if int(opt.we_dim) == 500 and getattr(opt, "we", None) is not None:
+            self.we.weight = nn.Parameter(torch.as_tensor(opt.we, dtype=torch.float32))  # pre-trained 500-d w2v
+        self.rnn = nn.GRU(int(opt.we_dim), self.rnn_size, 1, batch_first=True, bidirectional=False)
+        self._prepared: Dict[str, torch.Tensor] = {}
+
+    def train(self, mode: bool = True):
+        self._prepared = {}
+        return super().train(mode)
+
+    def load_state_dict(self, *a, **k):
+        self._prepared = {}
+        return super().load_state_dict(*a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._prepared = {}
+        return super()._load_from_state_dict(*a, **k)
+
+    def forward(self, caption_feat_dict, task3=False):
+        from . import text as _text
+        if self.training:
+            raise NotImplementedError("train-mode GRU (backward through time) is SURVEY §8f N4; call .eval()")
+        txt_input = caption_feat_dict["caption"]
+        idx_vecs = [self.t2v_idx.encoding(c) for c in txt_input]
+        lengths = [len(v) for v in idx_vecs]
+        ids = np.zeros((len(txt_input), max(lengths)), dtype=np.int32)
+        for i, v in enumerate(idx_vecs):
+            ids[i, : lengths[i]] = v
+        dev = _cuda_device(self.we.weight.device)
+        out = _text.gru_encode(self.we.weight, self.rnn.weight_ih_l0, self.rnn.weight_hh_l0, self.rnn.bias_ih_l0,
+                               self.rnn.bias_hh_l0, torch.from_numpy(ids).to(dev), torch.tensor(lengths, dtype=torch.int32, device=dev),
+                               self.pooling, self._prepared)
+        return {"text_features": out}
+
+
+class BoWTxtEncoder(TxtEncoder):
+    """model/model.py:399-416."""
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.t2v_bow = opt.t2v_bow
+
+    def forward(self, caption_feat_dict, task3=False):
+        return {"text_features": self.t2v_bow.encode_batch(caption_feat_dict["caption"])}
+
+
+class W2VTxtEncoder(TxtEncoder):
+    """model/model.py:419-434."""
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.t2v_w2v = opt.t2v_w2v
+
+    def forward(self, caption_feat_dict, task3=False):
+        return {"text_features": self.t2v_w2v.encode_batch(caption_feat_dict["caption"])}
+
+
 # reference encoder name -> (feature key accepted in caption_feat_dict, alternatives)
 _TXT_ENCODERS = (("rnn_encoder", ("gru", "rnn_encoder")), ("bow_encoder", ("bow", "bow_encoder")),
                  ("w2v_encoder", ("w2v", "w2v_encoder")), ("CLIP_encoder", ("clip", "CLIP_encoding", "CLIP_encoder")))
@@ -423,6 +506,18 @@ class MultiScaleTxtEncoderAttention(nn.Module):
             self.space_dict["CLIP_encoder"] = opt.clip_opt["size"]
         self.encoder_name_list = [n for n, _ in _TXT_ENCODERS if n in self.space_dict]
         self.txt_encoder_num = len(self.encoder_name_list)
+        # String front-end (init_txt_encoder, model/model.py:558-613): built when the config carries the vocabulary
+        # objects; otherwise the per-encoder features must arrive precomputed in caption_feat_dict.
+        self.encoder = nn.Module()
+        if "rnn_encoder" in self.space_dict and hasattr(getattr(opt, "t2v_idx", None), "vocab"):
+            if te["rnn_encoding"]["name"].split("_", 1)[0] != "gru":
+                raise NotImplementedError("bigru text encoder: the shipped LAFF configs use gru_mean (base_config.py:21)")
+            opt.pooling = te["rnn_encoding"]["name"].split("_", 1)[1]
+            self.encoder.add_module("rnn_encoder", GruTxtEncoder(opt))
+        if "bow_encoder" in self.space_dict and hasattr(opt.t2v_bow, "encode_batch"):
+            self.encoder.add_module("bow_encoder", BoWTxtEncoder(opt))
+        if "w2v_encoder" in self.space_dict and hasattr(opt.t2v_w2v, "encode_batch"):
+            self.encoder.add_module("w2v_encoder", W2VTxtEncoder(opt))
         self.transform_layer = nn.Module()
         # registration order follows init_transform (rnn, w2v, bow, CLIP) so that state_dict() order matches
         for name in ("rnn_encoder", "w2v_encoder", "bow_encoder", "CLIP_encoder"):
@@ -444,6 +539,9 @@ class MultiScaleTxtEncoderAttention(nn.Module):
         for key in dict(_TXT_ENCODERS)[enc]:
             if key in caption_feat_dict:
                 return caption_feat_dict[key]
+        front = dict(self.encoder.named_children()).get(enc)
+        if front is not None and "caption" in caption_feat_dict:
+            return front(caption_feat_dict)["text_features"]
         raise KeyError("caption_feat_dict has no feature for %s (expected one of %s)" % (enc, dict(_TXT_ENCODERS)[enc]))
 
     def encode(self, caption_feat_dict, out16_dtype=None, precision=None, want_att=False):

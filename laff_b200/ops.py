@@ -445,6 +445,65 @@ def frame_pool(frames: torch.Tensor, att_weight: torch.Tensor, att_bias: float, 
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# text front-end (after tokenisation)
+# ----------------------------------------------------------------------------------------------------------------
+def _csr(offsets: torch.Tensor, ids: torch.Tensor):
+    _need_cuda(offsets, ids)
+    return offsets.to(torch.int64).contiguous(), ids.to(torch.int32).contiguous()
+
+
+def bow_counts(offsets: torch.Tensor, ids: torch.Tensor, ndims: int) -> torch.Tensor:
+    """BowVec._encoding for a batch: CSR token ids -> fp32 [rows, ndims] count vectors (laff_bow_counts)."""
+    offsets, ids = _csr(offsets, ids)
+    rows = offsets.numel() - 1
+    out = torch.empty((rows, ndims), dtype=torch.float32, device=offsets.device)
+    _capi.call("laff_bow_counts", _ptr(offsets), _ptr(ids), rows, int(ndims), _ptr(out), out.stride(0), _stream(offsets))
+    return out
+
+
+def gather_mean(table: torch.Tensor, offsets: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """W2Vec._encoding for a batch: mean (fp64 accumulation, list order) of table rows per caption (laff_gather_mean)."""
+    _need_cuda(table)
+    table = _rowmajor(table.float() if table.dtype != torch.float32 else table)
+    offsets, ids = _csr(offsets, ids)
+    rows = offsets.numel() - 1
+    out = torch.empty((rows, table.shape[1]), dtype=torch.float32, device=table.device)
+    _capi.call("laff_gather_mean", _ptr(table), table.stride(0), table.shape[0], _ptr(offsets), _ptr(ids), rows, table.shape[1],
+               _ptr(out), out.stride(0), _stream(table))
+    return out
+
+
+def gather_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """nn.Embedding lookup: fp32 [n, dim] = table[ids] (laff_gather_rows)."""
+    _need_cuda(table, ids)
+    table = _rowmajor(table.float() if table.dtype != torch.float32 else table)
+    ids = ids.to(torch.int32).contiguous().view(-1)
+    out = torch.empty((ids.numel(), table.shape[1]), dtype=torch.float32, device=table.device)
+    _capi.call("laff_gather_rows", _ptr(table), table.stride(0), table.shape[0], _ptr(ids), ids.numel(), table.shape[1],
+               _ptr(out), out.stride(0), _stream(table))
+    return out
+
+
+def gru_cell(gi: torch.Tensor, gh: torch.Tensor, h_prev: torch.Tensor, lengths: torch.Tensor, t: int, h_out: torch.Tensor,
+             sum_out: Optional[torch.Tensor] = None, last_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One nn.GRU step over a batch of packed sequences (laff_gru_cell).  gi: fp32 [B, 3H] view (row pitch free) of the
+    input-side pre-activations of step t; gh: fp32 [B, 3H] hidden-side pre-activations."""
+    _need_cuda(gi, gh, h_prev, lengths, h_out, sum_out, last_out)
+    B, H = h_prev.shape
+    if gi.shape != (B, 3 * H) or gh.shape != (B, 3 * H) or gi.stride(1) != 1 or gh.stride(1) != 1:
+        raise LaffError("gru_cell: gi / gh must be [B, 3H] with contiguous rows")
+    _capi.call("laff_gru_cell", _ptr(gi), gi.stride(0), _ptr(gh), gh.stride(0), _ptr(h_prev), _ptr(lengths), int(t), B, H,
+               _ptr(h_out), _ptr(sum_out), _ptr(last_out), _stream(h_prev))
+    return h_out
+
+
+def mean_over_length(x: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x, lengths)
+    _capi.call("laff_mean_over_length", _ptr(x), _ptr(lengths), x.shape[0], x.shape[1], _stream(x))
+    return x
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # loss
 # ----------------------------------------------------------------------------------------------------------------
 def mrl_forward_backward(txt: torch.Tensor, vis: torch.Tensor, margin: float, max_violation: bool, direction: str,

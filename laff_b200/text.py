@@ -1,0 +1,278 @@
+"""Text front-end of the reference: tokeniser, vocabularies and the bag-of-words / word2vec / GRU
+sentence encoders (textlib.py:27-112, txt2vec.py:12-166, model/model.py:322-434).
+
+Strings are tokenised on the host (a regex and two dictionary lookups per word); everything numeric — the count
+vectors, the word-vector means, the embedding lookup and the GRU recurrence — runs on the device through the C ABI
+(`csrc/text.cu`, and the tcgen05 GEMM engine for the GRU's two matrix products).  There is no CPU arithmetic path:
+`encoding()` of a single query runs the same device kernels with a batch of one.
+
+The reference's stop-word list (`stopwords_en.txt`) is data of the reference tree and is not shipped here: point
+`TextTool.set_stopwords()` (or the environment variable LAFF_STOPWORDS_EN) at it; asking for stop-word removal without a
+list raises instead of silently keeping the words.
+"""
+from __future__ import annotations
+
+import io
+import os
+import pickle
+import re
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from ._capi import LaffError
+from .bigfile import BigFile
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# tokeniser and vocabulary (host)
+# ----------------------------------------------------------------------------------------------------------------
+class TextTool:
+    """textlib.py:27-59 (English branch; the Chinese branch is Python-2 code in the reference and raises there)."""
+    _stopwords: Optional[frozenset] = None
+
+    @classmethod
+    def set_stopwords(cls, words_or_path) -> None:
+        if isinstance(words_or_path, (str, os.PathLike)):
+            with open(words_or_path) as f:
+                cls._stopwords = frozenset(map(str.strip, f.readlines()))
+        else:
+            cls._stopwords = frozenset(words_or_path)
+
+    @classmethod
+    def stopwords(cls) -> frozenset:
+        if cls._stopwords is None:
+            path = os.environ.get("LAFF_STOPWORDS_EN")
+            if not path:
+                raise LaffError("stop-word removal requested but no list is configured: call TextTool.set_stopwords(path) "
+                                "or set LAFF_STOPWORDS_EN (the reference ships stopwords_en.txt)")
+            cls.set_stopwords(path)
+        return cls._stopwords
+
+    @staticmethod
+    def tokenize(input_str: str, clean: bool = True, language: str = "en", remove_stopword: bool = False) -> List[str]:
+        if language != "en":
+            raise NotImplementedError("only the English tokeniser of the reference is usable under Python 3")
+        sent = input_str
+        if clean:
+            sent = sent.replace("\r", " ")
+            sent = re.sub(r"[^A-Za-z0-9]", " ", sent).strip().lower()
+        tokens = sent.split()
+        if remove_stopword:
+            stop = TextTool.stopwords()
+            tokens = [x for x in tokens if x not in stop]
+        return tokens
+
+
+class Vocabulary:
+    """textlib.py:81-112."""
+
+    def __init__(self, encoding):
+        self.word2idx = {}
+        self.idx2word = {}
+        self.encoding = encoding
+
+    def add(self, word):
+        if word not in self.word2idx:
+            idx = len(self.word2idx)
+            self.word2idx[word] = idx
+            self.idx2word[idx] = word
+
+    def find(self, word):
+        return self.word2idx.get(word, -1)
+
+    def __getitem__(self, index):
+        return self.idx2word[index]
+
+    def __call__(self, word):
+        if word not in self.word2idx:
+            if "gru" in self.encoding:
+                return self.word2idx["<unk>"]
+            raise Exception("word out of vocab: %s" % word)
+        return self.word2idx[word]
+
+    def __len__(self):
+        return len(self.word2idx)
+
+
+class _VocabUnpickler(pickle.Unpickler):
+    """Reads the reference's vocabulary pickles (instances of textlib.Vocabulary) without the reference tree."""
+
+    def find_class(self, module, name):
+        if name == "Vocabulary" and module.split(".")[-1] in ("textlib", "text"):
+            return Vocabulary
+        return super().find_class(module, name)
+
+
+def load_vocab(path_or_bytes) -> Vocabulary:
+    if isinstance(path_or_bytes, (bytes, bytearray)):
+        return _VocabUnpickler(io.BytesIO(path_or_bytes)).load()
+    with open(path_or_bytes, "rb") as f:
+        return _VocabUnpickler(f).load()
+
+
+def _csr(lists: Sequence[Sequence[int]], device):
+    offsets = np.zeros(len(lists) + 1, dtype=np.int64)
+    np.cumsum([len(l) for l in lists], out=offsets[1:])
+    flat = np.fromiter((i for l in lists for i in l), dtype=np.int32, count=int(offsets[-1]))
+    return torch.from_numpy(offsets).to(device), torch.from_numpy(flat).to(device)
+
+
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise LaffError("laff_b200.text needs a CUDA device (no CPU fallback)")
+    return torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# txt2vec
+# ----------------------------------------------------------------------------------------------------------------
+class Txt2Vec:
+    """txt2vec.py:12-47.  norm: 0 none; 1 / 2 are declared by the reference but its `encoding` calls a method that does
+    not exist (`self.do_norm`, txt2vec.py:41) — the shipped configs use 0, anything else raises here too."""
+    remove_stopword = False
+
+    def __init__(self, data_path, norm=0, clean=True):
+        assert norm in [0, 1, 2], "invalid norm %s" % norm
+        if norm != 0:
+            raise AttributeError("'%s' object has no attribute 'do_norm' (the reference fails the same way for norm > 0)"
+                                 % self.__class__.__name__)
+        self.data_path = data_path
+        self.norm = norm
+        self.lang = "en"
+        self.clean = clean
+
+    def _preprocess(self, query):
+        return TextTool.tokenize(query, clean=self.clean, language=self.lang, remove_stopword=self.remove_stopword)
+
+    def encode_batch(self, captions: Sequence[str], device=None) -> torch.Tensor:
+        raise Exception("encoding not implemented yet!")
+
+    def encoding(self, query):
+        return self.encode_batch([query])[0].cpu().numpy().astype(np.float64)
+
+
+class BowVec(Txt2Vec):
+    """txt2vec.py:49-86: count of every in-vocabulary token."""
+
+    def __init__(self, data_path, norm=0, clean=True, vocab: Optional[Vocabulary] = None):
+        super().__init__(data_path, norm, clean)
+        self.vocab = vocab if vocab is not None else load_vocab(data_path)
+        self.ndims = len(self.vocab)
+
+    def token_ids(self, query) -> List[int]:
+        return [i for i in (self.vocab.find(w) for w in self._preprocess(query)) if i >= 0]
+
+    def encode_batch(self, captions, device=None):
+        dev = _device(device)
+        offsets, ids = _csr([self.token_ids(c) for c in captions], dev)
+        return ops.bow_counts(offsets, ids, self.ndims)
+
+    def __len__(self):
+        return self.ndims
+
+
+class BowVecNSW(BowVec):
+    remove_stopword = True
+
+
+class W2Vec(Txt2Vec):
+    """txt2vec.py:89-112: mean of the word vectors of the distinct in-vocabulary words (`BigFile.read` collapses
+    duplicates and orders by file position, bigfile.py:204-211), zeros when no word is known."""
+
+    def __init__(self, data_path, norm=0, clean=True, w2v: Optional[BigFile] = None):
+        super().__init__(data_path, norm, clean)
+        self.w2v = w2v if w2v is not None else BigFile(data_path)
+        _, self.ndims = self.w2v.shape()
+        self._table = None
+
+    def table(self, device=None) -> torch.Tensor:
+        """The word-vector table resident on the device (uploaded once, streamed from the feature file)."""
+        dev = _device(device)
+        if self._table is None or self._table.device != dev:
+            self._table = self.w2v.to_device(0, self.w2v.nr_of_images, dev)
+        return self._table
+
+    def word_ids(self, query) -> List[int]:
+        n2i = self.w2v.name2index
+        return sorted({n2i[w] for w in self._preprocess(query) if w in n2i})
+
+    def encode_batch(self, captions, device=None):
+        dev = _device(device)
+        offsets, ids = _csr([self.word_ids(c) for c in captions], dev)
+        return ops.gather_mean(self.table(dev), offsets, ids)
+
+
+class W2VecNSW(W2Vec):
+    remove_stopword = True
+
+
+class IndexVec(Txt2Vec):
+    """txt2vec.py:115-128: '<start>' + tokens + '<end>' as vocabulary indices (unknown words -> '<unk>')."""
+
+    def __init__(self, data_path, clean=True, vocab: Optional[Vocabulary] = None):
+        super().__init__(data_path, 0, clean)
+        self.vocab = vocab if vocab is not None else load_vocab(data_path)
+        self.ndims = len(self.vocab)
+
+    def _preprocess(self, query):
+        words = TextTool.tokenize(query, clean=self.clean, language=self.lang, remove_stopword=False)
+        return ["<start>"] + words + ["<end>"]
+
+    def encoding(self, query):
+        return np.array([self.vocab(word) for word in self._preprocess(query)])
+
+
+NAME_TO_T2V = {"bow": BowVec, "bow_nsw": BowVecNSW, "w2v": W2Vec, "w2v_nsw": W2VecNSW, "idxvec": IndexVec}
+
+
+def get_txt2vec(name):
+    assert name in NAME_TO_T2V
+    return NAME_TO_T2V[name]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GRU sentence encoder (numeric part)
+# ----------------------------------------------------------------------------------------------------------------
+def gru_encode(we: torch.Tensor, w_ih: torch.Tensor, w_hh: torch.Tensor, b_ih: torch.Tensor, b_hh: torch.Tensor,
+               ids: torch.Tensor, lengths: torch.Tensor, pooling: str = "mean", prepared: Optional[dict] = None):
+    """nn.Embedding -> single-layer unidirectional nn.GRU (batch_first, h0 = 0) over packed sequences -> pooling
+    (model/model.py:340-387).  ids int32 [B, T] (padding arbitrary beyond lengths[b]), lengths int32 [B].
+
+    The two matrix products run on the tcgen05 GEMM engine with 3-term bf16-split operands (fp32-grade products:
+    the recurrence feeds its own rounding back T times, so plain bf16 operands would drift); the input-side
+    product is one GEMM over all B*T tokens, the hidden-side one GEMM per step, gates in `laff_gru_cell`."""
+    B, T = ids.shape
+    H = w_hh.shape[1]
+    dev = we.device
+    p = prepared if prepared is not None else {}
+    if "wih16" not in p:
+        p["wih16"] = ops.split3_16(w_ih.detach().float(), 1, torch.bfloat16)
+        p["whh16"] = ops.split3_16(w_hh.detach().float(), 1, torch.bfloat16)
+        p["b_ih"] = b_ih.detach().float().contiguous()
+        p["b_hh"] = b_hh.detach().float().contiguous()
+    lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
+    x = ops.gather_rows(we.detach(), ids.to(dev).reshape(-1))
+    gi = ops.project(ops.split3_16(x, 0, torch.bfloat16), p["wih16"], p["b_ih"], "none").view(B, T, 3 * H)
+    h = torch.zeros((B, H), dtype=torch.float32, device=dev)
+    h2 = torch.empty_like(h)
+    want_mean = pooling in ("mean", "mean_last")
+    want_last = pooling in ("last", "mean_last")
+    if not (want_mean or want_last):
+        raise Exception("pooling %s is invalid" % pooling)
+    acc = torch.zeros_like(h) if want_mean else None
+    last = torch.zeros_like(h) if want_last else None
+    gh = torch.empty((B, 3 * H), dtype=torch.float32, device=dev)
+    for t in range(T):
+        ops.project(ops.split3_16(h, 0, torch.bfloat16), p["whh16"], p["b_hh"], "none", out=gh)
+        ops.gru_cell(gi[:, t], gh, h, lengths, t, h2, acc, last)
+        h, h2 = h2, h
+    if want_mean:
+        ops.mean_over_length(acc, lengths)
+    if pooling == "mean":
+        return acc
+    if pooling == "last":
+        return last
+    return torch.cat((acc, last), dim=1)

@@ -287,6 +287,72 @@ def eval_label_matrix(label_matrix: np.ndarray):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# text front-end
+# ----------------------------------------------------------------------------------------------------------------
+def tokenize(input_str: str, clean: bool = True, remove_stopword: bool = False, stopwords=()) -> list:
+    """textlib.py:27-47, English branch."""
+    import re
+    sent = input_str
+    if clean:
+        sent = sent.replace("\r", " ")
+        sent = re.sub(r"[^A-Za-z0-9]", " ", sent).strip().lower()
+    tokens = sent.split()
+    if remove_stopword:
+        tokens = [x for x in tokens if x not in stopwords]
+    return tokens
+
+
+def bow_encoding(words: Sequence[str], word2idx: Mapping[str, int]) -> np.ndarray:
+    """BowVec._encoding (txt2vec.py:56-63)."""
+    vec = np.zeros(len(word2idx))
+    for w in words:
+        idx = word2idx.get(w, -1)
+        if idx >= 0:
+            vec[idx] += 1
+    return vec
+
+
+def w2v_encoding(words: Sequence[str], name2index: Mapping[str, int], table: np.ndarray) -> np.ndarray:
+    """W2Vec._encoding (txt2vec.py:97-104) over BigFile.read (bigfile.py:197-220): distinct known words, in file
+    order, as float64 lists; mean over them, zeros if none."""
+    idx = sorted({name2index[w] for w in words if w in name2index})
+    if not idx:
+        return np.zeros(table.shape[1])
+    return np.array([table[i].tolist() for i in idx]).mean(axis=0)
+
+
+def index_encoding(words: Sequence[str], word2idx: Mapping[str, int]) -> np.ndarray:
+    """IndexVec (txt2vec.py:121-128) with the 'gru' vocabulary's <unk> rule (textlib.py:102-109)."""
+    words = ["<start>"] + list(words) + ["<end>"]
+    return np.array([word2idx[w] if w in word2idx else word2idx["<unk>"] for w in words])
+
+
+def gru_encoder(idx_vecs: Sequence[np.ndarray], we: np.ndarray, w_ih: np.ndarray, w_hh: np.ndarray, b_ih: np.ndarray,
+                b_hh: np.ndarray, pooling: str = "mean") -> np.ndarray:
+    """GruTxtEncoder.forward (model/model.py:340-387): embedding, one-layer nn.GRU (gate order r, z, n; h0 = 0) run over
+    each sequence's own length (pack_padded_sequence), then mean / last / mean_last pooling."""
+    H = w_hh.shape[1]
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))
+    outs = []
+    for ids in idx_vecs:
+        h = np.zeros(H, dtype=np.float32)
+        hs = []
+        for tok in ids:
+            x = we[tok].astype(np.float32)
+            gi = w_ih @ x + b_ih
+            gh = w_hh @ h + b_hh
+            r = sig(gi[:H] + gh[:H])
+            z = sig(gi[H:2 * H] + gh[H:2 * H])
+            n = np.tanh(gi[2 * H:] + r * gh[2 * H:])
+            h = ((1.0 - z) * n + z * h).astype(np.float32)
+            hs.append(h)
+        hs = np.stack(hs)
+        mean, last = hs.mean(axis=0), hs[-1]
+        outs.append(mean if pooling == "mean" else last if pooling == "last" else np.concatenate([mean, last]))
+    return np.stack(outs).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # predictor / validate: id-based ground truth, both directions, result writers  (SURVEY §8f N1)
 # ----------------------------------------------------------------------------------------------------------------
 def sorted_desc(scores: np.ndarray) -> np.ndarray:

@@ -1,0 +1,89 @@
+"""Text front-end, CPU: the oracle restatement and the host-side tokeniser / vocabulary code against
+outputs of the unmodified reference (tests/golden/text, written by tests/golden/make_golden_text.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from laff_b200 import synth
+from laff_b200 import text as T
+from laff_b200.bigfile import BigFile
+from oracle import laff_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+D = os.path.join(HERE, "golden", "text")
+META = json.load(open(os.path.join(D, "meta.json")))
+GOLD = np.load(os.path.join(D, "golden.npz"))
+
+
+@pytest.fixture(autouse=True)
+def stopwords():
+    T.TextTool.set_stopwords(META["stopwords_used"])
+    yield
+    T.TextTool._stopwords = None
+
+
+def test_tokenizer_matches_reference():
+    for c, a, b in zip(META["captions"], META["tokens"], META["tokens_nsw"]):
+        assert T.TextTool.tokenize(c) == a == O.tokenize(c)
+        assert T.TextTool.tokenize(c, remove_stopword=True) == b == O.tokenize(c, remove_stopword=True, stopwords=META["stopwords_used"])
+
+
+def test_stopword_removal_without_a_list_fails_loudly(monkeypatch):
+    T.TextTool._stopwords = None
+    monkeypatch.delenv("LAFF_STOPWORDS_EN", raising=False)
+    with pytest.raises(T.LaffError):
+        T.TextTool.tokenize("a dog", remove_stopword=True)
+
+
+def test_reference_vocabulary_pickles_load_without_the_reference():
+    bow = T.load_vocab(os.path.join(D, "vocab_bow_nsw.pkl"))
+    gru = T.load_vocab(os.path.join(D, "vocab_gru.pkl"))
+    assert isinstance(bow, T.Vocabulary) and [bow[i] for i in range(len(bow))] == META["bow_words"]
+    assert [gru[i] for i in range(len(gru))] == META["gru_words"]
+    assert bow.find("zebra") == -1 and gru("zebra") == gru("<unk>")
+    with pytest.raises(Exception, match="word out of vocab"):
+        bow("zebra")
+    idx = T.IndexVec(os.path.join(D, "vocab_gru.pkl"))
+    for c, ref in zip(META["captions"], META["index"]):
+        assert idx.encoding(c).tolist() == ref
+        assert O.index_encoding(O.tokenize(c), gru.word2idx).tolist() == ref
+
+
+def test_oracle_bow_w2v_match_reference():
+    bow = T.load_vocab(os.path.join(D, "vocab_bow_nsw.pkl"))
+    w2v = BigFile(os.path.join(D, "w2v"))
+    table = np.asarray(w2v.matrix())
+    assert np.array_equal(table, GOLD["w2v_table"])
+    for i, c in enumerate(META["captions"]):
+        words = O.tokenize(c, remove_stopword=True, stopwords=META["stopwords_used"])
+        assert np.array_equal(O.bow_encoding(words, bow.word2idx), GOLD["bow_enc"][i])
+        assert np.array_equal(O.w2v_encoding(words, w2v.name2index, table), GOLD["w2v_enc"][i])     # float64, bit-exact
+    assert np.array_equal(GOLD["bow_enc"].astype(np.float32), GOLD["bow_module"])
+    assert np.array_equal(GOLD["w2v_enc"].astype(np.float32), GOLD["w2v_module"])
+    assert not GOLD["w2v_enc"][2].any() and not GOLD["bow_enc"][4].any()                             # empty bags
+
+
+def gru_params(tag, shapes):
+    return {k: np.asarray(synth.param(71, "gru_%s/%s" % (tag, k), shp)) for k, shp in shapes.items()}
+
+
+def test_oracle_gru_matches_reference():
+    gru = T.load_vocab(os.path.join(D, "vocab_gru.pkl"))
+    ids = [np.array(v) for v in META["index"]]
+    sd = {k[len("gru_small/"):]: GOLD[k] for k in GOLD.files if k.startswith("gru_small/")}
+    for pooling in ("mean", "last", "mean_last"):
+        out = O.gru_encoder(ids, sd["we.weight"], sd["rnn.weight_ih_l0"], sd["rnn.weight_hh_l0"], sd["rnn.bias_ih_l0"],
+                            sd["rnn.bias_hh_l0"], pooling)
+        np.testing.assert_allclose(out, GOLD["gru_small_%s" % pooling], rtol=0, atol=2e-6)
+    V = len(gru)
+    p = gru_params("full", {"we.weight": (V, 500), "rnn.weight_ih_l0": (3072, 500), "rnn.weight_hh_l0": (3072, 1024),
+                            "rnn.bias_ih_l0": (3072,), "rnn.bias_hh_l0": (3072,)})
+    out = O.gru_encoder(ids, p["we.weight"], p["rnn.weight_ih_l0"], p["rnn.weight_hh_l0"], p["rnn.bias_ih_l0"], p["rnn.bias_hh_l0"])
+    np.testing.assert_allclose(out, GOLD["gru_full_mean"], rtol=0, atol=5e-6)
+
+
+def test_norm_other_than_zero_fails_like_the_reference():
+    with pytest.raises(AttributeError):
+        T.BowVec(os.path.join(D, "vocab_bow_nsw.pkl"), norm=2)
