@@ -24,7 +24,11 @@ class LaffConfig:
     max_violation = True               # base_config.py:88
     cost_style = "sum"                 # base_config.py:90
     measure = "cosine"                 # base_config.py:92
-    grad_clip = 2
+    optimizer = "rmsprop"              # base_config.py:95
+    lr = 0.0001                        # base_config.py:97
+    lr_decay_rate = 0.99               # base_config.py:98
+    grad_clip = 2                      # base_config.py:100
+    negative = False                   # base_config.py:245
     float16 = False
     multi_space = True                 # base_config.py:167
     attention_l2norm = False           # base_config.py:125

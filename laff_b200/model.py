@@ -30,6 +30,8 @@ from . import ops
 from . import loss as _loss
 from .loss import MarginRankingLoss, MarginRankingLossWithScore
 
+_PARAM_EPOCH = 0  # bumped by the device optimizer step, which updates parameters through raw pointers
+
 _ROW_CHUNK = 32768  # rows fused per pass: bounds the projected-feature scratch to L * 512 MB
 _FUSED_ROW_CHUNK = 131072  # rows per laff_fuse_forward launch: bounds the 16-bit input copies (1.3 GB for the video net)
 
@@ -79,7 +81,7 @@ class TransformNet(nn.Module):
 
     # -- prepared (16-bit / folded) parameters, rebuilt when the parameters change -----------------------------
     def _version(self):
-        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        return (_PARAM_EPOCH,) + tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
 
     def prepared(self, precision: str):
         key = (precision, self._version())
@@ -189,7 +191,7 @@ class Multi_head_MyApply_Attention(nn.Module):
 
     def head_params(self):
         ps = [self.attention_layer[h].embedding_common[0] for h in range(self.multi_heads)]
-        key = tuple((p.weight.data_ptr(), p.weight._version, p.bias._version) for p in ps)
+        key = (_PARAM_EPOCH,) + tuple((p.weight.data_ptr(), p.weight._version, p.bias._version) for p in ps)
         if self._cache.get("key") != key:
             w = torch.cat([p.weight.detach().view(1, -1) for p in ps], 0).float().contiguous()
             b = torch.cat([p.bias.detach().view(1) for p in ps], 0).float().contiguous()
@@ -663,9 +665,70 @@ class W2VVPP(nn.Module):
             return loss, {"triplet_loss": loss}
         raise Exception("vis_embs dims are not equal to txt_embs dims")
 
+    # ---------------------------------------------------------------- training step (model/model.py:964-1001)
+    def _train_features(self, net, inputs, dev):
+        """(x on the device, TransformNet) pairs of one fusion net, in the reference's feature order."""
+        if net is self.txt_net:
+            mods = dict(net.transform_layer.named_children())
+            return [(net._feature(inputs, n).to(dev, non_blocking=True).float(), mods[n + "_transform"])
+                    for n in net.encoder_name_list], net.attention_layer
+        if not isinstance(net, VisMutiTransformNetAddAttnetion):
+            raise NotImplementedError("training LAFF-ml (frame-level attention backward) is not built yet; 'LAFF' trains")
+        mods = dict(net.VisMutiTransformNet.named_children())
+        feats = []
+        for name in net.vis_net_space_dict.keys():
+            x = inputs[name].to(dev, non_blocking=True).float()
+            if not bool((x != 0).any()):  # train-mode quirk of the reference: an all-zero feature becomes noise
+                x = torch.randn_like(x)    # (model/model.py:1819-1821)
+            feats.append((x, mods[name]))
+        return feats, net.attention_layer
+
+    def _make_optimizer(self):
+        from .train import DeviceOptimizer
+        opt = self.opt
+        kind = getattr(opt, "optimizer", "rmsprop")
+        eps = self._adam_eps if kind == "adam" else None
+        return DeviceOptimizer(list(self.parameters()), kind=kind, lr=getattr(opt, "lr", 1e-4), eps=eps,
+                               max_grad_norm=self.grad_clip if self.grad_clip and self.grad_clip > 0 else 0.0)
+
+    _adam_eps = 1e-8  # torch default (model/model.py:824); the LAFF class overrides it with 1e-4 (model/model.py:2022)
+
     def forward(self, train_data, epoch=None):
-        raise NotImplementedError("the full training step (backward through the fusion nets, optimizer) is SURVEY "
-                                  "§8f N4; the loss and its embedding gradients are available via compute_loss")
+        """One training step (model/model.py:964-1001): forward of both nets in train mode, summed per-head
+        MarginRankingLoss, backward, clip_grad_norm_(params, grad_clip), optimizer step.  Returns loss_items.
+        Everything runs through the C ABI (laff_b200/train.py); no autograd graph is built."""
+        from .train import FusionTrainStep
+        global _PARAM_EPOCH
+        opt = self.opt
+        if getattr(opt, "negative", False):
+            raise NotImplementedError("negation-aware training (cal_foward_neg) is outside the LAFF hot path")
+        if not getattr(opt, "multi_space", True):
+            raise NotImplementedError("training through the score-matrix loss branch (multi_space = False) is not built")
+        if getattr(opt, "float16", False):
+            raise NotImplementedError("AMP / GradScaler training is not built; operand precision is set by `train_precision`")
+        if not self.training:
+            raise ops.LaffError("model(train_data) is a training step: call model.train() first")
+        self.iters += 1
+        dev = _cuda_device(next(self.parameters()).device)
+        precision = getattr(self, "train_precision", "bf16x3")
+        if getattr(self, "optimizer", None) is None:
+            self.optimizer = self._make_optimizer()
+            self._steps = {}
+        seed = (int(getattr(opt, "seed", 0) or 0) << 20) + self.iters
+        outs = {}
+        for key, net, inputs in (("txt", self.txt_net, train_data["captions"]), ("vis", self.vis_net, train_data["vis_feats"])):
+            feats, att = self._train_features(net, inputs, dev)
+            step = self._steps.get(key)
+            if step is None or step.att is not att or step.precision != precision:
+                step = self._steps[key] = FusionTrainStep(att, precision)
+            outs[key] = step.forward(feats, seed * 2 + (key == "vis"))
+        c = self.criterion
+        loss, d_txt, d_vis = ops.mrl_forward_backward(outs["txt"], outs["vis"], c.margin, c.max_violation, c.direction, c.cost_style)
+        self._steps["txt"].backward(d_txt)
+        self._steps["vis"].backward(d_vis)
+        self.last_grad_norm = self.optimizer.step()
+        _PARAM_EPOCH += 1  # parameters changed behind torch's version counters: drop the eval-mode operand caches
+        return {"triplet_loss": loss}
 
     # ---------------------------------------------------------------- predict (model/model.py:1018-1079)
     def _encode_vis(self, output_dict, out16_dtype=None):
@@ -712,6 +775,7 @@ class W2VVPP(nn.Module):
 
 class W2VVPP_MultiHeadAttention(W2VVPP):
     """'LAFF' (model/model.py:1930-2048)."""
+    _adam_eps = 1e-4  # model/model.py:2022
 
     def _init_vis_net(self, opt):
         self.vis_net = VisMutiTransformNetAddAttnetion(opt, opt.vis_fc_layers[0])

@@ -537,3 +537,80 @@ def mrl_score_forward_backward(score: torch.Tensor, margin: float, max_violation
                int(bool(max_violation)), _capi.DIRECTION[direction], int(cost_style != "sum"), _ptr(loss),
                _ptr(d_score), _stream(score))
     return loss, d_score
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# training step (T1 / N4)
+# ----------------------------------------------------------------------------------------------------------------
+def transform_train_forward(src: torch.Tensor, D: int, p_drop: float, seed: int, bn=None, momentum: float = 0.1):
+    """Dropout + train-mode BatchNorm1d after the activation (laff_transform_train_forward).
+    src fp32 [B, D] (activated projection) or [B, in_dim] (raw feature tiled D / in_dim times).
+    bn: None or an nn.BatchNorm1d whose running statistics are updated in place.
+    Returns (y [B, D], mask uint8 [B, D] or None, save_mean or None, save_invstd or None)."""
+    _need_cuda(src)
+    src = _rowmajor(src.float() if src.dtype != torch.float32 else src)
+    B = src.shape[0]
+    dev = src.device
+    y = torch.empty((B, D), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, D), dtype=torch.uint8, device=dev) if p_drop > 0 else None
+    sm = si = None
+    gamma = beta = rm = rv = None
+    eps = 1e-5
+    if bn is not None:
+        sm = torch.empty(D, dtype=torch.float32, device=dev)
+        si = torch.empty(D, dtype=torch.float32, device=dev)
+        gamma, beta, rm, rv, eps = bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps
+        momentum = bn.momentum if bn.momentum is not None else momentum
+    _capi.call("laff_transform_train_forward", _ptr(src), src.stride(0), src.shape[1], B, D, float(p_drop),
+               int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), float(momentum), float(eps),
+               int(bn is not None), _ptr(y), y.stride(0), _ptr(mask), _ptr(sm), _ptr(si), _stream(src))
+    return y, mask, sm, si
+
+
+def transform_train_backward(dy: torch.Tensor, a: Optional[torch.Tensor], tiled_x: Optional[torch.Tensor], mask, p_drop: float,
+                             activation, bn, save_mean, save_invstd, want_dz: bool = True, dgamma=None, dbeta=None, dbias=None):
+    """Backward of transform_train_forward down to the GEMM output (laff_transform_train_backward).
+    Returns dz [B, D] (None for a tiled feature); writes dgamma / dbeta / dbias [D] when given."""
+    _need_cuda(dy, a, tiled_x)
+    B, D = dy.shape
+    dz = torch.empty((B, D), dtype=torch.float32, device=dy.device) if (want_dz and a is not None) else None
+    act = activation if isinstance(activation, int) else _capi.ACT[activation]
+    _capi.call("laff_transform_train_backward", _ptr(dy), dy.stride(0), _ptr(a), 0 if a is None else a.stride(0), _ptr(tiled_x),
+               0 if tiled_x is None else tiled_x.stride(0), 0 if tiled_x is None else tiled_x.shape[1], _ptr(mask), float(p_drop),
+               act, int(bn is not None), _ptr(bn.weight if bn is not None else None), _ptr(save_mean), _ptr(save_invstd), B, D,
+               _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _stream(dy))
+    return dz
+
+
+def attention_pool_backward(ys: Sequence[torch.Tensor], att_weight: torch.Tensor, att_bias: torch.Tensor, heads: int, head_dim: int,
+                            dout: torch.Tensor, dw: torch.Tensor, dc: torch.Tensor, norm_eps: float = 1e-14):
+    """Backward of the LAFF block (with_ave = mul = False).  ys: the L inputs fp32 [rows, H*d_h]; dout [rows, H*d_h];
+    dw [H, d_h] / dc [H] receive the gradients of the logit weights / biases.  Returns the list of dy_l."""
+    _need_cuda(dout, att_weight, att_bias, dw, dc, *ys)
+    rows, D = dout.shape
+    dev = dout.device
+    ys = [_rowmajor(y) for y in ys]
+    dys = [torch.empty((rows, D), dtype=torch.float32, device=dev) for _ in ys]
+    yp = torch.tensor([y.data_ptr() for y in ys], dtype=torch.int64).to(dev)
+    dp = torch.tensor([d.data_ptr() for d in dys], dtype=torch.int64).to(dev)
+    lds = torch.tensor([y.stride(0) for y in ys], dtype=torch.int64).to(dev)
+    dw_part = torch.empty(rows * D, dtype=torch.float32, device=dev)
+    dc_part = torch.empty(rows * heads, dtype=torch.float32, device=dev)
+    dout = _rowmajor(dout)
+    _capi.call("laff_attention_pool_backward", _ptr(yp), _ptr(lds), len(ys), heads, head_dim, _ptr(att_weight), _ptr(att_bias),
+               _ptr(dout), dout.stride(0), rows, float(norm_eps), _ptr(dp), _ptr(dw_part), _ptr(dc_part), _ptr(dw), _ptr(dc),
+               _stream(dout))
+    return dys
+
+
+def transpose_16(x: torch.Tensor, dtype=torch.bfloat16, terms: int = 1, side: int = 0) -> torch.Tensor:
+    """fp32 [R, C] -> 16-bit [C, pad8(R) * terms] (laff_transpose_16): K-major operand of a product contracted over R."""
+    _need_cuda(x)
+    x = _rowmajor(x.float() if x.dtype != torch.float32 else x)
+    R, Cn = x.shape
+    kpad = (R + 7) // 8 * 8
+    dtype = torch_dtype(dtype)
+    out = torch.empty((Cn, kpad * terms), dtype=dtype, device=x.device)
+    _capi.call("laff_transpose_16", _ptr(x), x.stride(0), R, Cn, _DT[dtype], int(terms), int(side), _ptr(out), out.stride(0),
+               _stream(x))
+    return out

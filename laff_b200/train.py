@@ -1,0 +1,182 @@
+"""One training step of the LAFF model on the device (model/model.py:964-1001).
+
+The reference runs `txt_net` / `vis_net` in train mode under autograd, sums the per-head MarginRankingLoss, calls
+`loss.backward()`, `clip_grad_norm_(params, grad_clip)` and `optimizer.step()` (RMSprop lr 1e-4 in the shipped configs).
+Here the same step is an explicit forward / backward over the C ABI — no autograd graph:
+
+  forward   per projected feature: tcgen05 GEMM with fused bias + activation (`laff_project`), then dropout + train-mode
+            BatchNorm (`laff_transform_train_forward`); no-transform features: tile + train-mode BatchNorm; LAFF pooling
+            (`laff_attention_pool`); loss + its gradient w.r.t. both embeddings (`laff_mrl_forward_backward`).
+  backward  `laff_attention_pool_backward` -> `laff_transform_train_backward` -> weight gradients dW = dZ^T x as a
+            tcgen05 GEMM over K = batch (`laff_transpose_16` operands, `laff_sim_dense`), written straight into `.grad`.
+  update    `laff_optimizer_step`: gradient-norm clipping + RMSprop / Adam for every tensor in one pass, no host sync.
+
+Operand precision of the GEMMs: '3-term bf16 split' by default (fp32-grade products — the reference trains in fp32
+unless `config.float16`), or plain bf16 / fp16 via `precision=`.  Dropout uses a counter-based mask (seed per step and
+feature), not torch's generator: with p > 0 the step is statistically, not bitwise, the reference's.
+Restrictions (raise NotImplementedError): attention variants with the mean residual / product, the score-matrix loss
+branch (`multi_space = False`), and training the GRU text encoder (its features must arrive precomputed).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _capi, ops
+from ._capi import LaffError, OptTensor
+
+
+def _operands(x: torch.Tensor, precision: str, side: int):
+    if precision == "bf16x3":
+        return ops.split3_16(x, side, torch.bfloat16)
+    return ops.cast_pad_16(x, torch.bfloat16 if precision == "bf16" else torch.float16)
+
+
+def _grad_buffer(p: nn.Parameter) -> torch.Tensor:
+    if p.grad is None or p.grad.shape != p.shape or p.grad.device != p.device or not p.grad.is_contiguous():
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+class FusionTrainStep:
+    """Train-mode forward + backward of one fusion net: a list of (x, TransformNet) features and its attention layer."""
+
+    def __init__(self, attention, precision: str = "bf16x3"):
+        if getattr(attention, "with_ave", False) or getattr(attention, "mul", False):
+            raise NotImplementedError("training the mean-residual / product attention variants is not built (shipped: off)")
+        self.att = attention
+        self.precision = precision
+        self.cache: Optional[dict] = None
+
+    def forward(self, features: Sequence, seed: int) -> torch.Tensor:
+        att = self.att
+        H, dh = att.multi_heads, att.dim_per_head
+        D = H * dh
+        items = []
+        for i, (x, tn) in enumerate(features):
+            p = float(tn.dropout_p or 0.0)
+            it = {"x": x, "tn": tn, "p": p}
+            if tn.fc1 is not None:
+                w16 = _operands(tn.fc1.weight.detach(), self.precision, 1)
+                a = ops.project(_operands(x, self.precision, 0), w16, tn.fc1.bias.detach(), tn.activation_name)
+                it["a"] = a
+                if p > 0 or tn.bn1 is not None:
+                    y, mask, sm, si = ops.transform_train_forward(a, D, p, seed * 131 + i, tn.bn1)
+                else:
+                    y, mask, sm, si = a, None, None, None
+            else:
+                y, mask, sm, si = ops.transform_train_forward(x, D, p, seed * 131 + i, tn.bn1)
+            if tn.bn1 is not None:
+                tn.bn1.num_batches_tracked += 1
+            it.update(y=y, mask=mask, sm=sm, si=si)
+            items.append(it)
+        ps = [att.attention_layer[h].embedding_common[0] for h in range(H)]
+        w = torch.cat([q.weight.detach().view(1, -1) for q in ps], 0).float().contiguous()
+        b = torch.cat([q.bias.detach().view(1) for q in ps], 0).float().contiguous()
+        out, _, _ = ops.attention_pool([{"y": it["y"]} for it in items], w, b, H, dh)
+        self.cache = {"items": items, "w": w, "b": b, "heads": ps}
+        return out
+
+    def backward(self, dout: torch.Tensor) -> None:
+        c = self.cache
+        if c is None:
+            raise LaffError("FusionTrainStep.backward called before forward")
+        att = self.att
+        H, dh = att.multi_heads, att.dim_per_head
+        dev = dout.device
+        dout = dout.reshape(dout.shape[0], -1)
+        dw = getattr(self, "_dw", None)
+        if dw is None or dw.device != dev:
+            self._dw = dw = torch.zeros((H, dh), dtype=torch.float32, device=dev)
+            self._dc = torch.zeros(H, dtype=torch.float32, device=dev)
+        dys = ops.attention_pool_backward([it["y"] for it in c["items"]], c["w"], c["b"], H, dh, dout, dw, self._dc)
+        for h, q in enumerate(c["heads"]):  # per-head parameters: gradients are views of the two stacked buffers
+            q.weight.grad = dw[h:h + 1]
+            q.bias.grad = self._dc[h:h + 1]
+        for it, dy in zip(c["items"], dys):
+            tn = it["tn"]
+            dgamma = _grad_buffer(tn.bn1.weight) if tn.bn1 is not None else None
+            dbeta = _grad_buffer(tn.bn1.bias) if tn.bn1 is not None else None
+            if tn.fc1 is None:
+                if tn.bn1 is not None:
+                    ops.transform_train_backward(dy, None, it["x"], it["mask"], it["p"], "none", tn.bn1, it["sm"], it["si"],
+                                                 want_dz=False, dgamma=dgamma, dbeta=dbeta)
+                continue
+            dbias = _grad_buffer(tn.fc1.bias)
+            dz = ops.transform_train_backward(dy, it["a"], None, it["mask"], it["p"], tn.activation_name, tn.bn1, it["sm"],
+                                              it["si"], dgamma=dgamma, dbeta=dbeta, dbias=dbias)
+            terms = 3 if self.precision == "bf16x3" else 1
+            dt = torch.float16 if self.precision == "fp16" else torch.bfloat16
+            ops.sim_dense(ops.transpose_16(dz, dt, terms, 0), ops.transpose_16(it["x"], dt, terms, 1), 1.0,
+                          out=_grad_buffer(tn.fc1.weight))
+        self.cache = None
+
+
+class DeviceOptimizer:
+    """clip_grad_norm_ + torch.optim.RMSprop / Adam semantics for a fixed list of parameters, one fused device pass per
+    step (`laff_optimizer_step`).  State tensors are allocated on first use; parameters whose `.grad` is None at the
+    first step are skipped for good (like parameters that never receive a gradient in the reference's model)."""
+
+    def __init__(self, params: Sequence[nn.Parameter], kind: str = "rmsprop", lr: float = 1e-4, alpha: float = 0.99,
+                 betas=(0.9, 0.999), eps: Optional[float] = None, max_grad_norm: float = 0.0):
+        if kind not in ("rmsprop", "adam"):
+            raise LaffError("optimizer %r: the reference trains with 'rmsprop' or 'adam'" % kind)
+        self.params = [p for p in params]
+        self.kind, self.lr, self.alpha, self.betas = kind, float(lr), float(alpha), betas
+        self.eps = float(eps) if eps is not None else 1e-8
+        self.max_grad_norm = float(max_grad_norm)
+        self.step_count = 0
+        self._built = None
+        self.param_groups = [{"lr": self.lr}]  # lr schedulers of the caller read / write this like torch's
+
+    def _build(self):
+        live = [p for p in self.params if p.grad is not None]
+        if not live:
+            raise LaffError("DeviceOptimizer.step: no parameter has a gradient")
+        dev = live[0].device
+        self.state1 = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in live]
+        self.state2 = [torch.zeros_like(p, memory_format=torch.contiguous_format) if self.kind == "adam" else None for p in live]
+        arr = (OptTensor * len(live))()
+        for i, p in enumerate(live):
+            if not p.is_contiguous() or not p.grad.is_contiguous() or p.dtype != torch.float32:
+                raise LaffError("DeviceOptimizer needs contiguous fp32 parameters and gradients")
+            arr[i].param, arr[i].grad, arr[i].grad_out = p.data_ptr(), p.grad.data_ptr(), p.grad.data_ptr()
+            arr[i].state1 = self.state1[i].data_ptr()
+            arr[i].state2 = self.state2[i].data_ptr() if self.state2[i] is not None else None
+            arr[i].n = p.numel()
+        sizes = (C.c_longlong * len(live))(*[p.numel() for p in live])
+        lib = _capi.lib()
+        n_blocks = lib.laff_optimizer_blocks(sizes, len(live), None, None, 0)
+        if n_blocks < 0:
+            _capi.check(n_blocks, "laff_optimizer_blocks")
+        bt = (C.c_int * n_blocks)()
+        bs = (C.c_longlong * n_blocks)()
+        lib.laff_optimizer_blocks(sizes, len(live), bt, bs, n_blocks)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        self._built = {
+            "live": live, "ptrs": [(p.data_ptr(), p.grad.data_ptr()) for p in live], "desc": raw,
+            "bt": torch.tensor(list(bt), dtype=torch.int32, device=dev), "bs": torch.tensor(list(bs), dtype=torch.int64, device=dev),
+            "partial": torch.empty(n_blocks, dtype=torch.float64, device=dev),
+            "norm": torch.zeros(1, dtype=torch.float64, device=dev), "n_blocks": n_blocks}
+
+    def step(self) -> torch.Tensor:
+        """Returns the (device) total gradient norm before clipping."""
+        if self._built is None:
+            self._build()
+        b = self._built
+        if [(p.data_ptr(), p.grad.data_ptr()) for p in b["live"]] != b["ptrs"]:
+            self._build()  # a parameter or gradient was re-allocated
+            b = self._built
+        self.step_count += 1
+        lr = float(self.param_groups[0]["lr"])
+        first = self.alpha if self.kind == "rmsprop" else self.betas[0]
+        _capi.call("laff_optimizer_step", ops._ptr(b["desc"]), ops._ptr(b["bt"]), ops._ptr(b["bs"]), b["n_blocks"],
+                   0 if self.kind == "rmsprop" else 1, lr, float(first), float(self.betas[1]), self.eps, self.step_count,
+                   self.max_grad_norm, ops._ptr(b["partial"]), ops._ptr(b["norm"]), ops._stream(b["desc"]))
+        return b["norm"]
+
+    def zero_grad(self):
+        pass  # every gradient buffer is overwritten by the next backward

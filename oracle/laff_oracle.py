@@ -287,6 +287,137 @@ def eval_label_matrix(label_matrix: np.ndarray):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# training step: explicit forward / backward of what the reference leaves to autograd
+# ----------------------------------------------------------------------------------------------------------------
+def _act_grad(a: np.ndarray, name) -> np.ndarray:
+    if name == "tanh":
+        return 1.0 - a * a
+    if name == "sigmoid":
+        return a * (1.0 - a)
+    if name == "relu":
+        return (a > 0).astype(a.dtype)
+    return np.ones_like(a)
+
+
+def fusion_train_forward(feats: Sequence[Tuple[str, np.ndarray]], sd: dict, prefixes: Mapping[str, str], att_prefix: str,
+                         heads: int, no_transform: Sequence[str], activation="tanh", momentum=0.1, eps=1e-5):
+    """Train-mode forward of one fusion net (TransformNet.forward with batch-statistics BatchNorm, dropout p = 0;
+    model/model.py:257-276, :1807-1876) followed by the multi-head LAFF block.  Updates the running statistics in `sd`
+    in place like nn.BatchNorm1d.  Returns (embeddings [B, H, d_h], cache for fusion_train_backward)."""
+    items = []
+    for name, x in feats:
+        pre = prefixes[name]
+        it = {"name": name, "pre": pre, "x": x.astype(np.float64)}
+        if name in no_transform:
+            y = np.tile(it["x"], (1, heads))
+        else:
+            z = it["x"] @ sd[pre + "fc1.weight"].astype(np.float64).T + sd[pre + "fc1.bias"]
+            y = activation_fn(z, activation)
+            it["a"] = y
+        if pre + "bn1.weight" in sd:
+            B = y.shape[0]
+            mean, var = y.mean(0), y.var(0)
+            it["xhat"] = (y - mean) / np.sqrt(var + eps)
+            it["invstd"] = 1.0 / np.sqrt(var + eps)
+            y = it["xhat"] * sd[pre + "bn1.weight"] + sd[pre + "bn1.bias"]
+            sd[pre + "bn1.running_mean"] = ((1 - momentum) * sd[pre + "bn1.running_mean"] + momentum * mean).astype(np.float32)
+            sd[pre + "bn1.running_var"] = ((1 - momentum) * sd[pre + "bn1.running_var"] + momentum * var * B / (B - 1)).astype(np.float32)
+            if pre + "bn1.num_batches_tracked" in sd:
+                sd[pre + "bn1.num_batches_tracked"] = sd[pre + "bn1.num_batches_tracked"] + 1
+        it["y"] = y
+        items.append(it)
+    Y = np.stack([it["y"] for it in items], 1)                                  # [B, L, D]
+    B, L, D = Y.shape
+    dh = D // heads
+    Yh = Y.reshape(B, L, heads, dh)
+    W = np.stack([sd["%sattention_layer.%d.embedding_common.0.weight" % (att_prefix, h)].reshape(-1) for h in range(heads)]).astype(np.float64)
+    c = np.array([sd["%sattention_layer.%d.embedding_common.0.bias" % (att_prefix, h)].reshape(-1)[0] for h in range(heads)], dtype=np.float64)
+    e = np.einsum("blhd,hd->bhl", Yh, W) + c[None, :, None]
+    p = softmax(e, axis=2)
+    g = np.einsum("bhl,blhd->bhd", p, Yh)
+    nrm = np.sqrt((g * g).sum(-1, keepdims=True))
+    out = g / (nrm + 1e-14)
+    return out, {"items": items, "Yh": Yh, "W": W, "p": p, "g": g, "nrm": nrm, "out": out, "heads": heads, "att_prefix": att_prefix,
+                 "activation": activation}
+
+
+def fusion_train_backward(cache: dict, dout: np.ndarray, sd: Mapping[str, np.ndarray]) -> dict:
+    """Gradients of every parameter of one fusion net given d loss / d embeddings [B, H, d_h]."""
+    Yh, W, p, g, nrm, out, heads = (cache[k] for k in ("Yh", "W", "p", "g", "nrm", "out", "heads"))
+    B, L, H, dh = Yh.shape
+    inv = 1.0 / (nrm + 1e-14)
+    dot = (out * dout).sum(-1, keepdims=True)
+    dg = (dout - out * dot * nrm * inv) * inv
+    dp = np.einsum("bhd,blhd->bhl", dg, Yh)
+    de = p * (dp - (p * dp).sum(-1, keepdims=True))
+    dY = np.einsum("bhl,bhd->blhd", p, dg) + np.einsum("bhl,hd->blhd", de, W)
+    grads = {}
+    for h in range(H):
+        pre = "%sattention_layer.%d.embedding_common.0." % (cache["att_prefix"], h)
+        grads[pre + "weight"] = np.einsum("bl,bld->d", de[:, h, :], Yh[:, :, h, :]).reshape(1, dh)
+        grads[pre + "bias"] = de[:, h, :].sum().reshape(1)
+    dY = dY.reshape(B, L, H * dh)
+    for l, it in enumerate(cache["items"]):
+        pre, d = it["pre"], dY[:, l, :]
+        if "xhat" in it:
+            grads[pre + "bn1.weight"] = (d * it["xhat"]).sum(0)
+            grads[pre + "bn1.bias"] = d.sum(0)
+            gam = sd[pre + "bn1.weight"]
+            d = gam * it["invstd"] * (d - d.mean(0) - it["xhat"] * (d * it["xhat"]).mean(0))
+        if "a" in it:
+            dz = d * _act_grad(it["a"], cache["activation"])
+            grads[pre + "fc1.weight"] = dz.T @ it["x"]
+            grads[pre + "fc1.bias"] = dz.sum(0)
+    return grads
+
+
+def clip_and_step(sd: dict, grads: Mapping[str, np.ndarray], state: dict, optimizer="rmsprop", lr=1e-4, max_norm=2.0,
+                  alpha=0.99, betas=(0.9, 0.999), eps=None):
+    """clip_grad_norm_(params, max_norm) then torch.optim.RMSprop / Adam (model/model.py:824-827, :2021-2024, :996-998).
+    `state` carries the optimizer state between steps.  Returns the total gradient norm before clipping."""
+    total = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values())))
+    coef = min(1.0, max_norm / (total + 1e-6)) if max_norm and max_norm > 0 else 1.0
+    state["t"] = state.get("t", 0) + 1
+    t = state["t"]
+    for k, g in grads.items():
+        g = g.astype(np.float64).reshape(sd[k].shape) * coef
+        if optimizer == "rmsprop":
+            e = 1e-8 if eps is None else eps
+            sq = state.get(("sq", k), 0.0) * alpha + (1 - alpha) * g * g
+            state[("sq", k)] = sq
+            sd[k] = (sd[k] - lr * g / (np.sqrt(sq) + e)).astype(np.float32)
+        else:
+            e = 1e-8 if eps is None else eps
+            m = state.get(("m", k), 0.0) * betas[0] + (1 - betas[0]) * g
+            v = state.get(("v", k), 0.0) * betas[1] + (1 - betas[1]) * g * g
+            state[("m", k)], state[("v", k)] = m, v
+            denom = np.sqrt(v) / np.sqrt(1 - betas[1] ** t) + e
+            sd[k] = (sd[k] - lr / (1 - betas[0] ** t) * m / denom).astype(np.float32)
+    return total
+
+
+def laff_train_step(sd: dict, vis_in: Mapping[str, np.ndarray], txt_in: Mapping[str, np.ndarray], state: dict, heads: int,
+                    vis_no_transform: Sequence[str], optimizer="rmsprop", lr=1e-4, grad_clip=2.0, margin=0.2, adam_eps=1e-4):
+    """W2VVPP_MultiHeadAttention.forward(train_data) (model/model.py:964-1001 with :2021-2048): one step on the full
+    model state dict (keys 'vis_net.*' / 'txt_net.*'), dropout 0.  Returns (loss, clipped gradients, grad norm)."""
+    vfe = [(n, x) for n, x in vis_in.items()]
+    vpre = {n: "vis_net.VisMutiTransformNet.%s." % n for n in vis_in}
+    tfe = [(TXT_FEATURE_KEY[e], txt_in[TXT_FEATURE_KEY[e]]) for e in TXT_ENCODER_ORDER if TXT_FEATURE_KEY[e] in txt_in]
+    tpre = {TXT_FEATURE_KEY[e]: "txt_net.transform_layer.%s_transform." % e for e in TXT_ENCODER_ORDER}
+    t_emb, tc = fusion_train_forward(tfe, sd, tpre, "txt_net.attention_layer.", heads, ["clip"])
+    v_emb, vc = fusion_train_forward(vfe, sd, vpre, "vis_net.attention_layer.", heads, vis_no_transform)
+    loss, d_txt, d_vis = multi_head_loss(t_emb, v_emb, margin, True, "sum", "t2i", want_grad=True)
+    grads = {}
+    grads.update(fusion_train_backward(tc, d_txt, sd))
+    grads.update(fusion_train_backward(vc, d_vis, sd))
+    total = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values())))
+    coef = min(1.0, grad_clip / (total + 1e-6)) if grad_clip and grad_clip > 0 else 1.0
+    clipped = {k: (g * coef) for k, g in grads.items()}
+    clip_and_step(sd, grads, state, optimizer, lr, grad_clip, eps=(adam_eps if optimizer == "adam" else None))
+    return float(loss), clipped, total
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # text front-end (SURVEY §8f N2)
 # ----------------------------------------------------------------------------------------------------------------
 def tokenize(input_str: str, clean: bool = True, remove_stopword: bool = False, stopwords=()) -> list:

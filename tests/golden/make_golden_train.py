@@ -1,0 +1,75 @@
+"""Golden vectors for the training step from the UNMODIFIED reference: the 'LAFF' model
+(model.model.W2VVPP_MultiHeadAttention, configs.laff) in train mode, three calls of `model(train_data, epoch)` —
+forward, summed per-head MarginRankingLoss, backward, clip_grad_norm_(params, 2), RMSprop / Adam step.
+
+    python tests/golden/make_golden_train.py     # writes tests/golden/train_<case>.npz
+
+Dropout is set to 0 (torch's dropout mask cannot be reproduced outside torch); everything else is the shipped setting.
+Text encoders are the pass-through stand-ins of make_golden.py (their features are inputs at this tier).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden as mg  # noqa: E402
+from laff_b200 import synth  # noqa: E402
+
+SMALL = mg.SMALL
+
+
+def run_case(mm, tag, optimizer, lr, batch_norm, steps=3, B=16, D=256, H=8, seed=81):
+    import torch
+    dims = SMALL
+    vis_dims = {synth.VIS_CLIP_FT: dims["clip"], synth.VIS_TF: dims["tf"], synth.VIS_X3D: dims["x3d"], synth.VIS_IRCSN: dims["ircsn"]}
+    cfg = mg.make_config("laff", D, H, vis_dims, dims)
+    cfg.dropout = 0.0
+    cfg.batch_norm = batch_norm
+    cfg.optimizer, cfg.lr = optimizer, lr
+    torch.manual_seed(0)
+    model = mm.W2VVPP_MultiHeadAttention(cfg)
+    sd0 = mg.load_synth_state(model, seed)
+    model.train()
+    out = {"meta": np.array([B, D, H, steps, seed, int(batch_norm)]), "optimizer": np.array(optimizer), "lr": np.float64(lr),
+           "grad_clip": np.float64(cfg.grad_clip), "vis_names": np.array(list(vis_dims.keys()))}
+    for k, v in sd0.items():
+        out["sd0/" + k] = v
+    losses = []
+    for s in range(steps):
+        vis_in = {}
+        for name, d in vis_dims.items():
+            vis_in[name] = synth.feature(seed + s, "vis/" + name, B, d, "dense" if name == synth.VIS_CLIP_FT else "relu")
+        txt_in = {"gru": synth.feature(seed + s, "txt/gru", B, dims["gru"]), "bow": synth.feature(seed + s, "txt/bow", B, dims["bow"], "bow"),
+                  "w2v": synth.feature(seed + s, "txt/w2v", B, dims["w2v"]), "clip": synth.feature(seed + s, "txt/clip", B, dims["clip"])}
+        for k, v in vis_in.items():
+            out["step%d/vin/%s" % (s, k)] = v
+        for k, v in txt_in.items():
+            out["step%d/tin/%s" % (s, k)] = v
+        train_data = {"vis_feats": {k: torch.from_numpy(v) for k, v in vis_in.items()},
+                      "captions": {k: torch.from_numpy(v) for k, v in txt_in.items()},
+                      "captions_task2": None, "vis_frame_feat_dict": {}, "vis_origin_frame_tuple": None}
+        items = model(train_data, epoch=0)
+        losses.append(float(items["triplet_loss"]))
+        if s == 0:  # gradients of the first step (after clipping, as they sit in .grad)
+            for k, p in model.named_parameters():
+                if p.grad is not None:
+                    out["grad0/" + k] = p.grad.detach().numpy().copy()
+        for k, v in model.state_dict().items():
+            out["sd%d/%s" % (s + 1, k)] = v.detach().numpy().copy()
+    out["losses"] = np.array(losses)
+    print(tag, "losses", losses)
+    return out
+
+
+def main():
+    import torch
+    torch.set_num_threads(8)
+    mm, rloss, reval, ratt = mg.import_reference()
+    for tag, optimizer, lr, bn in (("rmsprop", "rmsprop", 1e-3, False), ("adam", "adam", 1e-3, False), ("rmsprop_bn", "rmsprop", 1e-3, True)):
+        np.savez_compressed(os.path.join(HERE, "train_%s.npz" % tag), **run_case(mm, tag, optimizer, lr, bn))
+
+
+if __name__ == "__main__":
+    main()
