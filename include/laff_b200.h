@@ -305,7 +305,8 @@ int laff_mrl_score_forward_backward(const float* score, int B, long long ld, flo
  *     GEMM entry points above (laff_project, laff_sim_dense); these are the stages around them.
  *
  * laff_transform_train_forward — TransformNet.forward in train mode after the activation (model/model.py:268-274):
- *     dropout (inverted, keep-probability 1 - p_drop, counter-based mask from `seed`, written to mask uint8 [B, D]) and
+ *     dropout (inverted, keep-probability 1 - p_drop, counter-based mask from `seed` (+ the device word *seed_dev when
+ *     given: a step counter that lets a captured CUDA graph draw a fresh mask per replay), written to mask uint8 [B, D]) and
  *     BatchNorm1d with batch statistics (biased variance normalises, unbiased updates running_var, momentum as torch).
  *     src fp32 [B, src_cols]: the activated projection (src_cols == D) or a raw "no-transform" feature tiled D / src_cols
  *     times (model/model.py:1822-1823).  save_mean / save_invstd [D] feed the backward.  running_* may be NULL.
@@ -313,7 +314,7 @@ int laff_mrl_score_forward_backward(const float* score, int B, long long ld, flo
  *     (a = activated projection saved by the forward), dgamma / dbeta / dbias [D].  For a tiled feature pass tiled_x
  *     instead of a (its input is a leaf: dz must be NULL).
  * laff_attention_pool_backward — backward of Multi_head_MyApply_Attention + Attention_1 (with_ave = mul = False):
- *     ys_dev / dys_dev: device arrays of n_features pointers to y_l / dy_l fp32 [rows, H*d_h] (pitches lds_dev);
+ *     ys / dys: HOST arrays of n_features device pointers to y_l / dy_l fp32 [rows, H*d_h] (pitches lds, host array);
  *     dw [H, d_h], dc [H]: gradients of the per-head logit weights / biases; dw_part [rows*H*d_h], dc_part [rows*H]
  *     scratch (per-row partials, reduced in a fixed order: deterministic).
  * laff_transpose_16 — fp32 [rows, cols] -> 16-bit [cols, pad8(rows) * terms] (terms 1: rounding; 3: 3-term split, side
@@ -322,7 +323,8 @@ int laff_mrl_score_forward_backward(const float* score, int B, long long ld, flo
  *     the gradients in place when grad_out == grad) followed by torch.optim.RMSprop (kind 0: alpha, eps) or Adam (kind 1:
  *     beta1, beta2, eps, bias correction at `step`), all tensors in one pass, no host synchronisation.  Tensors with
  *     grad == NULL are skipped like parameters without .grad.  blk_* come from laff_optimizer_blocks (host helper: call
- *     with NULL outputs for the count, then with buffers of that capacity). */
+ *     with NULL outputs for the count, then with buffers of that capacity).  step_dev / lr_dev (optional device words)
+ *     override `step` / `lr`, so a captured CUDA graph of the whole training step can be replayed. */
 typedef struct {
   float* param;
   const float* grad;
@@ -333,23 +335,25 @@ typedef struct {
 } laff_opt_tensor;
 
 int laff_transform_train_forward(const float* src, long long ld_src, int src_cols, int B, int D, float p_drop,
-                                 unsigned long long seed, const float* gamma, const float* beta, float* running_mean,
-                                 float* running_var, float momentum, float eps, int use_bn, float* y, long long ld_y,
-                                 uint8_t* mask, float* save_mean, float* save_invstd, void* stream);
+                                 unsigned long long seed, const unsigned long long* seed_dev, const float* gamma,
+                                 const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                 int use_bn, float* y, long long ld_y, uint8_t* mask, float* save_mean, float* save_invstd,
+                                 void* stream);
 int laff_transform_train_backward(const float* dy, long long ld_dy, const float* a, long long ld_a, const float* tiled_x,
                                   long long ld_x, int in_dim, const uint8_t* mask, float p_drop, int activation, int use_bn,
                                   const float* gamma, const float* save_mean, const float* save_invstd, int B, int D,
                                   float* dz, long long ld_dz, float* dgamma, float* dbeta, float* dbias, void* stream);
-int laff_attention_pool_backward(const float* const* ys_dev, const long long* lds_dev, int n_features, int heads,
-                                 int head_dim, const float* att_weight, const float* att_bias, const float* dout,
-                                 long long ld_dout, long long rows, float norm_eps, float* const* dys_dev, float* dw_part,
-                                 float* dc_part, float* dw, float* dc, void* stream);
+int laff_attention_pool_backward(const float* const* ys, const long long* lds, int n_features, int heads, int head_dim,
+                                 const float* att_weight, const float* att_bias, const float* dout, long long ld_dout,
+                                 long long rows, float norm_eps, float* const* dys, float* dw_part, float* dc_part, float* dw,
+                                 float* dc, void* stream);
 int laff_transpose_16(const float* x, long long ld, int rows, int cols, int dtype, int terms, int side, void* out16,
                       long long ld_out, void* stream);
 int laff_optimizer_blocks(const long long* sizes, int n_tensors, int* blk_tensor, long long* blk_start, int capacity);
 int laff_optimizer_step(const laff_opt_tensor* tensors_dev, const int* blk_tensor_dev, const long long* blk_start_dev,
                         int n_blocks, int kind, float lr, float alpha_or_beta1, float beta2, float eps, long long step,
-                        float max_grad_norm, double* partial_dev, double* total_norm_dev, void* stream);
+                        float max_grad_norm, double* partial_dev, double* total_norm_dev, const long long* step_dev,
+                        const float* lr_dev, void* stream);
 
 #ifdef __cplusplus
 }

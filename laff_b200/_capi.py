@@ -99,14 +99,14 @@ SIGNATURES = {
     "laff_rank_multi_gt": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _vp, _vp]),
     "laff_multi_gt_metrics": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "laff_rank_metrics": (_i, [_vp, _i, _vp, _vp]),
-    "laff_transform_train_forward": (_i, [_vp, _ll, _i, _i, _i, _f, _ull, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _ll, _vp, _vp,
-                                          _vp, _vp]),
+    "laff_transform_train_forward": (_i, [_vp, _ll, _i, _i, _i, _f, _ull, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _ll, _vp,
+                                          _vp, _vp, _vp]),
     "laff_transform_train_backward": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _vp, _f, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _ll,
                                            _vp, _vp, _vp, _vp]),
     "laff_attention_pool_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _ll, _ll, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "laff_transpose_16": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
     "laff_optimizer_blocks": (_i, [_vp, _i, _vp, _vp, _i]),
-    "laff_optimizer_step": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _ll, _f, _vp, _vp, _vp]),
+    "laff_optimizer_step": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _ll, _f, _vp, _vp, _vp, _vp, _vp]),
     "laff_bow_counts": (_i, [_vp, _vp, _i, _i, _vp, _ll, _vp]),
     "laff_gather_mean": (_i, [_vp, _ll, _ll, _vp, _vp, _i, _i, _vp, _ll, _vp]),
     "laff_gather_rows": (_i, [_vp, _ll, _ll, _vp, _ll, _i, _vp, _ll, _vp]),

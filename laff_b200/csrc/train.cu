@@ -33,62 +33,91 @@ __device__ __forceinline__ float act_grad_from_output(float a, int act) {
   }
 }
 
-// One thread per output column.  src is either the activated projection a [B, D] (src_cols == D) or a raw
-// "no-transform" feature [B, in_dim] tiled over the heads (src_cols == in_dim, model/model.py:1822-1823).
-__global__ void transform_train_fwd_kernel(const float* __restrict__ src, long long ld_src, int src_cols, int B, int D,
-                                           float p_drop, unsigned long long seed, const float* __restrict__ gamma,
-                                           const float* __restrict__ beta, float* __restrict__ running_mean,
-                                           float* __restrict__ running_var, float momentum, float eps, int use_bn,
-                                           float* __restrict__ y, long long ld_y, uint8_t* __restrict__ mask,
-                                           float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
-  const int sc = c % src_cols;
+// Column statistics need every row of a column; rows are the short dimension (B = 128 in the shipped configs), so a
+// block owns 32 columns and its 32 x kRowLanes threads stride over the rows: coalesced 128-byte row segments, then a
+// shared-memory tree over the row lanes.  Sums are kept in double: the batch statistics feed rsqrt and differences.
+constexpr int kRowLanes = 16;
+
+__device__ __forceinline__ double col_reduce(double v, double (*sh)[33]) {
+  __syncthreads();  // previous use of sh is over
+  sh[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  for (int o = kRowLanes / 2; o > 0; o >>= 1) {
+    if (threadIdx.y < o) sh[threadIdx.y][threadIdx.x] += sh[threadIdx.y + o][threadIdx.x];
+    __syncthreads();
+  }
+  return sh[0][threadIdx.x];
+}
+
+// src is either the activated projection a [B, D] (src_cols == D) or a raw "no-transform" feature [B, in_dim] tiled over
+// the heads (src_cols == in_dim, model/model.py:1822-1823).
+__global__ void __launch_bounds__(32 * kRowLanes)
+    transform_train_fwd_kernel(const float* __restrict__ src, long long ld_src, int src_cols, int B, int D, float p_drop,
+                               unsigned long long seed_base, const unsigned long long* __restrict__ seed_dev,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
+                               int use_bn, float* __restrict__ y, long long ld_y, uint8_t* __restrict__ mask,
+                               float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  __shared__ double sh[kRowLanes][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < D;
+  const int sc = ok ? c % src_cols : 0;
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  // seed_dev: a step counter kept on the device, so that a captured CUDA graph draws a fresh mask on every replay
+  const unsigned long long seed = seed_base + (seed_dev ? *seed_dev * 0x632BE59BD9B4E019ull : 0ull);
   double sum = 0.0;
-  for (int r = 0; r < B; ++r) {
-    float v = src[r * ld_src + sc];
-    if (p_drop > 0.f) {
-      const bool keep = uniform01(seed, static_cast<unsigned long long>(r) * D + c) >= p_drop;
-      mask[static_cast<long long>(r) * D + c] = keep ? 1 : 0;
-      v = keep ? v * keep_scale : 0.f;
+  if (ok) {
+    for (int r = threadIdx.y; r < B; r += kRowLanes) {
+      float v = src[r * ld_src + sc];
+      if (p_drop > 0.f) {
+        const bool keep = uniform01(seed, static_cast<unsigned long long>(r) * D + c) >= p_drop;
+        mask[static_cast<long long>(r) * D + c] = keep ? 1 : 0;
+        v = keep ? v * keep_scale : 0.f;
+      }
+      y[r * ld_y + c] = v;
+      sum += v;
     }
-    y[r * ld_y + c] = v;
-    sum += v;
   }
   if (!use_bn) return;
-  const double mean = sum / B;
+  const double mean = col_reduce(sum, sh) / B;
   double ss = 0.0;
-  for (int r = 0; r < B; ++r) {
-    const double d = static_cast<double>(y[r * ld_y + c]) - mean;
-    ss += d * d;
+  if (ok) {
+    for (int r = threadIdx.y; r < B; r += kRowLanes) {
+      const double d = static_cast<double>(y[r * ld_y + c]) - mean;
+      ss += d * d;
+    }
   }
+  ss = col_reduce(ss, sh);
+  if (!ok) return;
   const double var = ss / B;  // biased: what normalises the batch
   const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
   const float meanf = static_cast<float>(mean);
-  for (int r = 0; r < B; ++r) y[r * ld_y + c] = (y[r * ld_y + c] - meanf) * invstd * g + b;
-  save_mean[c] = meanf;
-  save_invstd[c] = invstd;
-  if (running_mean) {
-    const double unbiased = B > 1 ? ss / (B - 1) : var;
-    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * meanf;
-    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  for (int r = threadIdx.y; r < B; r += kRowLanes) y[r * ld_y + c] = (y[r * ld_y + c] - meanf) * invstd * g + b;
+  if (threadIdx.y == 0) {
+    save_mean[c] = meanf;
+    save_invstd[c] = invstd;
+    if (running_mean) {
+      const double unbiased = B > 1 ? ss / (B - 1) : var;
+      running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * meanf;
+      running_var[c] = (1.0f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    }
   }
 }
 
-// Backward of the stage above (one thread per column): dy -> dz (gradient at the GEMM output, before the activation),
-// d gamma, d beta, d bias (= column sum of dz).  `a` is the activated projection saved by the forward (NULL for a tiled
-// feature, whose input is a leaf: only the BatchNorm parameters get gradients).
-__global__ void transform_train_bwd_kernel(const float* __restrict__ dy, long long ld_dy, const float* __restrict__ a,
-                                           long long ld_a, const float* __restrict__ tiled_x, long long ld_x, int in_dim,
-                                           const uint8_t* __restrict__ mask, float p_drop, int act, int use_bn,
-                                           const float* __restrict__ gamma, const float* __restrict__ save_mean,
-                                           const float* __restrict__ save_invstd, int B, int D, float* __restrict__ dz,
-                                           long long ld_dz, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                           float* __restrict__ dbias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
+// Backward of the stage above: dy -> dz (gradient at the GEMM output, before the activation), d gamma, d beta, d bias
+// (= column sum of dz).  `a` is the activated projection saved by the forward (NULL for a tiled feature, whose input is a
+// leaf: only the BatchNorm parameters get gradients).
+__global__ void __launch_bounds__(32 * kRowLanes)
+    transform_train_bwd_kernel(const float* __restrict__ dy, long long ld_dy, const float* __restrict__ a, long long ld_a,
+                               const float* __restrict__ tiled_x, long long ld_x, int in_dim, const uint8_t* __restrict__ mask,
+                               float p_drop, int act, int use_bn, const float* __restrict__ gamma,
+                               const float* __restrict__ save_mean, const float* __restrict__ save_invstd, int B, int D,
+                               float* __restrict__ dz, long long ld_dz, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                               float* __restrict__ dbias) {
+  __shared__ double sh[kRowLanes][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < D;
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   auto dropped = [&](int r) -> float {  // value that entered BatchNorm
     float v = a ? a[r * ld_a + c] : tiled_x[r * ld_x + (c % in_dim)];
@@ -98,41 +127,58 @@ __global__ void transform_train_bwd_kernel(const float* __restrict__ dy, long lo
   float g = 1.f, mean = 0.f, invstd = 1.f;
   double sb = 0.0, sg = 0.0;
   if (use_bn) {
-    g = gamma ? gamma[c] : 1.0f;
-    mean = save_mean[c];
-    invstd = save_invstd[c];
-    for (int r = 0; r < B; ++r) {
-      const float d = dy[r * ld_dy + c];
-      sb += d;
-      sg += static_cast<double>(d) * ((dropped(r) - mean) * invstd);
+    if (ok) {
+      g = gamma ? gamma[c] : 1.0f;
+      mean = save_mean[c];
+      invstd = save_invstd[c];
+      for (int r = threadIdx.y; r < B; r += kRowLanes) {
+        const float d = dy[r * ld_dy + c];
+        sb += d;
+        sg += static_cast<double>(d) * ((dropped(r) - mean) * invstd);
+      }
     }
-    if (dgamma) dgamma[c] = static_cast<float>(sg);
-    if (dbeta) dbeta[c] = static_cast<float>(sb);
+    sb = col_reduce(sb, sh);
+    sg = col_reduce(sg, sh);
+    if (ok && threadIdx.y == 0) {
+      if (dgamma) dgamma[c] = static_cast<float>(sg);
+      if (dbeta) dbeta[c] = static_cast<float>(sb);
+    }
   }
   if (!dz) return;
   const float mb = static_cast<float>(sb / B), mg = static_cast<float>(sg / B);
   double sbias = 0.0;
-  for (int r = 0; r < B; ++r) {
-    float d = dy[r * ld_dy + c];
-    if (use_bn) d = g * invstd * (d - mb - ((dropped(r) - mean) * invstd) * mg);
-    if (p_drop > 0.f) d = mask[static_cast<long long>(r) * D + c] ? d * keep_scale : 0.f;
-    d *= act_grad_from_output(a[r * ld_a + c], act);
-    dz[r * ld_dz + c] = d;
-    sbias += d;
+  if (ok) {
+    for (int r = threadIdx.y; r < B; r += kRowLanes) {
+      float d = dy[r * ld_dy + c];
+      if (use_bn) d = g * invstd * (d - mb - ((dropped(r) - mean) * invstd) * mg);
+      if (p_drop > 0.f) d = mask[static_cast<long long>(r) * D + c] ? d * keep_scale : 0.f;
+      d *= act_grad_from_output(a[r * ld_a + c], act);
+      dz[r * ld_dz + c] = d;
+      sbias += d;
+    }
   }
-  if (dbias) dbias[c] = static_cast<float>(sbias);
+  sbias = col_reduce(sbias, sh);
+  if (ok && threadIdx.y == 0 && dbias) dbias[c] = static_cast<float>(sbias);
 }
 
 // Backward of the LAFF block (Attention_1 without the mean residual / product variants, the shipped setting):
 //   e_l = w_h . y_l + c_h,  p = softmax_l(e),  g = sum_l p_l y_l,  out = g / (|g| + eps)
 // One warp per (row, head); lanes own d_h / 32 columns.  dW / dc are written per (row, head) and reduced afterwards
 // (deterministic).
+struct PoolBwdArgs {  // passed by value: nothing to upload, and a captured graph keeps its own copy
+  const float* ys[LAFF_MAX_FEATURES];
+  float* dys[LAFF_MAX_FEATURES];
+  long long lds[LAFF_MAX_FEATURES];
+};
+
 template <int VPL, int LMAX>
-__global__ void __launch_bounds__(128) pool_train_bwd_kernel(const float* const* __restrict__ ys, const long long* __restrict__ lds,
-                                                             int L, const float* __restrict__ att_w, const float* __restrict__ att_b,
+__global__ void __launch_bounds__(128) pool_train_bwd_kernel(const __grid_constant__ PoolBwdArgs args, int L,
+                                                             const float* __restrict__ att_w, const float* __restrict__ att_b,
                                                              const float* __restrict__ dout, long long ld_dout, long long rows, int heads,
-                                                             float norm_eps, float* const* __restrict__ dys, float* __restrict__ dw_part,
-                                                             float* __restrict__ dc_part) {
+                                                             float norm_eps, float* __restrict__ dw_part, float* __restrict__ dc_part) {
+  const float* const* ys = args.ys;
+  float* const* dys = args.dys;
+  const long long* lds = args.lds;
   const int lane = threadIdx.x & 31;
   const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= rows * heads) return;
@@ -270,20 +316,23 @@ __global__ void transpose16_kernel(const float* __restrict__ x, long long ld, in
 // ---- optimizer -------------------------------------------------------------------------------------------------------
 constexpr int kOptChunk = 256 * 8;  // elements one block of the optimizer kernels walks
 
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const laff_opt_tensor* __restrict__ ts, const int* __restrict__ blk_tensor,
                                                           const long long* __restrict__ blk_start, double* __restrict__ partial) {
   const laff_opt_tensor t = ts[blk_tensor[blockIdx.x]];
   const long long s = blk_start[blockIdx.x];
-  double acc = 0.0;
+  float part = 0.f;  // 8 squares per thread in fp32, everything above that in fp64
   if (t.grad) {
-    for (int i = threadIdx.x; i < kOptChunk; i += 256) {
-      const long long j = s + i;
-      if (j < t.n) {
-        const double g = t.grad[j];
-        acc += g * g;
-      }
+    const long long j0 = s + threadIdx.x * 8;
+    if (aligned16(t.grad) && j0 + 8 <= t.n) {
+      const float4 a = *reinterpret_cast<const float4*>(t.grad + j0), b = *reinterpret_cast<const float4*>(t.grad + j0 + 4);
+      part = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+    } else {
+      for (long long j = j0; j < j0 + 8 && j < t.n; ++j) part = fmaf(t.grad[j], t.grad[j], part);
     }
   }
+  const double acc = part;
   __shared__ double sh[256];
   sh[threadIdx.x] = acc;
   __syncthreads();
@@ -313,31 +362,63 @@ __global__ void sqnorm_final_kernel(const double* __restrict__ partial, int n, d
 __global__ void __launch_bounds__(256) opt_step_kernel(const laff_opt_tensor* __restrict__ ts, const int* __restrict__ blk_tensor,
                                                        const long long* __restrict__ blk_start, const double* __restrict__ total_norm,
                                                        float max_norm, int kind, float lr, float alpha_or_beta1, float beta2, float eps,
-                                                       float bias_c1, float bias_c2) {
+                                                       float bias_c1, float bias_c2, const long long* __restrict__ step_dev,
+                                                       const float* __restrict__ lr_dev) {
   const laff_opt_tensor t = ts[blk_tensor[blockIdx.x]];
   if (!t.grad) return;
+  if (lr_dev) lr = *lr_dev;
+  if (step_dev && kind == 1) {  // graph replays: the step count lives on the device
+    const double st = static_cast<double>(*step_dev);
+    bias_c1 = static_cast<float>(1.0 - pow(static_cast<double>(alpha_or_beta1), st));
+    bias_c2 = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), st)));
+  }
   const long long s = blk_start[blockIdx.x];
   float coef = 1.0f;
   if (max_norm > 0.f) {
     const float c = static_cast<float>(static_cast<double>(max_norm) / (*total_norm + 1e-6));
     coef = c < 1.0f ? c : 1.0f;
   }
-  for (int i = threadIdx.x; i < kOptChunk; i += 256) {
-    const long long j = s + i;
-    if (j >= t.n) break;
-    const float g = t.grad[j] * coef;
-    if (t.grad_out) t.grad_out[j] = g;
+  auto update = [&](float gr, float& p, float& s1, float& s2) -> float {
+    const float g = gr * coef;
     if (kind == 0) {
-      const float sq = alpha_or_beta1 * t.state1[j] + (1.0f - alpha_or_beta1) * g * g;
-      t.state1[j] = sq;
-      t.param[j] -= lr * (g / (sqrtf(sq) + eps));
+      s1 = alpha_or_beta1 * s1 + (1.0f - alpha_or_beta1) * g * g;
+      p -= lr * (g / (sqrtf(s1) + eps));
     } else {
-      const float m = alpha_or_beta1 * t.state1[j] + (1.0f - alpha_or_beta1) * g;
-      const float v = beta2 * t.state2[j] + (1.0f - beta2) * g * g;
-      t.state1[j] = m;
-      t.state2[j] = v;
-      const float denom = sqrtf(v) / bias_c2 + eps;  // bias_c2 = sqrt(1 - beta2^t)
-      t.param[j] -= (lr / bias_c1) * (m / denom);    // bias_c1 = 1 - beta1^t
+      s1 = alpha_or_beta1 * s1 + (1.0f - alpha_or_beta1) * g;
+      s2 = beta2 * s2 + (1.0f - beta2) * g * g;
+      const float denom = sqrtf(s2) / bias_c2 + eps;  // bias_c2 = sqrt(1 - beta2^t)
+      p -= (lr / bias_c1) * (s1 / denom);             // bias_c1 = 1 - beta1^t
+    }
+    return g;
+  };
+  const long long j0 = s + threadIdx.x * 8;  // 8 consecutive elements per thread: two 16-byte accesses per array
+  const bool vec = j0 + 8 <= t.n && aligned16(t.param) && aligned16(t.grad) && aligned16(t.state1) &&
+                   (kind == 0 || aligned16(t.state2)) && (!t.grad_out || aligned16(t.grad_out));
+  if (vec) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long j = j0 + 4 * h;
+      float4 g = *reinterpret_cast<const float4*>(t.grad + j);
+      float4 p = *reinterpret_cast<float4*>(t.param + j);
+      float4 a = *reinterpret_cast<float4*>(t.state1 + j);
+      float4 b = kind == 1 ? *reinterpret_cast<float4*>(t.state2 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g.x = update(g.x, p.x, a.x, b.x);
+      g.y = update(g.y, p.y, a.y, b.y);
+      g.z = update(g.z, p.z, a.z, b.z);
+      g.w = update(g.w, p.w, a.w, b.w);
+      *reinterpret_cast<float4*>(t.param + j) = p;
+      *reinterpret_cast<float4*>(t.state1 + j) = a;
+      if (kind == 1) *reinterpret_cast<float4*>(t.state2 + j) = b;
+      if (t.grad_out) *reinterpret_cast<float4*>(t.grad_out + j) = g;
+    }
+  } else {
+    for (long long j = j0; j < j0 + 8 && j < t.n; ++j) {
+      float p = t.param[j], a = t.state1[j], b = kind == 1 ? t.state2[j] : 0.f;
+      const float g = update(t.grad[j], p, a, b);
+      t.param[j] = p;
+      t.state1[j] = a;
+      if (kind == 1) t.state2[j] = b;
+      if (t.grad_out) t.grad_out[j] = g;
     }
   }
 }
@@ -347,9 +428,10 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const laff_opt_tensor* __
 using namespace laff;
 
 extern "C" int laff_transform_train_forward(const float* src, long long ld_src, int src_cols, int B, int D, float p_drop,
-                                            unsigned long long seed, const float* gamma, const float* beta, float* running_mean,
-                                            float* running_var, float momentum, float eps, int use_bn, float* y, long long ld_y,
-                                            uint8_t* mask, float* save_mean, float* save_invstd, void* stream) {
+                                            unsigned long long seed, const unsigned long long* seed_dev, const float* gamma,
+                                            const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                            int use_bn, float* y, long long ld_y, uint8_t* mask, float* save_mean,
+                                            float* save_invstd, void* stream) {
   LAFF_REQUIRE(src && y && B > 0 && D > 0 && src_cols > 0 && src_cols <= D && D % src_cols == 0 && ld_src >= src_cols && ld_y >= D,
                LAFF_EINVAL, "laff_transform_train_forward: bad arguments");
   LAFF_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || mask), LAFF_EINVAL,
@@ -361,9 +443,9 @@ extern "C" int laff_transform_train_forward(const float* src, long long ld_src, 
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
-  transform_train_fwd_kernel<<<(D + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, ld_src, src_cols, B, D, p_drop, seed, gamma, beta, running_mean, running_var, momentum, eps, use_bn, y, ld_y, mask,
-      save_mean, save_invstd);
+  transform_train_fwd_kernel<<<(D + 31) / 32, dim3(32, kRowLanes), 0, static_cast<cudaStream_t>(stream)>>>(
+      src, ld_src, src_cols, B, D, p_drop, seed, seed_dev, gamma, beta, running_mean, running_var, momentum, eps, use_bn, y, ld_y,
+      mask, save_mean, save_invstd);
   count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
@@ -386,7 +468,7 @@ extern "C" int laff_transform_train_backward(const float* dy, long long ld_dy, c
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
-  transform_train_bwd_kernel<<<(D + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  transform_train_bwd_kernel<<<(D + 31) / 32, dim3(32, kRowLanes), 0, static_cast<cudaStream_t>(stream)>>>(
       dy, ld_dy, a, ld_a, tiled_x, ld_x, in_dim, mask, p_drop, activation, use_bn, gamma, save_mean, save_invstd, B, D, dz, ld_dz,
       dgamma, dbeta, dbias);
   count_launch();
@@ -394,11 +476,11 @@ extern "C" int laff_transform_train_backward(const float* dy, long long ld_dy, c
   return LAFF_OK;
 }
 
-extern "C" int laff_attention_pool_backward(const float* const* ys_dev, const long long* lds_dev, int n_features, int heads,
+extern "C" int laff_attention_pool_backward(const float* const* ys, const long long* lds, int n_features, int heads,
                                             int head_dim, const float* att_weight, const float* att_bias, const float* dout,
-                                            long long ld_dout, long long rows, float norm_eps, float* const* dys_dev, float* dw_part,
+                                            long long ld_dout, long long rows, float norm_eps, float* const* dys, float* dw_part,
                                             float* dc_part, float* dw, float* dc, void* stream) {
-  LAFF_REQUIRE(ys_dev && lds_dev && dys_dev && att_weight && att_bias && dout && dw_part && dc_part && dw && dc && rows > 0,
+  LAFF_REQUIRE(ys && lds && dys && att_weight && att_bias && dout && dw_part && dc_part && dw && dc && rows > 0,
                LAFF_EINVAL, "laff_attention_pool_backward: bad arguments");
   LAFF_REQUIRE(n_features >= 1 && n_features <= LAFF_MAX_FEATURES && heads > 0 && ld_dout >= static_cast<long long>(heads) * head_dim,
                LAFF_EINVAL, "laff_attention_pool_backward: bad shape");
@@ -406,11 +488,19 @@ extern "C" int laff_attention_pool_backward(const float* const* ys_dev, const lo
   int rc = get_device_info(&di);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PoolBwdArgs args = {};
+  const long long D = static_cast<long long>(heads) * head_dim;
+  for (int l = 0; l < n_features; ++l) {
+    LAFF_REQUIRE(ys[l] && dys[l] && lds[l] >= D, LAFF_EINVAL, "laff_attention_pool_backward: feature %d: bad pointer / pitch", l);
+    args.ys[l] = ys[l];
+    args.dys[l] = dys[l];
+    args.lds[l] = lds[l];
+  }
   const long long warps = rows * heads;
   const unsigned blocks = static_cast<unsigned>((warps + 3) / 4);
-#define LAFF_POOL_BWD(VPL)                                                                                                  \
-  pool_train_bwd_kernel<VPL, LAFF_MAX_FEATURES><<<blocks, 128, 0, st>>>(ys_dev, lds_dev, n_features, att_weight, att_bias, dout, \
-                                                                         ld_dout, rows, heads, norm_eps, dys_dev, dw_part, dc_part)
+#define LAFF_POOL_BWD(VPL)                                                                                                       \
+  pool_train_bwd_kernel<VPL, LAFF_MAX_FEATURES><<<blocks, 128, 0, st>>>(args, n_features, att_weight, att_bias, dout, ld_dout, rows, \
+                                                                         heads, norm_eps, dw_part, dc_part)
   switch (head_dim) {
     case 32: LAFF_POOL_BWD(1); break;
     case 64: LAFF_POOL_BWD(2); break;
@@ -470,7 +560,8 @@ extern "C" int laff_optimizer_blocks(const long long* sizes, int n_tensors, int*
 
 extern "C" int laff_optimizer_step(const laff_opt_tensor* tensors_dev, const int* blk_tensor_dev, const long long* blk_start_dev,
                                    int n_blocks, int kind, float lr, float alpha_or_beta1, float beta2, float eps, long long step,
-                                   float max_grad_norm, double* partial_dev, double* total_norm_dev, void* stream) {
+                                   float max_grad_norm, double* partial_dev, double* total_norm_dev, const long long* step_dev,
+                                   const float* lr_dev, void* stream) {
   LAFF_REQUIRE(tensors_dev && blk_tensor_dev && blk_start_dev && partial_dev && total_norm_dev && n_blocks >= 0 &&
                    (kind == 0 || kind == 1) && step >= 1,
                LAFF_EINVAL, "laff_optimizer_step: bad arguments");
@@ -487,7 +578,7 @@ extern "C" int laff_optimizer_step(const laff_opt_tensor* tensors_dev, const int
     c2 = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step))));
   }
   opt_step_kernel<<<n_blocks, 256, 0, st>>>(tensors_dev, blk_tensor_dev, blk_start_dev, total_norm_dev, max_grad_norm, kind, lr,
-                                            alpha_or_beta1, beta2, eps, c1, c2);
+                                            alpha_or_beta1, beta2, eps, c1, c2, step_dev, lr_dev);
   count_launch(3);
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;

@@ -666,22 +666,38 @@ class W2VVPP(nn.Module):
         raise Exception("vis_embs dims are not equal to txt_embs dims")
 
     # ---------------------------------------------------------------- training step (model/model.py:964-1001)
-    def _train_features(self, net, inputs, dev):
-        """(x on the device, TransformNet) pairs of one fusion net, in the reference's feature order."""
-        if net is self.txt_net:
-            mods = dict(net.transform_layer.named_children())
-            return [(net._feature(inputs, n).to(dev, non_blocking=True).float(), mods[n + "_transform"])
-                    for n in net.encoder_name_list], net.attention_layer
-        if not isinstance(net, VisMutiTransformNetAddAttnetion):
+    def _stage_train_inputs(self, train_data, dev):
+        """Device fp32 tensors of one batch: ({text encoder name: feature}, {video feature name: feature}).  String
+        front-ends (BoW / word2vec) run here, before anything that a CUDA graph captures."""
+        if not isinstance(self.vis_net, VisMutiTransformNetAddAttnetion):
             raise NotImplementedError("training LAFF-ml (frame-level attention backward) is not built yet; 'LAFF' trains")
-        mods = dict(net.VisMutiTransformNet.named_children())
-        feats = []
-        for name in net.vis_net_space_dict.keys():
-            x = inputs[name].to(dev, non_blocking=True).float()
-            if not bool((x != 0).any()):  # train-mode quirk of the reference: an all-zero feature becomes noise
-                x = torch.randn_like(x)    # (model/model.py:1819-1821)
-            feats.append((x, mods[name]))
-        return feats, net.attention_layer
+        txt = {n: self.txt_net._feature(train_data["captions"], n).to(dev, non_blocking=True).float()
+               for n in self.txt_net.encoder_name_list}
+        vis = {n: train_data["vis_feats"][n].to(dev, non_blocking=True).float() for n in self.vis_net.vis_net_space_dict.keys()}
+        return txt, vis
+
+    def _train_step_device(self, txt, vis, precision):
+        """forward (train mode) -> loss -> backward -> clip + optimizer step, all on the current stream, no host sync."""
+        from .train import FusionTrainStep
+        self._seed_dev.add_(1)
+        tmods = dict(self.txt_net.transform_layer.named_children())
+        vmods = dict(self.vis_net.VisMutiTransformNet.named_children())
+        tfeats = [(txt[n], tmods[n + "_transform"]) for n in self.txt_net.encoder_name_list]
+        # train-mode quirk of the reference: an all-zero video feature becomes noise (model/model.py:1819-1821).  Selected
+        # on the device: the reference's `torch.nonzero(...)` costs a host synchronisation per feature per step.
+        vfeats = [(torch.where((x != 0).any(), x, torch.randn_like(x)), vmods[n]) for n, x in vis.items()]
+        outs = {}
+        for key, feats, att in (("txt", tfeats, self.txt_net.attention_layer), ("vis", vfeats, self.vis_net.attention_layer)):
+            step = self._steps.get(key)
+            if step is None or step.att is not att or step.precision != precision:
+                step = self._steps[key] = FusionTrainStep(att, precision)
+            outs[key] = step.forward(feats, self._seed_base * 2 + (key == "vis"), self._seed_dev)
+        c = self.criterion
+        loss, d_txt, d_vis = ops.mrl_forward_backward(outs["txt"], outs["vis"], c.margin, c.max_violation, c.direction, c.cost_style)
+        self._steps["txt"].backward(d_txt)
+        self._steps["vis"].backward(d_vis)
+        self.last_grad_norm = self.optimizer.step()
+        return loss
 
     def _make_optimizer(self):
         from .train import DeviceOptimizer
@@ -692,12 +708,14 @@ class W2VVPP(nn.Module):
                                max_grad_norm=self.grad_clip if self.grad_clip and self.grad_clip > 0 else 0.0)
 
     _adam_eps = 1e-8  # torch default (model/model.py:824); the LAFF class overrides it with 1e-4 (model/model.py:2022)
+    use_cuda_graph = True   # replay the whole step as one CUDA graph from the 4th step on (launch-bound at B = 128)
+    train_precision = "bf16x3"
 
     def forward(self, train_data, epoch=None):
         """One training step (model/model.py:964-1001): forward of both nets in train mode, summed per-head
         MarginRankingLoss, backward, clip_grad_norm_(params, grad_clip), optimizer step.  Returns loss_items.
-        Everything runs through the C ABI (laff_b200/train.py); no autograd graph is built."""
-        from .train import FusionTrainStep
+        Everything runs through the C ABI (laff_b200/train.py); no autograd graph is built.  After three eager steps
+        the step is captured once into a CUDA graph and replayed (same shapes): ~100 launches become one."""
         global _PARAM_EPOCH
         opt = self.opt
         if getattr(opt, "negative", False):
@@ -710,29 +728,43 @@ class W2VVPP(nn.Module):
             raise ops.LaffError("model(train_data) is a training step: call model.train() first")
         self.iters += 1
         dev = _cuda_device(next(self.parameters()).device)
-        precision = getattr(self, "train_precision", "bf16x3")
+        precision = self.train_precision
         if getattr(self, "optimizer", None) is None:
             self.optimizer = self._make_optimizer()
             self._steps = {}
-        seed = (int(getattr(opt, "seed", 0) or 0) << 20) + self.iters
-        outs = {}
-        for key, net, inputs in (("txt", self.txt_net, train_data["captions"]), ("vis", self.vis_net, train_data["vis_feats"])):
-            feats, att = self._train_features(net, inputs, dev)
-            step = self._steps.get(key)
-            if step is None or step.att is not att or step.precision != precision:
-                step = self._steps[key] = FusionTrainStep(att, precision)
-            outs[key] = step.forward(feats, seed * 2 + (key == "vis"))
-        c = self.criterion
-        loss, d_txt, d_vis = ops.mrl_forward_backward(outs["txt"], outs["vis"], c.margin, c.max_violation, c.direction, c.cost_style)
-        self._steps["txt"].backward(d_txt)
-        self._steps["vis"].backward(d_vis)
-        self.last_grad_norm = self.optimizer.step()
+            self._seed_base = int(getattr(opt, "seed", 0) or 0) << 20
+            self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._graph = None
+        txt, vis = self._stage_train_inputs(train_data, dev)
+        sig = (precision,) + tuple((k, tuple(v.shape)) for k, v in list(txt.items()) + list(vis.items()))
+        g = self._graph
+        if g is not None and g["sig"] == sig:
+            self.optimizer.sync_lr()
+            for k, v in txt.items():
+                g["txt"][k].copy_(v, non_blocking=True)
+            for k, v in vis.items():
+                g["vis"][k].copy_(v, non_blocking=True)
+            g["graph"].replay()
+            loss = g["loss"].clone()
+        else:
+            loss = self._train_step_device(txt, vis, precision)
+            if self.use_cuda_graph and self.iters >= 3:
+                self._graph = self._capture_train_graph(txt, vis, precision, sig)
         _PARAM_EPOCH += 1  # parameters changed behind torch's version counters: drop the eval-mode operand caches
         return {"triplet_loss": loss}
 
-    # ---------------------------------------------------------------- predict (model/model.py:1018-1079)
-    def _encode_vis(self, output_dict, out16_dtype=None):
-        return self.vis_net.encode(output_dict["vis_feat_dict"], out16_dtype)
+    def _capture_train_graph(self, txt, vis, precision, sig):
+        st_txt = {k: v.clone() for k, v in txt.items()}
+        st_vis = {k: v.clone() for k, v in vis.items()}
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph):
+            loss = self._train_step_device(st_txt, st_vis, precision)
+        return {"graph": graph, "txt": st_txt, "vis": st_vis, "loss": loss, "sig": sig}
+
+    def train(self, mode: bool = True):
+        self._graph = None  # BatchNorm / dropout behaviour is baked into a captured step
+        return super().train(mode)
 
     def predict(self, txt_loader, vis_loader, measure, record_emb=False):
         """Dense score matrix for small galleries; same return contract as the reference:

@@ -542,7 +542,8 @@ def mrl_score_forward_backward(score: torch.Tensor, margin: float, max_violation
 # ----------------------------------------------------------------------------------------------------------------
 # training step (T1 / N4)
 # ----------------------------------------------------------------------------------------------------------------
-def transform_train_forward(src: torch.Tensor, D: int, p_drop: float, seed: int, bn=None, momentum: float = 0.1):
+def transform_train_forward(src: torch.Tensor, D: int, p_drop: float, seed: int, bn=None, momentum: float = 0.1,
+                            seed_dev: Optional[torch.Tensor] = None):
     """Dropout + train-mode BatchNorm1d after the activation (laff_transform_train_forward).
     src fp32 [B, D] (activated projection) or [B, in_dim] (raw feature tiled D / in_dim times).
     bn: None or an nn.BatchNorm1d whose running statistics are updated in place.
@@ -562,7 +563,7 @@ def transform_train_forward(src: torch.Tensor, D: int, p_drop: float, seed: int,
         gamma, beta, rm, rv, eps = bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps
         momentum = bn.momentum if bn.momentum is not None else momentum
     _capi.call("laff_transform_train_forward", _ptr(src), src.stride(0), src.shape[1], B, D, float(p_drop),
-               int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), float(momentum), float(eps),
+               int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev), _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), float(momentum), float(eps),
                int(bn is not None), _ptr(y), y.stride(0), _ptr(mask), _ptr(sm), _ptr(si), _stream(src))
     return y, mask, sm, si
 
@@ -591,14 +592,15 @@ def attention_pool_backward(ys: Sequence[torch.Tensor], att_weight: torch.Tensor
     dev = dout.device
     ys = [_rowmajor(y) for y in ys]
     dys = [torch.empty((rows, D), dtype=torch.float32, device=dev) for _ in ys]
-    yp = torch.tensor([y.data_ptr() for y in ys], dtype=torch.int64).to(dev)
-    dp = torch.tensor([d.data_ptr() for d in dys], dtype=torch.int64).to(dev)
-    lds = torch.tensor([y.stride(0) for y in ys], dtype=torch.int64).to(dev)
+    n = len(ys)
+    yp = (C.c_void_p * n)(*[y.data_ptr() for y in ys])          # host arrays: the entry point copies them into the
+    dp = (C.c_void_p * n)(*[d.data_ptr() for d in dys])         # kernel's by-value argument block
+    lds = (C.c_longlong * n)(*[y.stride(0) for y in ys])
     dw_part = torch.empty(rows * D, dtype=torch.float32, device=dev)
     dc_part = torch.empty(rows * heads, dtype=torch.float32, device=dev)
     dout = _rowmajor(dout)
-    _capi.call("laff_attention_pool_backward", _ptr(yp), _ptr(lds), len(ys), heads, head_dim, _ptr(att_weight), _ptr(att_bias),
-               _ptr(dout), dout.stride(0), rows, float(norm_eps), _ptr(dp), _ptr(dw_part), _ptr(dc_part), _ptr(dw), _ptr(dc),
+    _capi.call("laff_attention_pool_backward", yp, lds, n, heads, head_dim, _ptr(att_weight), _ptr(att_bias),
+               _ptr(dout), dout.stride(0), rows, float(norm_eps), dp, _ptr(dw_part), _ptr(dc_part), _ptr(dw), _ptr(dc),
                _stream(dout))
     return dys
 

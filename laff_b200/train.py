@@ -51,7 +51,9 @@ class FusionTrainStep:
         self.precision = precision
         self.cache: Optional[dict] = None
 
-    def forward(self, features: Sequence, seed: int) -> torch.Tensor:
+    def forward(self, features: Sequence, seed: int, seed_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """features: [(x fp32 on the device, TransformNet)].  seed (+ the device step counter seed_dev) keys the dropout
+        masks."""
         att = self.att
         H, dh = att.multi_heads, att.dim_per_head
         D = H * dh
@@ -64,11 +66,11 @@ class FusionTrainStep:
                 a = ops.project(_operands(x, self.precision, 0), w16, tn.fc1.bias.detach(), tn.activation_name)
                 it["a"] = a
                 if p > 0 or tn.bn1 is not None:
-                    y, mask, sm, si = ops.transform_train_forward(a, D, p, seed * 131 + i, tn.bn1)
+                    y, mask, sm, si = ops.transform_train_forward(a, D, p, seed * 131 + i, tn.bn1, seed_dev=seed_dev)
                 else:
                     y, mask, sm, si = a, None, None, None
             else:
-                y, mask, sm, si = ops.transform_train_forward(x, D, p, seed * 131 + i, tn.bn1)
+                y, mask, sm, si = ops.transform_train_forward(x, D, p, seed * 131 + i, tn.bn1, seed_dev=seed_dev)
             if tn.bn1 is not None:
                 tn.bn1.num_batches_tracked += 1
             it.update(y=y, mask=mask, sm=sm, si=si)
@@ -160,23 +162,40 @@ class DeviceOptimizer:
             "live": live, "ptrs": [(p.data_ptr(), p.grad.data_ptr()) for p in live], "desc": raw,
             "bt": torch.tensor(list(bt), dtype=torch.int32, device=dev), "bs": torch.tensor(list(bs), dtype=torch.int64, device=dev),
             "partial": torch.empty(n_blocks, dtype=torch.float64, device=dev),
-            "norm": torch.zeros(1, dtype=torch.float64, device=dev), "n_blocks": n_blocks}
+            "norm": torch.zeros(1, dtype=torch.float64, device=dev), "n_blocks": n_blocks,
+            "step_dev": torch.full((1,), self.step_count, dtype=torch.int64, device=dev),
+            "lr_dev": torch.zeros(1, dtype=torch.float32, device=dev), "lr_host": None}
 
     def step(self) -> torch.Tensor:
-        """Returns the (device) total gradient norm before clipping."""
+        """Returns the (device) total gradient norm before clipping.  The step count and the learning rate are read
+        from device words, so the call can sit inside a captured CUDA graph; `param_groups[0]['lr']` is pushed to the
+        device whenever it changes (outside any capture)."""
         if self._built is None:
             self._build()
         b = self._built
         if [(p.data_ptr(), p.grad.data_ptr()) for p in b["live"]] != b["ptrs"]:
             self._build()  # a parameter or gradient was re-allocated
             b = self._built
+        self.sync_lr()
         self.step_count += 1
-        lr = float(self.param_groups[0]["lr"])
+        b["step_dev"].add_(1)
         first = self.alpha if self.kind == "rmsprop" else self.betas[0]
         _capi.call("laff_optimizer_step", ops._ptr(b["desc"]), ops._ptr(b["bt"]), ops._ptr(b["bs"]), b["n_blocks"],
-                   0 if self.kind == "rmsprop" else 1, lr, float(first), float(self.betas[1]), self.eps, self.step_count,
-                   self.max_grad_norm, ops._ptr(b["partial"]), ops._ptr(b["norm"]), ops._stream(b["desc"]))
+                   0 if self.kind == "rmsprop" else 1, float(b["lr_host"]), float(first), float(self.betas[1]), self.eps,
+                   max(1, self.step_count), self.max_grad_norm, ops._ptr(b["partial"]), ops._ptr(b["norm"]),
+                   ops._ptr(b["step_dev"]), ops._ptr(b["lr_dev"]), ops._stream(b["desc"]))
         return b["norm"]
+
+    def sync_lr(self) -> None:
+        b = self._built
+        if b is None:
+            return
+        lr = float(self.param_groups[0]["lr"])
+        if b.get("lr_host") != lr:
+            if torch.cuda.is_current_stream_capturing():
+                raise LaffError("the learning rate changed inside a CUDA graph capture")
+            b["lr_dev"].fill_(lr)
+            b["lr_host"] = lr
 
     def zero_grad(self):
         pass  # every gradient buffer is overwritten by the next backward

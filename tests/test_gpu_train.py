@@ -75,6 +75,35 @@ def test_train_steps_match_reference(tag):
     assert int(model.iters) == steps
 
 
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+def test_cuda_graph_replay_equals_eager_steps(dropout):
+    """From the 4th step on the whole step is one replayed CUDA graph (device-side step counter, learning rate and
+    dropout seed): parameters and losses must equal those of the same steps issued eagerly, bit for bit."""
+    g, sd, H, steps = load_case("adam")
+    D = int(g["meta"][1])
+    runs = []
+    for use_graph in (False, True):
+        model = build_model(g, sd, H, D).train()
+        model.opt.dropout = dropout
+        for m in model.modules():
+            if isinstance(m, M.TransformNet) and m.fc1 is not None:
+                m.dropout_p = dropout if dropout > 0 else None
+        model.use_cuda_graph = use_graph
+        losses = []
+        for s in range(8):
+            vis_in, txt_in = step_inputs(g, s % steps)
+            if s == 6:
+                model.optimizer.param_groups[0]["lr"] *= 0.5          # an lr scheduler acting between steps
+            losses.append(float(model(train_data(vis_in, txt_in))["triplet_loss"]))
+        assert (model._graph is not None) == use_graph
+        runs.append((losses, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    assert runs[0][0] == runs[1][0]
+    for k in runs[0][1]:
+        assert torch.equal(runs[0][1][k], runs[1][1][k]), k
+    key = "vis_net.VisMutiTransformNet.%s.bn1.num_batches_tracked" % synth.VIS_CLIP_FT
+    assert int(runs[1][1][key]) == int(sd[key]) + 8
+
+
 def test_eval_after_training_uses_the_updated_parameters():
     """The optimizer updates parameters through raw pointers; the eval-mode operand caches must follow."""
     g, sd, H, steps = load_case("rmsprop")

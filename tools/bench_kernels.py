@@ -135,6 +135,24 @@ def main():
     emit("C2 via dense matrix 2990x2990 (encode + sim_dense + rank_from_scores + metrics)", ms,
          note="%.0f queries/s" % (n / (ms * 1e-3)))
 
+    # C3 / T1: one full training step of the LAFF model, B = 128 (forward both nets in train mode, loss, backward,
+    # clip + RMSprop), device-resident inputs; dropout 0.2 as shipped
+    Bt = 128
+    model = M.get_model("LAFF", torch.device(dev), c).train()
+    lib = __import__("laff_b200._capi", fromlist=["lib"]).lib()
+    td = {"vis_feats": {k: torch.randn(Bt, d, generator=g, device=dev) for k, d in c.vis_fc_layers[0].items()},
+          "captions": {"gru": torch.randn(Bt, 1024, generator=g, device=dev), "bow": torch.zeros(Bt, 3981, device=dev),
+                       "w2v": torch.randn(Bt, 500, generator=g, device=dev), "clip": torch.randn(Bt, 512, generator=g, device=dev)},
+          "captions_task2": None, "vis_frame_feat_dict": {}, "vis_origin_frame_tuple": None}
+    model(td)
+    lib.laff_launch_count(1)
+    model(td)
+    launches = int(lib.laff_launch_count(0))
+    ms = timeit(lambda: model(td), iters=30)
+    n_par = sum(p.numel() for p in model.parameters())
+    emit("LAFF training step B=128 (train-mode forward, loss, backward, clip + RMSprop; %.1f M parameters)" % (n_par / 1e6), ms,
+         note="%d kernel launches of this library per step; latency-bound (14.6 GFLOP of GEMM work)" % launches)
+
 
 if __name__ == "__main__":
     main()
