@@ -349,6 +349,13 @@ int laff_attention_pool_backward(const float* const* ys, const long long* lds, i
                                  float* dc, void* stream);
 int laff_transpose_16(const float* x, long long ld, int rows, int cols, int dtype, int terms, int side, void* out16,
                       long long ld_out, void* stream);
+/* LAFF-ml (model/model.py:2147-2190): gradient reaching a tiled "no-transform" feature, dx[b, j] = sum_h dz[b, h*in_dim + j]
+ * (backward of x.repeat(1, heads)); and the backward of the frame-level Attention_1 block that produced it — gradients
+ * of its logit weight [dim] / bias [1] (frames fp32 [B, F, dim] are leaves; F <= 128; dw_part [B*dim], dc_part [B] scratch). */
+int laff_fold_tiles(const float* dz, long long ld_dz, int B, int D, int in_dim, float* dx, long long ld_dx, void* stream);
+int laff_frame_pool_backward(const float* frames, long long B, int F, int dim, const float* att_weight, const float* dout,
+                             long long ld_dout, double norm_eps, float* dw_part, float* dc_part, float* dw, float* dc,
+                             void* stream);
 int laff_optimizer_blocks(const long long* sizes, int n_tensors, int* blk_tensor, long long* blk_start, int capacity);
 int laff_optimizer_step(const laff_opt_tensor* tensors_dev, const int* blk_tensor_dev, const long long* blk_start_dev,
                         int n_blocks, int kind, float lr, float alpha_or_beta1, float beta2, float eps, long long step,

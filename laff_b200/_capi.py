@@ -105,6 +105,8 @@ SIGNATURES = {
                                            _vp, _vp, _vp, _vp]),
     "laff_attention_pool_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _ll, _ll, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "laff_transpose_16": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
+    "laff_fold_tiles": (_i, [_vp, _ll, _i, _i, _i, _vp, _ll, _vp]),
+    "laff_frame_pool_backward": (_i, [_vp, _ll, _i, _i, _vp, _vp, _ll, _d, _vp, _vp, _vp, _vp, _vp]),
     "laff_optimizer_blocks": (_i, [_vp, _i, _vp, _vp, _i]),
     "laff_optimizer_step": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _ll, _f, _vp, _vp, _vp, _vp, _vp]),
     "laff_bow_counts": (_i, [_vp, _vp, _i, _i, _vp, _ll, _vp]),

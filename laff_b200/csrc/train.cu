@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(32 * kRowLanes)
       float d = dy[r * ld_dy + c];
       if (use_bn) d = g * invstd * (d - mb - ((dropped(r) - mean) * invstd) * mg);
       if (p_drop > 0.f) d = mask[static_cast<long long>(r) * D + c] ? d * keep_scale : 0.f;
-      d *= act_grad_from_output(a[r * ld_a + c], act);
+      if (a) d *= act_grad_from_output(a[r * ld_a + c], act);
       dz[r * ld_dz + c] = d;
       sbias += d;
     }
@@ -267,6 +267,100 @@ __global__ void __launch_bounds__(128) pool_train_bwd_kernel(const __grid_consta
 #pragma unroll
   for (int v = 0; v < VPL; ++v) dw_part[wid * dh + v * 32 + lane] = dwv[v];
   if (lane == 0) dc_part[wid] = dcv;
+}
+
+// Gradient w.r.t. a tiled ("no-transform") feature: dx[b, j] = sum_h dz[b, h * in_dim + j]  (x.repeat(1, heads) backward).
+__global__ void fold_tiles_kernel(const float* __restrict__ dz, long long ld_dz, int B, int D, int in_dim, float* __restrict__ dx,
+                                  long long ld_dx) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * in_dim) return;
+  const int b = static_cast<int>(i / in_dim), j = static_cast<int>(i - static_cast<long long>(b) * in_dim);
+  float s = 0.f;
+  for (int c = j; c < D; c += in_dim) s += dz[b * ld_dz + c];
+  dx[b * ld_dx + j] = s;
+}
+
+// Backward of the frame-level LAFF block (Attention_1(dim) over the F frames of a video, with_ave = mul = False;
+// model/model.py:2167-2173): gradients of the logit weight / bias only (frame features are leaves).  One warp per
+// video; softmax weights and d p_f are kept in shared memory (F <= kMaxFrames).
+constexpr int kMaxFrames = 128;
+template <int VPL>
+__global__ void __launch_bounds__(128) frame_pool_bwd_kernel(const float* __restrict__ frames, long long B, int F, int dim,
+                                                            const float* __restrict__ att_w, const float* __restrict__ dout,
+                                                            long long ld_dout, float norm_eps, float* __restrict__ dw_part,
+                                                            float* __restrict__ dc_part) {
+  __shared__ float s_p[4][kMaxFrames], s_dp[4][kMaxFrames];
+  const long long vid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  if (vid >= B) return;
+  const float* base = frames + vid * static_cast<long long>(F) * dim;
+  auto wsum = [&](float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+  };
+  float w[VPL];
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) w[t] = att_w[lane + 32 * t];
+  float m = -INFINITY;
+  for (int f = 0; f < F; ++f) {
+    float sdot = 0.f;
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) sdot = fmaf(w[t], base[static_cast<long long>(f) * dim + lane + 32 * t], sdot);
+    const float e = wsum(sdot);  // the bias shifts every logit alike: it cancels in the softmax
+    if (lane == 0) s_p[wl][f] = e;
+    m = fmaxf(m, e);
+  }
+  __syncwarp();
+  float z = 0.f;
+  for (int f = 0; f < F; ++f) z += expf(s_p[wl][f] - m);
+  float g[VPL];
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) g[t] = 0.f;
+  for (int f = 0; f < F; ++f) {
+    const float pf = expf(s_p[wl][f] - m) / z;
+    __syncwarp();
+    if (lane == 0) s_p[wl][f] = pf;
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) g[t] = fmaf(pf, base[static_cast<long long>(f) * dim + lane + 32 * t], g[t]);
+  }
+  __syncwarp();
+  float ss = 0.f, dot = 0.f, dg[VPL];
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) {
+    dg[t] = dout[vid * ld_dout + lane + 32 * t];
+    ss = fmaf(g[t], g[t], ss);
+  }
+  const float nrm = sqrtf(wsum(ss));
+  const float inv = 1.0f / (nrm + norm_eps);
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) dot = fmaf(g[t] * inv, dg[t], dot);
+  dot = wsum(dot);
+  const float shrink = nrm > 0.f ? dot * nrm * inv : 0.f;
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) dg[t] = (dg[t] - (g[t] * inv) * shrink) * inv;
+  float mix = 0.f;
+  for (int f = 0; f < F; ++f) {
+    float part = 0.f;
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) part = fmaf(dg[t], base[static_cast<long long>(f) * dim + lane + 32 * t], part);
+    part = wsum(part);
+    if (lane == 0) s_dp[wl][f] = part;
+    mix = fmaf(s_p[wl][f], part, mix);
+  }
+  __syncwarp();
+  float dwv[VPL], dcv = 0.f;
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) dwv[t] = 0.f;
+  for (int f = 0; f < F; ++f) {
+    const float de = s_p[wl][f] * (s_dp[wl][f] - mix);
+    dcv += de;
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) dwv[t] = fmaf(de, base[static_cast<long long>(f) * dim + lane + 32 * t], dwv[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) dw_part[vid * dim + lane + 32 * t] = dwv[t];
+  if (lane == 0) dc_part[vid] = dcv;
 }
 
 // out[c] = sum_r part[r, c]   (rows x cols, deterministic order)
@@ -459,8 +553,8 @@ extern "C" int laff_transform_train_backward(const float* dy, long long ld_dy, c
   LAFF_REQUIRE(dy && B > 0 && D > 0 && ld_dy >= D && (a != nullptr) != (tiled_x != nullptr), LAFF_EINVAL,
                "laff_transform_train_backward: exactly one of a / tiled_x must be given");
   LAFF_REQUIRE(!a || ld_a >= D, LAFF_EINVAL, "laff_transform_train_backward: bad pitch of a");
-  LAFF_REQUIRE(!tiled_x || (in_dim > 0 && D % in_dim == 0 && ld_x >= in_dim && !dz), LAFF_EINVAL,
-               "laff_transform_train_backward: tiled feature: in_dim must divide D and dz must be NULL (the input is a leaf)");
+  LAFF_REQUIRE(!tiled_x || (in_dim > 0 && D % in_dim == 0 && ld_x >= in_dim), LAFF_EINVAL,
+               "laff_transform_train_backward: tiled feature: in_dim must divide D");
   LAFF_REQUIRE(!dz || ld_dz >= D, LAFF_EINVAL, "laff_transform_train_backward: bad pitch of dz");
   LAFF_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || mask), LAFF_EINVAL, "laff_transform_train_backward: dropout mask missing");
   LAFF_REQUIRE(!use_bn || (save_mean && save_invstd), LAFF_EINVAL, "laff_transform_train_backward: BatchNorm statistics missing");
@@ -518,6 +612,57 @@ extern "C" int laff_attention_pool_backward(const float* const* ys, const long l
   const int cols = heads * head_dim;
   colsum_kernel<<<(cols + 127) / 128, 128, 0, st>>>(dw_part, rows, cols, dw);
   colsum_kernel<<<(heads + 127) / 128, 128, 0, st>>>(dc_part, rows, heads, dc);
+  count_launch(2);
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}
+
+extern "C" int laff_fold_tiles(const float* dz, long long ld_dz, int B, int D, int in_dim, float* dx, long long ld_dx, void* stream) {
+  LAFF_REQUIRE(dz && dx && B > 0 && D > 0 && in_dim > 0 && D % in_dim == 0 && ld_dz >= D && ld_dx >= in_dim, LAFF_EINVAL,
+               "laff_fold_tiles: bad arguments");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const long long n = static_cast<long long>(B) * in_dim;
+  fold_tiles_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dz, ld_dz, B, D, in_dim, dx,
+                                                                                                        ld_dx);
+  count_launch();
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}
+
+extern "C" int laff_frame_pool_backward(const float* frames, long long B, int F, int dim, const float* att_weight, const float* dout,
+                                        long long ld_dout, double norm_eps, float* dw_part, float* dc_part, float* dw, float* dc,
+                                        void* stream) {
+  LAFF_REQUIRE(frames && att_weight && dout && dw_part && dc_part && dw && dc && B > 0 && F > 0 && ld_dout >= dim, LAFF_EINVAL,
+               "laff_frame_pool_backward: bad arguments");
+  LAFF_REQUIRE(F <= kMaxFrames, LAFF_ENOTSUP, "laff_frame_pool_backward: at most %d frames per video (got %d)", kMaxFrames, F);
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>((B + 3) / 4);
+#define LAFF_FRAME_BWD(V)                                                                                                   \
+  case V:                                                                                                                   \
+    frame_pool_bwd_kernel<V><<<blocks, 128, 0, st>>>(frames, B, F, dim, att_weight, dout, ld_dout, static_cast<float>(norm_eps), \
+                                                     dw_part, dc_part);                                                     \
+    break;
+  switch (dim % 32 == 0 ? dim / 32 : 0) {
+    LAFF_FRAME_BWD(1)
+    LAFF_FRAME_BWD(2)
+    LAFF_FRAME_BWD(4)
+    LAFF_FRAME_BWD(8)
+    LAFF_FRAME_BWD(16)
+    LAFF_FRAME_BWD(32)
+    default:
+      set_error("laff_frame_pool_backward: dim %d not in {32, 64, 128, 256, 512, 1024}", dim);
+      return LAFF_ENOTSUP;
+  }
+#undef LAFF_FRAME_BWD
+  count_launch();
+  LAFF_CUDA(cudaGetLastError());
+  colsum_kernel<<<(dim + 127) / 128, 128, 0, st>>>(dw_part, B, dim, dw);
+  colsum_kernel<<<1, 128, 0, st>>>(dc_part, B, 1, dc);
   count_launch(2);
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;

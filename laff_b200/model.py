@@ -669,10 +669,17 @@ class W2VVPP(nn.Module):
     def _stage_train_inputs(self, train_data, dev):
         """Device fp32 tensors of one batch: ({text encoder name: feature}, {video feature name: feature}).  String
         front-ends (BoW / word2vec) run here, before anything that a CUDA graph captures."""
-        if not isinstance(self.vis_net, VisMutiTransformNetAddAttnetion):
-            raise NotImplementedError("training LAFF-ml (frame-level attention backward) is not built yet; 'LAFF' trains")
         txt = {n: self.txt_net._feature(train_data["captions"], n).to(dev, non_blocking=True).float()
                for n in self.txt_net.encoder_name_list}
+        if isinstance(self.vis_net, VisMutiTransformNetPlusFrameFeat):
+            frames = train_data.get("vis_frame_feat_dict") or {}
+            names = [n for n in self.vis_net.vis_net_space_dict.keys() if n not in self.vis_net.frame_attention]
+            if not self.opt.frame_feat_with_video_feat:
+                names = []
+            vis = {n: train_data["vis_feats"][n].to(dev, non_blocking=True).float() for n in names}
+            for n in self.vis_net.frame_attention.keys():  # zero-padded frames take part, as in the reference (SURVEY §3.3)
+                vis["frames/" + n] = frames[n].to(dev, non_blocking=True).float().contiguous()
+            return txt, vis
         vis = {n: train_data["vis_feats"][n].to(dev, non_blocking=True).float() for n in self.vis_net.vis_net_space_dict.keys()}
         return txt, vis
 
@@ -681,13 +688,32 @@ class W2VVPP(nn.Module):
         from .train import FusionTrainStep
         self._seed_dev.add_(1)
         tmods = dict(self.txt_net.transform_layer.named_children())
-        vmods = dict(self.vis_net.VisMutiTransformNet.named_children())
         tfeats = [(txt[n], tmods[n + "_transform"]) for n in self.txt_net.encoder_name_list]
-        # train-mode quirk of the reference: an all-zero video feature becomes noise (model/model.py:1819-1821).  Selected
-        # on the device: the reference's `torch.nonzero(...)` costs a host synchronisation per feature per step.
-        vfeats = [(torch.where((x != 0).any(), x, torch.randn_like(x)), vmods[n]) for n, x in vis.items()]
+        frame_ml = isinstance(self.vis_net, VisMutiTransformNetPlusFrameFeat)
+        pooled = {}
+        if frame_ml:
+            # LAFF-ml (model/model.py:2147-2190): frame-level Attention_1 per video, its output joins the video-level
+            # features as a no-transform feature.  (The logit bias cancels in the softmax: passed as 0, no host read.)
+            vmods = dict(self.vis_net.named_children())
+            vis_att = self.vis_net.vis_attention_layer
+            vfeats = []
+            for n, x in vis.items():
+                if n.startswith("frames/"):
+                    fa = self.vis_net.frame_attention[n[7:]][0]
+                    if fa.with_ave or fa.mul:
+                        raise NotImplementedError("training the mean-residual / product frame attention is not built")
+                    pooled[len(vfeats)] = (n[7:], x)
+                    vfeats.append((ops.frame_pool(x, fa.embedding_common[0].weight, 0.0), vmods[n[7:]], True))
+                else:
+                    vfeats.append((x, vmods[n]))
+        else:
+            vmods = dict(self.vis_net.VisMutiTransformNet.named_children())
+            vis_att = self.vis_net.attention_layer
+            # train-mode quirk of the reference: an all-zero video feature becomes noise (model/model.py:1819-1821).
+            # Selected on the device: the reference's `torch.nonzero(...)` costs a host synchronisation per feature per step.
+            vfeats = [(torch.where((x != 0).any(), x, torch.randn_like(x)), vmods[n]) for n, x in vis.items()]
         outs = {}
-        for key, feats, att in (("txt", tfeats, self.txt_net.attention_layer), ("vis", vfeats, self.vis_net.attention_layer)):
+        for key, feats, att in (("txt", tfeats, self.txt_net.attention_layer), ("vis", vfeats, vis_att)):
             step = self._steps.get(key)
             if step is None or step.att is not att or step.precision != precision:
                 step = self._steps[key] = FusionTrainStep(att, precision)
@@ -695,7 +721,14 @@ class W2VVPP(nn.Module):
         c = self.criterion
         loss, d_txt, d_vis = ops.mrl_forward_backward(outs["txt"], outs["vis"], c.margin, c.max_violation, c.direction, c.cost_style)
         self._steps["txt"].backward(d_txt)
-        self._steps["vis"].backward(d_vis)
+        dxs = self._steps["vis"].backward(d_vis)
+        for idx, (name, frames) in pooled.items():
+            lin = self.vis_net.frame_attention[name][0].embedding_common[0]
+            bufs = self._frame_grads.get(name)
+            if bufs is None:
+                bufs = self._frame_grads[name] = (torch.zeros_like(lin.weight), torch.zeros_like(lin.bias))
+            lin.weight.grad, lin.bias.grad = bufs
+            ops.frame_pool_backward(frames, lin.weight, dxs[idx], bufs[0], bufs[1])
         self.last_grad_norm = self.optimizer.step()
         return loss
 
@@ -722,18 +755,20 @@ class W2VVPP(nn.Module):
             raise NotImplementedError("negation-aware training (cal_foward_neg) is outside the LAFF hot path")
         if not getattr(opt, "multi_space", True):
             raise NotImplementedError("training through the score-matrix loss branch (multi_space = False) is not built")
-        if getattr(opt, "float16", False):
-            raise NotImplementedError("AMP / GradScaler training is not built; operand precision is set by `train_precision`")
         if not self.training:
             raise ops.LaffError("model(train_data) is a training step: call model.train() first")
         self.iters += 1
         dev = _cuda_device(next(self.parameters()).device)
-        precision = self.train_precision
+        # config.float16 (AMP in the reference, model/model.py:970-989): fp16 tensor-core operands with fp32 accumulation,
+        # master weights and gradients — no GradScaler is needed (nothing is stored in fp16), and the reference's
+        # clip-before-unscale ordering has no counterpart.
+        precision = "fp16" if getattr(opt, "float16", False) else self.train_precision
         if getattr(self, "optimizer", None) is None:
             self.optimizer = self._make_optimizer()
             self._steps = {}
             self._seed_base = int(getattr(opt, "seed", 0) or 0) << 20
             self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._frame_grads = {}
             self._graph = None
         txt, vis = self._stage_train_inputs(train_data, dev)
         sig = (precision,) + tuple((k, tuple(v.shape)) for k, v in list(txt.items()) + list(vis.items()))

@@ -574,7 +574,7 @@ def transform_train_backward(dy: torch.Tensor, a: Optional[torch.Tensor], tiled_
     Returns dz [B, D] (None for a tiled feature); writes dgamma / dbeta / dbias [D] when given."""
     _need_cuda(dy, a, tiled_x)
     B, D = dy.shape
-    dz = torch.empty((B, D), dtype=torch.float32, device=dy.device) if (want_dz and a is not None) else None
+    dz = torch.empty((B, D), dtype=torch.float32, device=dy.device) if want_dz else None
     act = activation if isinstance(activation, int) else _capi.ACT[activation]
     _capi.call("laff_transform_train_backward", _ptr(dy), dy.stride(0), _ptr(a), 0 if a is None else a.stride(0), _ptr(tiled_x),
                0 if tiled_x is None else tiled_x.stride(0), 0 if tiled_x is None else tiled_x.shape[1], _ptr(mask), float(p_drop),
@@ -616,3 +616,26 @@ def transpose_16(x: torch.Tensor, dtype=torch.bfloat16, terms: int = 1, side: in
     _capi.call("laff_transpose_16", _ptr(x), x.stride(0), R, Cn, _DT[dtype], int(terms), int(side), _ptr(out), out.stride(0),
                _stream(x))
     return out
+
+
+def fold_tiles(dz: torch.Tensor, in_dim: int) -> torch.Tensor:
+    """Gradient w.r.t. a feature that was tiled over the heads: [B, D] -> [B, in_dim] (laff_fold_tiles)."""
+    _need_cuda(dz)
+    B, D = dz.shape
+    dx = torch.empty((B, in_dim), dtype=torch.float32, device=dz.device)
+    _capi.call("laff_fold_tiles", _ptr(dz), dz.stride(0), B, D, int(in_dim), _ptr(dx), dx.stride(0), _stream(dz))
+    return dx
+
+
+def frame_pool_backward(frames: torch.Tensor, att_weight: torch.Tensor, dout: torch.Tensor, dw: torch.Tensor, dc: torch.Tensor,
+                        norm_eps: float = 1e-14) -> None:
+    """Backward of the frame-level LAFF block w.r.t. its logit weight / bias (laff_frame_pool_backward)."""
+    _need_cuda(frames, att_weight, dout, dw, dc)
+    frames = frames.float().contiguous()
+    B, F, dim = frames.shape
+    att_weight = att_weight.detach().float().contiguous().view(-1)
+    dout = _rowmajor(dout)
+    dw_part = torch.empty(B * dim, dtype=torch.float32, device=frames.device)
+    dc_part = torch.empty(B, dtype=torch.float32, device=frames.device)
+    _capi.call("laff_frame_pool_backward", _ptr(frames), B, F, dim, _ptr(att_weight), _ptr(dout), dout.stride(0), float(norm_eps),
+               _ptr(dw_part), _ptr(dc_part), _ptr(dw), _ptr(dc), _stream(frames))

@@ -58,9 +58,10 @@ class FusionTrainStep:
         H, dh = att.multi_heads, att.dim_per_head
         D = H * dh
         items = []
-        for i, (x, tn) in enumerate(features):
+        for i, f in enumerate(features):
+            x, tn = f[0], f[1]
             p = float(tn.dropout_p or 0.0)
-            it = {"x": x, "tn": tn, "p": p}
+            it = {"x": x, "tn": tn, "p": p, "want_dx": len(f) > 2 and bool(f[2])}
             if tn.fc1 is not None:
                 w16 = _operands(tn.fc1.weight.detach(), self.precision, 1)
                 a = ops.project(_operands(x, self.precision, 0), w16, tn.fc1.bias.detach(), tn.activation_name)
@@ -82,7 +83,10 @@ class FusionTrainStep:
         self.cache = {"items": items, "w": w, "b": b, "heads": ps}
         return out
 
-    def backward(self, dout: torch.Tensor) -> None:
+    def backward(self, dout: torch.Tensor) -> Dict[int, torch.Tensor]:
+        """Writes every parameter gradient of the net into `.grad`; returns {feature index: d loss / d x} for the
+        no-transform features given as (x, TransformNet, True) — inputs that are themselves computed (LAFF-ml's pooled
+        frame feature)."""
         c = self.cache
         if c is None:
             raise LaffError("FusionTrainStep.backward called before forward")
@@ -98,14 +102,17 @@ class FusionTrainStep:
         for h, q in enumerate(c["heads"]):  # per-head parameters: gradients are views of the two stacked buffers
             q.weight.grad = dw[h:h + 1]
             q.bias.grad = self._dc[h:h + 1]
-        for it, dy in zip(c["items"], dys):
+        dxs: Dict[int, torch.Tensor] = {}
+        for idx, (it, dy) in enumerate(zip(c["items"], dys)):
             tn = it["tn"]
             dgamma = _grad_buffer(tn.bn1.weight) if tn.bn1 is not None else None
             dbeta = _grad_buffer(tn.bn1.bias) if tn.bn1 is not None else None
             if tn.fc1 is None:
-                if tn.bn1 is not None:
-                    ops.transform_train_backward(dy, None, it["x"], it["mask"], it["p"], "none", tn.bn1, it["sm"], it["si"],
-                                                 want_dz=False, dgamma=dgamma, dbeta=dbeta)
+                if tn.bn1 is not None or it["want_dx"]:
+                    dzt = ops.transform_train_backward(dy, None, it["x"], it["mask"], it["p"], "none", tn.bn1, it["sm"], it["si"],
+                                                       want_dz=it["want_dx"], dgamma=dgamma, dbeta=dbeta)
+                    if it["want_dx"]:
+                        dxs[idx] = ops.fold_tiles(dzt, it["x"].shape[1])
                 continue
             dbias = _grad_buffer(tn.fc1.bias)
             dz = ops.transform_train_backward(dy, it["a"], None, it["mask"], it["p"], tn.activation_name, tn.bn1, it["sm"],
@@ -115,6 +122,7 @@ class FusionTrainStep:
             ops.sim_dense(ops.transpose_16(dz, dt, terms, 0), ops.transpose_16(it["x"], dt, terms, 1), 1.0,
                           out=_grad_buffer(tn.fc1.weight))
         self.cache = None
+        return dxs
 
 
 class DeviceOptimizer:

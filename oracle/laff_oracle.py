@@ -357,6 +357,7 @@ def fusion_train_backward(cache: dict, dout: np.ndarray, sd: Mapping[str, np.nda
         grads[pre + "weight"] = np.einsum("bl,bld->d", de[:, h, :], Yh[:, :, h, :]).reshape(1, dh)
         grads[pre + "bias"] = de[:, h, :].sum().reshape(1)
     dY = dY.reshape(B, L, H * dh)
+    cache["dx"] = {}
     for l, it in enumerate(cache["items"]):
         pre, d = it["pre"], dY[:, l, :]
         if "xhat" in it:
@@ -368,7 +369,27 @@ def fusion_train_backward(cache: dict, dout: np.ndarray, sd: Mapping[str, np.nda
             dz = d * _act_grad(it["a"], cache["activation"])
             grads[pre + "fc1.weight"] = dz.T @ it["x"]
             grads[pre + "fc1.bias"] = dz.sum(0)
+        else:  # tiled feature: x.repeat(1, heads) backward (needed when x is itself computed, LAFF-ml)
+            cache["dx"][it["name"]] = d.reshape(B, H, -1).sum(1)
     return grads
+
+
+def frame_attention_train(frames: np.ndarray, w: np.ndarray, dout: Optional[np.ndarray] = None):
+    """Frame-level Attention_1 (with_ave = mul = False) per video over all F (zero-padded) frames
+    (model/model.py:2167-2173).  Without dout: pooled features [B, dim].  With dout: (d w [dim], d c scalar)."""
+    x = frames.astype(np.float64)
+    e = x @ w.astype(np.float64)                                        # the bias cancels in the softmax
+    p = softmax(e, axis=1)
+    g = np.einsum("bf,bfd->bd", p, x)
+    nrm = np.sqrt((g * g).sum(-1, keepdims=True))
+    out = g / (nrm + 1e-14)
+    if dout is None:
+        return out
+    inv = 1.0 / (nrm + 1e-14)
+    dg = (dout - out * (out * dout).sum(-1, keepdims=True) * nrm * inv) * inv
+    dp = np.einsum("bd,bfd->bf", dg, x)
+    de = p * (dp - (p * dp).sum(-1, keepdims=True))
+    return np.einsum("bf,bfd->d", de, x), de.sum()
 
 
 def clip_and_step(sd: dict, grads: Mapping[str, np.ndarray], state: dict, optimizer="rmsprop", lr=1e-4, max_norm=2.0,
@@ -410,6 +431,33 @@ def laff_train_step(sd: dict, vis_in: Mapping[str, np.ndarray], txt_in: Mapping[
     grads = {}
     grads.update(fusion_train_backward(tc, d_txt, sd))
     grads.update(fusion_train_backward(vc, d_vis, sd))
+    total = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values())))
+    coef = min(1.0, grad_clip / (total + 1e-6)) if grad_clip and grad_clip > 0 else 1.0
+    clipped = {k: (g * coef) for k, g in grads.items()}
+    clip_and_step(sd, grads, state, optimizer, lr, grad_clip, eps=(adam_eps if optimizer == "adam" else None))
+    return float(loss), clipped, total
+
+
+def laff_ml_train_step(sd: dict, vis_in: Mapping[str, np.ndarray], frames: np.ndarray, frame_feat: str,
+                       txt_in: Mapping[str, np.ndarray], state: dict, heads: int, optimizer="rmsprop", lr=1e-4, grad_clip=2.0,
+                       margin=0.2, adam_eps=1e-8):
+    """W2VVPP_MutiVisFrameFeat ('FrameLAFF' / LAFF-ml) training step: as laff_train_step with the frame-level block in
+    front of the video net (model/model.py:2147-2190) and BatchNorm on every projected feature."""
+    wkey = "vis_net.frame_attention.%s.0.embedding_common.0." % frame_feat
+    pooled = frame_attention_train(frames, sd[wkey + "weight"].reshape(-1))
+    vfe = [(n, x) for n, x in vis_in.items()] + [(frame_feat, pooled)]
+    vpre = {n: "vis_net.%s." % n for n, _ in vfe}
+    tfe = [(TXT_FEATURE_KEY[e], txt_in[TXT_FEATURE_KEY[e]]) for e in TXT_ENCODER_ORDER if TXT_FEATURE_KEY[e] in txt_in]
+    tpre = {TXT_FEATURE_KEY[e]: "txt_net.transform_layer.%s_transform." % e for e in TXT_ENCODER_ORDER}
+    t_emb, tc = fusion_train_forward(tfe, sd, tpre, "txt_net.attention_layer.", heads, ["clip"])
+    v_emb, vc = fusion_train_forward(vfe, sd, vpre, "vis_net.vis_attention_layer.", heads, [frame_feat])
+    loss, d_txt, d_vis = multi_head_loss(t_emb, v_emb, margin, True, "sum", "t2i", want_grad=True)
+    grads = {}
+    grads.update(fusion_train_backward(tc, d_txt, sd))
+    grads.update(fusion_train_backward(vc, d_vis, sd))
+    dw, dc = frame_attention_train(frames, sd[wkey + "weight"].reshape(-1), vc["dx"][frame_feat])
+    grads[wkey + "weight"] = dw.reshape(1, -1)
+    grads[wkey + "bias"] = np.array([dc])
     total = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values())))
     coef = min(1.0, grad_clip / (total + 1e-6)) if grad_clip and grad_clip > 0 else 1.0
     clipped = {k: (g * coef) for k, g in grads.items()}

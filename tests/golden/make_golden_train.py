@@ -63,12 +63,69 @@ def run_case(mm, tag, optimizer, lr, batch_norm, steps=3, B=16, D=256, H=8, seed
     return out
 
 
+def run_frame_case(mm, tag, optimizer, lr, steps=3, B=16, D=256, H=8, F=6, seed=91):
+    """'FrameLAFF' (LAFF-ml, W2VVPP_MutiVisFrameFeat): frame-level attention + BatchNorm on every projected feature."""
+    import torch
+    dims = SMALL
+    vis_dims = {synth.VIS_C3D: dims["c3d"], synth.VIS_TF: dims["tf"], synth.VIS_X3D: dims["x3d"], synth.VIS_IRCSN: dims["ircsn"],
+                synth.VIS_FRAME: dims["clip"]}
+    cfg = mg.make_config("frame", D, H, vis_dims, dims)
+    cfg.dropout = 0.0
+    cfg.float16 = False            # AMP needs CUDA autocast; the fp32 path is the numerical reference
+    cfg.optimizer, cfg.lr = optimizer, lr
+    torch.manual_seed(0)
+    model = mm.W2VVPP_MutiVisFrameFeat(cfg)
+    sd0 = mg.load_synth_state(model, seed)
+    model.train()
+    out = {"meta": np.array([B, D, H, steps, seed, 1, F]), "optimizer": np.array(optimizer), "lr": np.float64(lr),
+           "grad_clip": np.float64(cfg.grad_clip), "vis_names": np.array([n for n in vis_dims if n != synth.VIS_FRAME]),
+           "frame_feat": np.array(synth.VIS_FRAME)}
+    for k, v in sd0.items():
+        out["sd0/" + k] = v
+    losses = []
+    for s in range(steps):
+        vis_in = {n: synth.feature(seed + s, "vis/" + n, B, d, "relu") for n, d in vis_dims.items() if n != synth.VIS_FRAME}
+        fr = synth.feature(seed + s, "frames", B * F, dims["clip"]).reshape(B, F, dims["clip"])
+        lens = synth.rng_for(seed + s, "lens").randint(1, F + 1, size=B)
+        lens[0] = F
+        mask = np.ones((B, F), dtype=np.float32)
+        for i, n in enumerate(lens):  # zero-padded tails as collate_pair produces them (data_provider.py:108-121)
+            fr[i, n:] = 0
+            mask[i, n:] = 0
+        txt_in = {"gru": synth.feature(seed + s, "txt/gru", B, dims["gru"]), "bow": synth.feature(seed + s, "txt/bow", B, dims["bow"], "bow"),
+                  "w2v": synth.feature(seed + s, "txt/w2v", B, dims["w2v"]), "clip": synth.feature(seed + s, "txt/clip", B, dims["clip"])}
+        for k, v in vis_in.items():
+            out["step%d/vin/%s" % (s, k)] = v
+        for k, v in txt_in.items():
+            out["step%d/tin/%s" % (s, k)] = v
+        out["step%d/frames" % s], out["step%d/mask" % s] = fr.copy(), mask
+        train_data = {"vis_feats": {k: torch.from_numpy(v) for k, v in vis_in.items()},
+                      "captions": {k: torch.from_numpy(v) for k, v in txt_in.items()}, "captions_task2": None,
+                      "vis_frame_feat_dict": {"mask_tensor": torch.from_numpy(mask), synth.VIS_FRAME: torch.from_numpy(fr.copy())},
+                      "vis_origin_frame_tuple": None}
+        items = model(train_data, epoch=0)
+        losses.append(float(items["triplet_loss"]))
+        if s == 0:
+            for k, p in model.named_parameters():
+                if p.grad is not None:
+                    out["grad0/" + k] = p.grad.detach().numpy().copy()
+        for k, v in model.state_dict().items():
+            out["sd%d/%s" % (s + 1, k)] = v.detach().numpy().copy()
+    out["losses"] = np.array(losses)
+    print(tag, "losses", losses)
+    return out
+
+
 def main():
     import torch
     torch.set_num_threads(8)
     mm, rloss, reval, ratt = mg.import_reference()
+    only = sys.argv[1:]
     for tag, optimizer, lr, bn in (("rmsprop", "rmsprop", 1e-3, False), ("adam", "adam", 1e-3, False), ("rmsprop_bn", "rmsprop", 1e-3, True)):
-        np.savez_compressed(os.path.join(HERE, "train_%s.npz" % tag), **run_case(mm, tag, optimizer, lr, bn))
+        if not only or tag in only:
+            np.savez_compressed(os.path.join(HERE, "train_%s.npz" % tag), **run_case(mm, tag, optimizer, lr, bn))
+    if not only or "frame_rmsprop" in only:
+        np.savez_compressed(os.path.join(HERE, "train_frame_rmsprop.npz"), **run_frame_case(mm, "frame_rmsprop", "rmsprop", 1e-3))
 
 
 if __name__ == "__main__":

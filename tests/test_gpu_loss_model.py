@@ -155,7 +155,7 @@ def test_predict_and_model_surface_vs_oracle(golden):
     loss, items = model.compute_loss(v, t)
     rl = O.multi_head_loss(ot, ov, 0.2, True, "sum", "t2i")
     assert abs(loss.item() - float(rl)) <= 2e-4 * max(1.0, abs(float(rl))) and "triplet_loss" in items
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ops.LaffError):      # a training step needs model.train() (tests/test_gpu_train.py covers the step)
         model({}, 0)
     with pytest.raises(AssertionError):
         M.get_model("W2VVPP", "cuda", c)

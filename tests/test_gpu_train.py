@@ -166,3 +166,41 @@ def test_optimizer_matches_torch_and_skips_gradless_parameters():
                 assert (p - q).abs().max().item() <= 2e-6, (kind, step)
                 assert (p.grad - q.grad).abs().max().item() <= 1e-6 * max(1.0, q.grad.abs().max().item())
         assert torch.equal(extra, e0)
+
+
+def test_laff_ml_train_steps_match_reference():
+    """'FrameLAFF' (LAFF-ml): frame-level attention backward, gradient through the tiled pooled frame feature, BatchNorm
+    on every projected feature — three steps against the unmodified reference model."""
+    from test_train_cpu import check_params
+    g, sd, H, steps = load_case("frame_rmsprop")
+    D = int(g["meta"][1])
+    ff = str(g["frame_feat"])
+    c = cfg.frame_laff_config(D, H, SMALL)
+    c.dropout, c.float16 = 0.0, False
+    c.optimizer, c.lr, c.grad_clip = str(g["optimizer"]), float(g["lr"]), float(g["grad_clip"])
+    model = M.get_model("FrameLAFF", torch.device("cuda"), c)
+    load_numpy_state(model, sd)
+    model.train()
+    for s in range(steps + 3):                      # three more steps run through the replayed CUDA graph
+        vis_in, txt_in = step_inputs(g, s % steps)
+        td = train_data(vis_in, txt_in)
+        td["vis_frame_feat_dict"] = {"mask_tensor": torch.from_numpy(g["step%d/mask" % (s % steps)]),
+                                     ff: torch.from_numpy(g["step%d/frames" % (s % steps)])}
+        loss = float(model(td, epoch=0)["triplet_loss"])
+        if s >= steps:
+            assert np.isfinite(loss)
+            continue
+        # step 0 is a pure function of the inputs: tight.  Later steps inherit the first RMSprop step, which is sign-SGD
+        # (g / sqrt(0.01 g^2)): the ~0.1 % of elements whose gradient lies below the 1e-5 relative noise of the split-bf16
+        # products step the other way by 2 * lr / sqrt(1 - alpha), which moves the next losses by ~1e-4 relative.
+        assert abs(loss - g["losses"][s]) <= (2e-5 if s == 0 else 5e-4) * abs(g["losses"][s]), (s, loss, g["losses"][s])
+        if s == 0:
+            grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+            ref_keys = [k[6:] for k in g.files if k.startswith("grad0/")]
+            assert sorted(ref_keys) == sorted(grads.keys())
+            for k in ref_keys:
+                ref = g["grad0/" + k]
+                got = grads[k].cpu().numpy().reshape(ref.shape)
+                assert np.abs(got - ref).max() <= 1e-4 * max(1e-3, np.abs(ref).max()), (k, np.abs(got - ref).max())
+        check_params({k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}, g, s, float(g["lr"]), tight0=5e-5, frac=0.97)
+    assert model._graph is not None
