@@ -69,6 +69,7 @@ def laff_config(D: int = 4096, heads: int = 8, dims: Optional[Mapping[str, int]]
     c.vis_attention = c.txt_attention = "Multi_head_MyApply_Attention"                       # attention_types[12]
     c.vis_no_transform = [synth.VIS_CLIP_FT]                                                 # configs/laff.py:49
     c.txt_no_transform = ["CLIP_encoder"]                                                    # configs/laff.py:50
+    c.vid_feats = list(c.vis_fc_layers[0].keys())                                            # configs/laff.py:28-33
     return c
 
 

@@ -179,14 +179,14 @@ def write_to_predict_result_file(predict_result_file, model_path, checkpoint, re
     text += " * mAP: {}\n".format(round(mAP, 3))
     text += " * " + "-" * 10
     print(text)
-    opt = checkpoint["opt"] if isinstance(checkpoint, Mapping) else checkpoint.opt
+    opt = None if checkpoint is None else (checkpoint["opt"] if isinstance(checkpoint, Mapping) else checkpoint.opt)
     with open(predict_result_file, "a") as f:
         f.write(str(time.asctime(time.localtime(time.time()))) + "\t")
         for each in [model_path, round(r1, 3), round(r5, 3), round(r10, 3), round(medr, 3), round(meanr, 3), round(mir, 3),
                      round(mAP, 3)]:
             f.write(str(each))
             f.write("\t")
-        f.write(opt.parm_adjust_config.replace("_", "\t"))
+        f.write(opt.parm_adjust_config.replace("_", "\t") if opt is not None else "")
         f.write("\n")
 
 
