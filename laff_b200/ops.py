@@ -226,6 +226,9 @@ def topk_dense(scores: torch.Tensor, k: int, idx_in: Optional[torch.Tensor] = No
         if tuple(idx_in.shape) != (R, Cn):
             raise LaffError("topk_dense: idx_in must have the shape of scores")
         ld_idx = idx_in.stride(0)
+    if R == 0 or Cn == 0:  # nothing to rank: empty lists
+        return (torch.full((R, k), float("-inf"), dtype=torch.float32, device=scores.device),
+                torch.full((R, k), -1, dtype=torch.int32, device=scores.device))
     tv = torch.empty((R, k), dtype=torch.float32, device=scores.device)
     ti = torch.empty((R, k), dtype=torch.int32, device=scores.device)
     _capi.call("laff_topk_dense", _ptr(scores), scores.stride(0), _ptr(idx_in), ld_idx, R, Cn, int(k), float(scale), _ptr(tv),

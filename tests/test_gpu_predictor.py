@@ -59,6 +59,19 @@ def test_topk_dense_more_than_candidates_and_scale():
         ops.topk_dense(torch.zeros(2, 5000, device="cuda"), 4096)
 
 
+def test_topk_dense_infinities_and_empty_inputs():
+    s = np.array([[0.0, np.inf, -np.inf, 1.0, np.inf, -np.inf]], dtype=np.float32)
+    for cols_pad in (0, 20000):                      # whole-row sort path and radix-select path
+        row = np.concatenate([s, np.full((1, cols_pad), -2.0, np.float32)], 1)
+        tv, ti = ops.topk_dense(torch.from_numpy(row).cuda(), 6 if cols_pad == 0 else 5)
+        ref_v, ref_i = O.tie_rule_topk(row, tv.shape[1])
+        assert np.array_equal(ti.cpu().numpy().astype(np.int64), ref_i) and np.array_equal(tv.cpu().numpy(), ref_v)
+    tv, ti = ops.topk_dense(torch.zeros(3, 0, device="cuda"), 4)
+    assert tv.shape == (3, 4) and bool(torch.isinf(tv).all()) and bool((ti == -1).all())
+    tv, ti = ops.topk_dense(torch.zeros(0, 7, device="cuda"), 4)
+    assert tv.shape == (0, 4)
+
+
 def test_topk_dense_merges_shard_lists_by_global_index():
     """Per-shard lists concatenated (as all_gather delivers them) -> the global list, ties resolved by global index."""
     rng = np.random.RandomState(5)
