@@ -300,6 +300,12 @@ int laff_mrl_forward_backward(const float* txt, const float* vis, int B, int H, 
 int laff_mrl_score_forward_backward(const float* score, int B, long long ld, float margin, int max_violation,
                                     int direction, int cost_mean, float* loss, float* d_score, void* stream);
 
+/* DualSoftmaxLoss (loss.py:291-310; config.loss == 'dsl'), summed over heads like the margin loss:
+ *   sim = cosine_sim(s, im);  f(A) = -sum_i log_softmax(A * softmax(A / temp, dim=0) * len(A), dim=-1)[i, i];
+ *   loss = (f(sim) + f(sim^T)) / 2.   B <= 1024.  Workspace: laff_mrl_workspace_bytes(B, H, dh). */
+int laff_dsl_forward_backward(const float* txt, const float* vis, int B, int H, int dh, float temp, float* loss, float* d_txt,
+                              float* d_vis, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * T1 / N4  Training step (model/model.py:964-1001).  The projections and the weight-gradient products run on the
  *     GEMM entry points above (laff_project, laff_sim_dense); these are the stages around them.
@@ -313,7 +319,8 @@ int laff_mrl_score_forward_backward(const float* score, int B, long long ld, flo
  * laff_transform_train_backward — its backward down to the GEMM output: dz = BN'(dy) * mask / (1 - p) * act'(a)
  *     (a = activated projection saved by the forward), dgamma / dbeta / dbias [D].  For a tiled feature pass tiled_x
  *     instead of a (its input is a leaf: dz must be NULL).
- * laff_attention_pool_backward — backward of Multi_head_MyApply_Attention + Attention_1 (with_ave = mul = False):
+ * laff_attention_pool_backward — backward of Multi_head_MyApply_Attention + Attention_1 (with_ave / mul / omega as in
+ *     laff_attention_pool; omega itself gets no gradient: the reference reads it with .item(), model/Attention.py:96):
  *     ys / dys: HOST arrays of n_features device pointers to y_l / dy_l fp32 [rows, H*d_h] (pitches lds, host array);
  *     dw [H, d_h], dc [H]: gradients of the per-head logit weights / biases; dw_part [rows*H*d_h], dc_part [rows*H]
  *     scratch (per-row partials, reduced in a fixed order: deterministic).
@@ -345,8 +352,8 @@ int laff_transform_train_backward(const float* dy, long long ld_dy, const float*
                                   float* dz, long long ld_dz, float* dgamma, float* dbeta, float* dbias, void* stream);
 int laff_attention_pool_backward(const float* const* ys, const long long* lds, int n_features, int heads, int head_dim,
                                  const float* att_weight, const float* att_bias, const float* dout, long long ld_dout,
-                                 long long rows, float norm_eps, float* const* dys, float* dw_part, float* dc_part, float* dw,
-                                 float* dc, void* stream);
+                                 long long rows, float norm_eps, int with_ave, int mul, float omega, float* const* dys,
+                                 float* dw_part, float* dc_part, float* dw, float* dc, void* stream);
 int laff_transpose_16(const float* x, long long ld, int rows, int cols, int dtype, int terms, int side, void* out16,
                       long long ld_out, void* stream);
 /* LAFF-ml (model/model.py:2147-2190): gradient reaching a tiled "no-transform" feature, dx[b, j] = sum_h dz[b, h*in_dim + j]

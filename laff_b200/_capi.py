@@ -103,7 +103,8 @@ SIGNATURES = {
                                           _vp, _vp, _vp]),
     "laff_transform_train_backward": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _vp, _f, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _ll,
                                            _vp, _vp, _vp, _vp]),
-    "laff_attention_pool_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _ll, _ll, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "laff_attention_pool_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _ll, _ll, _f, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
+                                          _vp]),
     "laff_transpose_16": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
     "laff_fold_tiles": (_i, [_vp, _ll, _i, _i, _i, _vp, _ll, _vp]),
     "laff_frame_pool_backward": (_i, [_vp, _ll, _i, _i, _vp, _vp, _ll, _d, _vp, _vp, _vp, _vp, _vp]),
@@ -123,6 +124,7 @@ SIGNATURES = {
     "laff_mrl_workspace_bytes": (_sz, [_i, _i, _i]),
     "laff_mrl_forward_backward": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "laff_mrl_score_forward_backward": (_i, [_vp, _i, _ll, _f, _i, _i, _i, _vp, _vp, _vp]),
+    "laff_dsl_forward_backward": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

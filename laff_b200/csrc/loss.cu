@@ -150,6 +150,87 @@ __global__ void mrl_hinge_kernel(const float* __restrict__ S, int B, long long l
   }
 }
 
+// DualSoftmaxLoss (loss.py:291-310) on one head's score matrix X [B, B] (rows = videos, columns = sentences):
+//   loss = (f(X^T) + f(X)) / 2,   f(A) = -sum_i log_softmax_row(B * A * softmax_col(A / temp))[i, i]
+// One block per head, thread t owns column t in the column passes and row t in the row passes.  dX (may be NULL)
+// receives dLoss/dX.  All statistics live in shared memory (B <= 1024).
+template <bool TR>
+__device__ void dsl_term(const float* __restrict__ X, int B, float temp, float* s_cm, float* s_cz, float* s_rm, float* s_rz,
+                         float* s_cc, float* s_red, float* loss_acc, float* __restrict__ dX, bool accumulate) {
+  auto A = [&](int i, int j) -> float { return TR ? X[static_cast<long long>(j) * B + i] : X[static_cast<long long>(i) * B + j]; };
+  const float invT = 1.0f / temp, fB = static_cast<float>(B);
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {  // column softmax statistics
+    float m = -INFINITY;
+    for (int i = 0; i < B; ++i) m = fmaxf(m, A(i, j) * invT);
+    float z = 0.f;
+    for (int i = 0; i < B; ++i) z += expf(A(i, j) * invT - m);
+    s_cm[j] = m;
+    s_cz[j] = z;
+  }
+  __syncthreads();
+  auto P0 = [&](int i, int j) -> float { return expf(A(i, j) * invT - s_cm[j]) / s_cz[j]; };
+  float local = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {  // row log-softmax of M = B * A * P0
+    float m = -INFINITY;
+    for (int j = 0; j < B; ++j) m = fmaxf(m, fB * A(i, j) * P0(i, j));
+    float z = 0.f;
+    for (int j = 0; j < B; ++j) z += expf(fB * A(i, j) * P0(i, j) - m);
+    s_rm[i] = m;
+    s_rz[i] = z;
+    local -= fB * A(i, i) * P0(i, i) - m - logf(z);
+  }
+  local = wsum(local);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += s_red[w];
+    *loss_acc += 0.5f * t;
+  }
+  if (!dX) {
+    __syncthreads();
+    return;
+  }
+  auto dM = [&](int i, int j) -> float {
+    const float a = A(i, j), p0 = P0(i, j);
+    return expf(fB * a * p0 - s_rm[i]) / s_rz[i] - (i == j ? 1.0f : 0.0f);
+  };
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {  // c_j = sum_k P0_kj * dP0_kj,  dP0 = B * A * dM
+    float c = 0.f;
+    for (int k = 0; k < B; ++k) c = fmaf(P0(k, j), fB * A(k, j) * dM(k, j), c);
+    s_cc[j] = c;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < B * B; e += blockDim.x) {
+    const int i = e / B, j = e - i * B;
+    const float a = A(i, j), p0 = P0(i, j), dm = dM(i, j);
+    const float d = 0.5f * (fB * p0 * dm + invT * p0 * (fB * a * dm - s_cc[j]));
+    float* o = TR ? dX + static_cast<long long>(j) * B + i : dX + static_cast<long long>(i) * B + j;
+    *o = accumulate ? *o + d : d;
+  }
+  __syncthreads();
+}
+
+__global__ void dsl_kernel(const float* __restrict__ S, int B, long long head_stride, float temp, float* __restrict__ head_loss,
+                           float* __restrict__ dS) {
+  extern __shared__ float s_dsl[];  // 5 * B + 32 floats
+  float* s_cm = s_dsl;
+  float* s_cz = s_cm + B;
+  float* s_rm = s_cz + B;
+  float* s_rz = s_rm + B;
+  float* s_cc = s_rz + B;
+  float* s_red = s_cc + B;
+  __shared__ float s_loss;
+  const int h = blockIdx.x;
+  if (threadIdx.x == 0) s_loss = 0.f;
+  __syncthreads();
+  const float* X = S + h * head_stride;
+  float* dX = dS ? dS + h * head_stride : nullptr;
+  dsl_term<true>(X, B, temp, s_cm, s_cz, s_rm, s_rz, s_cc, s_red, &s_loss, dX, false);   // f(cosine_sim(s, im)) = f(X^T)
+  dsl_term<false>(X, B, temp, s_cm, s_cz, s_rm, s_rz, s_cc, s_red, &s_loss, dX, true);   // f(sim^T) = f(X)
+  if (threadIdx.x == 0) head_loss[h] = s_loss;
+}
+
 __global__ void mrl_sum_heads_kernel(const float* __restrict__ head_loss, int H, float* __restrict__ loss) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float t = 0.f;
@@ -208,12 +289,13 @@ size_t laff_mrl_workspace_bytes(int B, int H, int dh) {
   return 2 * emb + 2 * nrm + 2 * mat + align256(static_cast<size_t>(H) * 4) + 256;
 }
 
-int laff_mrl_forward_backward(const float* txt, const float* vis, int B, int H, int dh, float margin,
-                              int max_violation, int direction, int cost_mean, float* loss, float* d_txt,
-                              float* d_vis, void* workspace, size_t workspace_bytes, void* stream) {
+static int embedding_loss(int kind, const float* txt, const float* vis, int B, int H, int dh, float margin, int max_violation,
+                          int direction, int cost_mean, float temp, float* loss, float* d_txt, float* d_vis, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   LAFF_REQUIRE(txt && vis && loss && workspace && B > 0 && H > 0 && dh > 0, LAFF_EINVAL,
-               "laff_mrl_forward_backward: bad arguments");
+               "laff_mrl_forward_backward / laff_dsl_forward_backward: bad arguments");
   LAFF_REQUIRE(direction >= 0 && direction <= 2, LAFF_EINVAL, "laff_mrl_forward_backward: bad direction %d", direction);
+  LAFF_REQUIRE(kind == 0 || (B <= 1024 && temp > 0.f), LAFF_ENOTSUP, "laff_dsl_forward_backward: batch size %d > 1024 or temp <= 0", B);
   LAFF_REQUIRE(workspace_bytes >= laff_mrl_workspace_bytes(B, H, dh), LAFF_EWORKSPACE,
                "laff_mrl_forward_backward: workspace too small");
   LAFF_REQUIRE(dh <= 8192, LAFF_ENOTSUP, "laff_mrl_forward_backward: head dim %d too large", dh);
@@ -242,14 +324,32 @@ int laff_mrl_forward_backward(const float* txt, const float* vis, int B, int H, 
   const bool need_grad = d_txt != nullptr || d_vis != nullptr;
   if (need_grad) LAFF_CUDA(cudaMemsetAsync(dS, 0, static_cast<size_t>(H) * B * B * 4, st));
   const int hthreads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
-  mrl_hinge_kernel<<<H, hthreads, 0, st>>>(S, B, B, static_cast<long long>(B) * B, margin, max_violation, direction,
-                                           cost_mean, head_loss, need_grad ? dS : nullptr); laff::count_launch();
+  if (kind == 0) {
+    mrl_hinge_kernel<<<H, hthreads, 0, st>>>(S, B, B, static_cast<long long>(B) * B, margin, max_violation, direction,
+                                             cost_mean, head_loss, need_grad ? dS : nullptr);
+  } else {
+    dsl_kernel<<<H, hthreads, static_cast<size_t>(5 * B + 32) * 4, st>>>(S, B, static_cast<long long>(B) * B, temp, head_loss,
+                                                                         need_grad ? dS : nullptr);
+  }
+  laff::count_launch();
   mrl_sum_heads_kernel<<<1, 32, 0, st>>>(head_loss, H, loss); laff::count_launch();
   const size_t gsm = static_cast<size_t>(dh + 32) * 4;
   if (d_vis) mrl_grad_kernel<<<dim3(B, H), 128, gsm, st>>>(dS, txt_hat, vis_hat, vis_nrm, B, H, dh, eps, 0, d_vis); laff::count_launch();
   if (d_txt) mrl_grad_kernel<<<dim3(B, H), 128, gsm, st>>>(dS, vis_hat, txt_hat, txt_nrm, B, H, dh, eps, 1, d_txt); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
+}
+
+int laff_mrl_forward_backward(const float* txt, const float* vis, int B, int H, int dh, float margin,
+                              int max_violation, int direction, int cost_mean, float* loss, float* d_txt,
+                              float* d_vis, void* workspace, size_t workspace_bytes, void* stream) {
+  return embedding_loss(0, txt, vis, B, H, dh, margin, max_violation, direction, cost_mean, 1.0f, loss, d_txt, d_vis, workspace,
+                        workspace_bytes, stream);
+}
+
+int laff_dsl_forward_backward(const float* txt, const float* vis, int B, int H, int dh, float temp, float* loss, float* d_txt,
+                              float* d_vis, void* workspace, size_t workspace_bytes, void* stream) {
+  return embedding_loss(1, txt, vis, B, H, dh, 0.f, 0, 0, 0, temp, loss, d_txt, d_vis, workspace, workspace_bytes, stream);
 }
 
 int laff_mrl_score_forward_backward(const float* score, int B, long long ld, float margin, int max_violation,

@@ -161,8 +161,10 @@ __global__ void __launch_bounds__(32 * kRowLanes)
   if (ok && threadIdx.y == 0 && dbias) dbias[c] = static_cast<float>(sbias);
 }
 
-// Backward of the LAFF block (Attention_1 without the mean residual / product variants, the shipped setting):
-//   e_l = w_h . y_l + c_h,  p = softmax_l(e),  g = sum_l p_l y_l,  out = g / (|g| + eps)
+// Backward of the LAFF block (Attention_1, model/Attention.py:78-105):
+//   r = mean_l y_l,  common_l = mul ? y_l * r : y_l,  e_l = w_h . common_l + c_h,  p = softmax_l(e),
+//   g = sum_l (p_l + omega') y_l  (omega' = with_ave ? omega : 0; omega is read with .item() by the reference, so it
+//   gets no gradient),  out = g / (|g| + eps).   The shipped setting is with_ave = mul = 0.
 // One warp per (row, head); lanes own d_h / 32 columns.  dW / dc are written per (row, head) and reduced afterwards
 // (deterministic).
 struct PoolBwdArgs {  // passed by value: nothing to upload, and a captured graph keeps its own copy
@@ -175,7 +177,8 @@ template <int VPL, int LMAX>
 __global__ void __launch_bounds__(128) pool_train_bwd_kernel(const __grid_constant__ PoolBwdArgs args, int L,
                                                              const float* __restrict__ att_w, const float* __restrict__ att_b,
                                                              const float* __restrict__ dout, long long ld_dout, long long rows, int heads,
-                                                             float norm_eps, float* __restrict__ dw_part, float* __restrict__ dc_part) {
+                                                             float norm_eps, int with_ave, int mul, float omega,
+                                                             float* __restrict__ dw_part, float* __restrict__ dc_part) {
   const float* const* ys = args.ys;
   float* const* dys = args.dys;
   const long long* lds = args.lds;
@@ -195,15 +198,29 @@ __global__ void __launch_bounds__(128) pool_train_bwd_kernel(const __grid_consta
     return x;
   };
   float emax = -INFINITY;
+  float rmean[VPL];  // r = mean over the features (only used by the product variant)
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) rmean[v] = 0.f;
+#pragma unroll
+  for (int l = 0; l < LMAX; ++l) {
+    if (l < L) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        y[l][v] = ys[l][row * lds[l] + col0 + v * 32 + lane];
+        rmean[v] += y[l][v];
+      }
+    }
+  }
+  const float invL = 1.0f / static_cast<float>(L);
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) rmean[v] *= invL;
+  const float wave = with_ave ? omega : 0.f;
 #pragma unroll
   for (int l = 0; l < LMAX; ++l) {
     if (l < L) {
       float part = 0.f;
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        y[l][v] = ys[l][row * lds[l] + col0 + v * 32 + lane];
-        part = fmaf(w[v], y[l][v], part);
-      }
+      for (int v = 0; v < VPL; ++v) part = fmaf(w[v], mul ? y[l][v] * rmean[v] : y[l][v], part);
       e[l] = wsum(part) + att_b[h];
       emax = fmaxf(emax, e[l]);
     }
@@ -223,7 +240,7 @@ __global__ void __launch_bounds__(128) pool_train_bwd_kernel(const __grid_consta
     if (l < L) {
       e[l] /= den;  // p_l
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) g[v] = fmaf(e[l], y[l][v], g[v]);
+      for (int v = 0; v < VPL; ++v) g[v] = fmaf(e[l] + wave, y[l][v], g[v]);
     }
   float ss = 0.f, dot = 0.f;
 #pragma unroll
@@ -250,9 +267,20 @@ __global__ void __launch_bounds__(128) pool_train_bwd_kernel(const __grid_consta
       dp[l] = wsum(part);
       mix = fmaf(e[l], dp[l], mix);
     }
-  float dwv[VPL], dcv = 0.f;
+  float dwv[VPL], dcv = 0.f, dmean[VPL];  // dmean = (1/L) sum_m de_m * w * y_m: gradient reaching every y_l through r
 #pragma unroll
-  for (int v = 0; v < VPL; ++v) dwv[v] = 0.f;
+  for (int v = 0; v < VPL; ++v) dwv[v] = dmean[v] = 0.f;
+  if (mul) {
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < L) {
+        const float de = e[l] * (dp[l] - mix);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) dmean[v] = fmaf(de * w[v], y[l][v], dmean[v]);
+      }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) dmean[v] *= invL;
+  }
 #pragma unroll
   for (int l = 0; l < LMAX; ++l)
     if (l < L) {
@@ -260,8 +288,10 @@ __global__ void __launch_bounds__(128) pool_train_bwd_kernel(const __grid_consta
       dcv += de;
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
-        dys[l][row * lds[l] + col0 + v * 32 + lane] = fmaf(e[l], dg[v], de * w[v]);
-        dwv[v] = fmaf(de, y[l][v], dwv[v]);
+        const float common = mul ? y[l][v] * rmean[v] : y[l][v];
+        const float through_e = mul ? de * w[v] * rmean[v] + dmean[v] : de * w[v];
+        dys[l][row * lds[l] + col0 + v * 32 + lane] = fmaf(e[l] + wave, dg[v], through_e);
+        dwv[v] = fmaf(de, common, dwv[v]);
       }
     }
 #pragma unroll
@@ -572,8 +602,8 @@ extern "C" int laff_transform_train_backward(const float* dy, long long ld_dy, c
 
 extern "C" int laff_attention_pool_backward(const float* const* ys, const long long* lds, int n_features, int heads,
                                             int head_dim, const float* att_weight, const float* att_bias, const float* dout,
-                                            long long ld_dout, long long rows, float norm_eps, float* const* dys, float* dw_part,
-                                            float* dc_part, float* dw, float* dc, void* stream) {
+                                            long long ld_dout, long long rows, float norm_eps, int with_ave, int mul, float omega,
+                                            float* const* dys, float* dw_part, float* dc_part, float* dw, float* dc, void* stream) {
   LAFF_REQUIRE(ys && lds && dys && att_weight && att_bias && dout && dw_part && dc_part && dw && dc && rows > 0,
                LAFF_EINVAL, "laff_attention_pool_backward: bad arguments");
   LAFF_REQUIRE(n_features >= 1 && n_features <= LAFF_MAX_FEATURES && heads > 0 && ld_dout >= static_cast<long long>(heads) * head_dim,
@@ -594,7 +624,7 @@ extern "C" int laff_attention_pool_backward(const float* const* ys, const long l
   const unsigned blocks = static_cast<unsigned>((warps + 3) / 4);
 #define LAFF_POOL_BWD(VPL)                                                                                                       \
   pool_train_bwd_kernel<VPL, LAFF_MAX_FEATURES><<<blocks, 128, 0, st>>>(args, n_features, att_weight, att_bias, dout, ld_dout, rows, \
-                                                                         heads, norm_eps, dw_part, dc_part)
+                                                                         heads, norm_eps, with_ave, mul, omega, dw_part, dc_part)
   switch (head_dim) {
     case 32: LAFF_POOL_BWD(1); break;
     case 64: LAFF_POOL_BWD(2); break;

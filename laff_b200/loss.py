@@ -88,6 +88,29 @@ class _MRLScoreFunction(torch.autograd.Function):
         return g * d, None, None, None, None
 
 
+class _DSLFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, im, temp):
+        need = s.requires_grad or im.requires_grad
+        loss, d_s, d_im = ops.dsl_forward_backward(s, im, temp, need_grad=need)
+        ctx.shape = s.shape
+        ctx.save_for_backward(d_s, d_im) if need else None
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d_s, d_im = ctx.saved_tensors
+        return g * d_s.reshape(ctx.shape), g * d_im.reshape(ctx.shape), None
+
+
+class DualSoftmaxLoss(nn.Module):
+    """loss.py:291-310.  forward(s, im, temp=1000) on [B, d] embeddings; [B, H, d] inputs return the sum over heads
+    (model/model.py:2036-2038 applies the criterion head by head)."""
+
+    def forward(self, s, im, temp=1000):
+        return _DSLFunction.apply(s, im, float(temp))
+
+
 class MarginRankingLoss(nn.Module):
     """Margin ranking loss on (sentence, image/video) embedding batches (loss.py:68-135).
 

@@ -28,7 +28,7 @@ import torch.nn as nn
 
 from . import ops
 from . import loss as _loss
-from .loss import MarginRankingLoss, MarginRankingLossWithScore
+from .loss import DualSoftmaxLoss, MarginRankingLoss, MarginRankingLossWithScore
 
 _PARAM_EPOCH = 0  # bumped by the device optimizer step, which updates parameters through raw pointers
 
@@ -628,10 +628,15 @@ class W2VVPP(nn.Module):
         self._init_txt_net(opt)
         self.opt = opt
         self.grad_clip = getattr(opt, "grad_clip", 2)
-        if getattr(opt, "loss", "mrl") != "mrl":
-            raise NotImplementedError("loss %r is outside the LAFF hot path (shipped configs use 'mrl')" % opt.loss)
-        self.criterion = MarginRankingLoss(margin=opt.margin, measure=opt.measure, max_violation=opt.max_violation,
-                                           cost_style=opt.cost_style, direction=opt.direction)
+        kind = getattr(opt, "loss", "mrl")
+        if kind == "mrl":
+            self.criterion = MarginRankingLoss(margin=opt.margin, measure=opt.measure, max_violation=opt.max_violation,
+                                               cost_style=opt.cost_style, direction=opt.direction)
+        elif kind == "dsl":
+            self.criterion = DualSoftmaxLoss()                                          # model/model.py:1995-1996
+        else:
+            raise NotImplementedError("loss %r: the reference's CELoss is dead code (its cal_loss signature does not match "
+                                      "its call, loss.py:275-285); 'mrl' and 'dsl' are built" % kind)
         self.criterion_with_score = MarginRankingLossWithScore(margin=opt.margin, max_violation=opt.max_violation,
                                                                cost_style=opt.cost_style, direction=opt.direction)
         self.iters = 0
@@ -719,7 +724,10 @@ class W2VVPP(nn.Module):
                 step = self._steps[key] = FusionTrainStep(att, precision)
             outs[key] = step.forward(feats, self._seed_base * 2 + (key == "vis"), self._seed_dev)
         c = self.criterion
-        loss, d_txt, d_vis = ops.mrl_forward_backward(outs["txt"], outs["vis"], c.margin, c.max_violation, c.direction, c.cost_style)
+        if isinstance(c, DualSoftmaxLoss):
+            loss, d_txt, d_vis = ops.dsl_forward_backward(outs["txt"], outs["vis"], 1000.0)
+        else:
+            loss, d_txt, d_vis = ops.mrl_forward_backward(outs["txt"], outs["vis"], c.margin, c.max_violation, c.direction, c.cost_style)
         self._steps["txt"].backward(d_txt)
         dxs = self._steps["vis"].backward(d_vis)
         for idx, (name, frames) in pooled.items():
@@ -783,7 +791,7 @@ class W2VVPP(nn.Module):
             loss = g["loss"].clone()
         else:
             loss = self._train_step_device(txt, vis, precision)
-            if self.use_cuda_graph and self.iters >= 3:
+            if self.use_cuda_graph and self.iters >= 3 and all(st.capturable for st in self._steps.values()):
                 self._graph = self._capture_train_graph(txt, vis, precision, sig)
         _PARAM_EPOCH += 1  # parameters changed behind torch's version counters: drop the eval-mode operand caches
         return {"triplet_loss": loss}

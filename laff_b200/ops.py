@@ -529,6 +529,24 @@ def mrl_forward_backward(txt: torch.Tensor, vis: torch.Tensor, margin: float, ma
     return loss, d_txt, d_vis
 
 
+def dsl_forward_backward(txt: torch.Tensor, vis: torch.Tensor, temp: float = 1000.0, need_grad: bool = True):
+    """Sum over heads of DualSoftmaxLoss(s=txt[:,h], im=vis[:,h], temp) (loss.py:291-310); (loss, d_txt, d_vis)."""
+    _need_cuda(txt, vis)
+    if txt.dim() == 2:
+        txt, vis = txt.unsqueeze(1), vis.unsqueeze(1)
+    txt = txt.detach().float().contiguous()
+    vis = vis.detach().float().contiguous()
+    B, H, dh = txt.shape
+    loss = torch.empty((), dtype=torch.float32, device=txt.device)
+    d_txt = torch.empty_like(txt) if need_grad else None
+    d_vis = torch.empty_like(vis) if need_grad else None
+    nbytes = _capi.lib().laff_mrl_workspace_bytes(B, H, dh)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=txt.device)
+    _capi.call("laff_dsl_forward_backward", _ptr(txt), _ptr(vis), B, H, dh, float(temp), _ptr(loss), _ptr(d_txt), _ptr(d_vis),
+               _ptr(ws), nbytes, _stream(txt))
+    return loss, d_txt, d_vis
+
+
 def mrl_score_forward_backward(score: torch.Tensor, margin: float, max_violation: bool, direction: str,
                                cost_style: str, need_grad: bool = True):
     _need_cuda(score)
@@ -587,8 +605,9 @@ def transform_train_backward(dy: torch.Tensor, a: Optional[torch.Tensor], tiled_
 
 
 def attention_pool_backward(ys: Sequence[torch.Tensor], att_weight: torch.Tensor, att_bias: torch.Tensor, heads: int, head_dim: int,
-                            dout: torch.Tensor, dw: torch.Tensor, dc: torch.Tensor, norm_eps: float = 1e-14):
-    """Backward of the LAFF block (with_ave = mul = False).  ys: the L inputs fp32 [rows, H*d_h]; dout [rows, H*d_h];
+                            dout: torch.Tensor, dw: torch.Tensor, dc: torch.Tensor, norm_eps: float = 1e-14, with_ave: bool = False,
+                            mul: bool = False, omega: float = 0.0):
+    """Backward of the LAFF block.  ys: the L inputs fp32 [rows, H*d_h]; dout [rows, H*d_h];
     dw [H, d_h] / dc [H] receive the gradients of the logit weights / biases.  Returns the list of dy_l."""
     _need_cuda(dout, att_weight, att_bias, dw, dc, *ys)
     rows, D = dout.shape
@@ -603,8 +622,8 @@ def attention_pool_backward(ys: Sequence[torch.Tensor], att_weight: torch.Tensor
     dc_part = torch.empty(rows * heads, dtype=torch.float32, device=dev)
     dout = _rowmajor(dout)
     _capi.call("laff_attention_pool_backward", yp, lds, n, heads, head_dim, _ptr(att_weight), _ptr(att_bias),
-               _ptr(dout), dout.stride(0), rows, float(norm_eps), dp, _ptr(dw_part), _ptr(dc_part), _ptr(dw), _ptr(dc),
-               _stream(dout))
+               _ptr(dout), dout.stride(0), rows, float(norm_eps), int(bool(with_ave)), int(bool(mul)), float(omega), dp,
+               _ptr(dw_part), _ptr(dc_part), _ptr(dw), _ptr(dc), _stream(dout))
     return dys
 
 

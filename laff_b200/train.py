@@ -45,9 +45,10 @@ class FusionTrainStep:
     """Train-mode forward + backward of one fusion net: a list of (x, TransformNet) features and its attention layer."""
 
     def __init__(self, attention, precision: str = "bf16x3"):
-        if getattr(attention, "with_ave", False) or getattr(attention, "mul", False):
-            raise NotImplementedError("training the mean-residual / product attention variants is not built (shipped: off)")
         self.att = attention
+        # mean-residual / product variants (ablations; shipped: off): omega is read with .item() like the reference does
+        # (model/Attention.py:96) — a host synchronisation, so steps of these variants are not graph-captured
+        self.capturable = not (getattr(attention, "with_ave", False) or getattr(attention, "mul", False))
         self.precision = precision
         self.cache: Optional[dict] = None
 
@@ -79,8 +80,9 @@ class FusionTrainStep:
         ps = [att.attention_layer[h].embedding_common[0] for h in range(H)]
         w = torch.cat([q.weight.detach().view(1, -1) for q in ps], 0).float().contiguous()
         b = torch.cat([q.bias.detach().view(1) for q in ps], 0).float().contiguous()
-        out, _, _ = ops.attention_pool([{"y": it["y"]} for it in items], w, b, H, dh)
-        self.cache = {"items": items, "w": w, "b": b, "heads": ps}
+        omega = float(att.attention_layer[0].global_emb_weight_net.weight.item()) if att.with_ave else 0.0
+        out, _, _ = ops.attention_pool([{"y": it["y"]} for it in items], w, b, H, dh, att.with_ave, att.mul, omega=omega)
+        self.cache = {"items": items, "w": w, "b": b, "heads": ps, "omega": omega}
         return out
 
     def backward(self, dout: torch.Tensor) -> Dict[int, torch.Tensor]:
@@ -98,7 +100,8 @@ class FusionTrainStep:
         if dw is None or dw.device != dev:
             self._dw = dw = torch.zeros((H, dh), dtype=torch.float32, device=dev)
             self._dc = torch.zeros(H, dtype=torch.float32, device=dev)
-        dys = ops.attention_pool_backward([it["y"] for it in c["items"]], c["w"], c["b"], H, dh, dout, dw, self._dc)
+        dys = ops.attention_pool_backward([it["y"] for it in c["items"]], c["w"], c["b"], H, dh, dout, dw, self._dc,
+                                          with_ave=att.with_ave, mul=att.mul, omega=c["omega"])
         for h, q in enumerate(c["heads"]):  # per-head parameters: gradients are views of the two stacked buffers
             q.weight.grad = dw[h:h + 1]
             q.bias.grad = self._dc[h:h + 1]

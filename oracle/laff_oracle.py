@@ -300,7 +300,8 @@ def _act_grad(a: np.ndarray, name) -> np.ndarray:
 
 
 def fusion_train_forward(feats: Sequence[Tuple[str, np.ndarray]], sd: dict, prefixes: Mapping[str, str], att_prefix: str,
-                         heads: int, no_transform: Sequence[str], activation="tanh", momentum=0.1, eps=1e-5):
+                         heads: int, no_transform: Sequence[str], activation="tanh", momentum=0.1, eps=1e-5, with_ave=False,
+                         mul=False):
     """Train-mode forward of one fusion net (TransformNet.forward with batch-statistics BatchNorm, dropout p = 0;
     model/model.py:257-276, :1807-1876) followed by the multi-head LAFF block.  Updates the running statistics in `sd`
     in place like nn.BatchNorm1d.  Returns (embeddings [B, H, d_h], cache for fusion_train_backward)."""
@@ -332,13 +333,17 @@ def fusion_train_forward(feats: Sequence[Tuple[str, np.ndarray]], sd: dict, pref
     Yh = Y.reshape(B, L, heads, dh)
     W = np.stack([sd["%sattention_layer.%d.embedding_common.0.weight" % (att_prefix, h)].reshape(-1) for h in range(heads)]).astype(np.float64)
     c = np.array([sd["%sattention_layer.%d.embedding_common.0.bias" % (att_prefix, h)].reshape(-1)[0] for h in range(heads)], dtype=np.float64)
-    e = np.einsum("blhd,hd->bhl", Yh, W) + c[None, :, None]
+    r = Yh.mean(1)                                                                # [B, H, dh]   model/Attention.py:81
+    common = Yh * r[:, None] if mul else Yh                                       # :83-86
+    e = np.einsum("blhd,hd->bhl", common, W) + c[None, :, None]
     p = softmax(e, axis=2)
-    g = np.einsum("bhl,blhd->bhd", p, Yh)
+    omega = np.array([float(sd["%sattention_layer.%d.global_emb_weight_net.weight" % (att_prefix, h)].reshape(-1)[0])
+                      for h in range(heads)]) if with_ave else np.zeros(heads)    # read with .item(): a constant (:96)
+    g = np.einsum("bhl,blhd->bhd", p + omega[None, :, None], Yh)
     nrm = np.sqrt((g * g).sum(-1, keepdims=True))
     out = g / (nrm + 1e-14)
     return out, {"items": items, "Yh": Yh, "W": W, "p": p, "g": g, "nrm": nrm, "out": out, "heads": heads, "att_prefix": att_prefix,
-                 "activation": activation}
+                 "activation": activation, "r": r, "common": common, "omega": omega, "mul": mul}
 
 
 def fusion_train_backward(cache: dict, dout: np.ndarray, sd: Mapping[str, np.ndarray]) -> dict:
@@ -350,11 +355,16 @@ def fusion_train_backward(cache: dict, dout: np.ndarray, sd: Mapping[str, np.nda
     dg = (dout - out * dot * nrm * inv) * inv
     dp = np.einsum("bhd,blhd->bhl", dg, Yh)
     de = p * (dp - (p * dp).sum(-1, keepdims=True))
-    dY = np.einsum("bhl,bhd->blhd", p, dg) + np.einsum("bhl,hd->blhd", de, W)
+    dY = np.einsum("bhl,bhd->blhd", p + cache["omega"][None, :, None], dg)
+    dcommon = np.einsum("bhl,hd->blhd", de, W)
+    if cache["mul"]:
+        dY = dY + dcommon * cache["r"][:, None] + (dcommon * Yh).sum(1, keepdims=True) / L
+    else:
+        dY = dY + dcommon
     grads = {}
     for h in range(H):
         pre = "%sattention_layer.%d.embedding_common.0." % (cache["att_prefix"], h)
-        grads[pre + "weight"] = np.einsum("bl,bld->d", de[:, h, :], Yh[:, :, h, :]).reshape(1, dh)
+        grads[pre + "weight"] = np.einsum("bl,bld->d", de[:, h, :], cache["common"][:, :, h, :]).reshape(1, dh)
         grads[pre + "bias"] = de[:, h, :].sum().reshape(1)
     dY = dY.reshape(B, L, H * dh)
     cache["dx"] = {}
@@ -418,16 +428,24 @@ def clip_and_step(sd: dict, grads: Mapping[str, np.ndarray], state: dict, optimi
 
 
 def laff_train_step(sd: dict, vis_in: Mapping[str, np.ndarray], txt_in: Mapping[str, np.ndarray], state: dict, heads: int,
-                    vis_no_transform: Sequence[str], optimizer="rmsprop", lr=1e-4, grad_clip=2.0, margin=0.2, adam_eps=1e-4):
+                    vis_no_transform: Sequence[str], optimizer="rmsprop", lr=1e-4, grad_clip=2.0, margin=0.2, adam_eps=1e-4,
+                    with_ave=False, mul=False, loss_kind="mrl"):
     """W2VVPP_MultiHeadAttention.forward(train_data) (model/model.py:964-1001 with :2021-2048): one step on the full
     model state dict (keys 'vis_net.*' / 'txt_net.*'), dropout 0.  Returns (loss, clipped gradients, grad norm)."""
     vfe = [(n, x) for n, x in vis_in.items()]
     vpre = {n: "vis_net.VisMutiTransformNet.%s." % n for n in vis_in}
     tfe = [(TXT_FEATURE_KEY[e], txt_in[TXT_FEATURE_KEY[e]]) for e in TXT_ENCODER_ORDER if TXT_FEATURE_KEY[e] in txt_in]
     tpre = {TXT_FEATURE_KEY[e]: "txt_net.transform_layer.%s_transform." % e for e in TXT_ENCODER_ORDER}
-    t_emb, tc = fusion_train_forward(tfe, sd, tpre, "txt_net.attention_layer.", heads, ["clip"])
-    v_emb, vc = fusion_train_forward(vfe, sd, vpre, "vis_net.attention_layer.", heads, vis_no_transform)
-    loss, d_txt, d_vis = multi_head_loss(t_emb, v_emb, margin, True, "sum", "t2i", want_grad=True)
+    t_emb, tc = fusion_train_forward(tfe, sd, tpre, "txt_net.attention_layer.", heads, ["clip"], with_ave=with_ave, mul=mul)
+    v_emb, vc = fusion_train_forward(vfe, sd, vpre, "vis_net.attention_layer.", heads, vis_no_transform, with_ave=with_ave, mul=mul)
+    if loss_kind == "dsl":                                                        # model/model.py:1995-1996, :2036-2038
+        loss, d_txt, d_vis = 0.0, np.zeros_like(t_emb), np.zeros_like(v_emb)
+        for h in range(heads):
+            l, a, b = dual_softmax_loss(t_emb[:, h], v_emb[:, h], 1000.0, want_grad=True)
+            loss += l
+            d_txt[:, h], d_vis[:, h] = a, b
+    else:
+        loss, d_txt, d_vis = multi_head_loss(t_emb, v_emb, margin, True, "sum", "t2i", want_grad=True)
     grads = {}
     grads.update(fusion_train_backward(tc, d_txt, sd))
     grads.update(fusion_train_backward(vc, d_vis, sd))
@@ -678,6 +696,37 @@ def multi_head_loss(txt_embs: np.ndarray, vis_embs: np.ndarray, margin=0.2, max_
         else:
             total = total + r
     return (total, d_txt, d_vis) if want_grad else total
+
+
+def dual_softmax_loss(s: np.ndarray, im: np.ndarray, temp=1000.0, want_grad: bool = False):
+    """DualSoftmaxLoss.forward(s, im, temp) (loss.py:291-310) on [B, d] embeddings, in float64; with want_grad also
+    (d loss / d s, d loss / d im) through cosine_sim's normalisation."""
+    s64, im64 = s.astype(np.float64), im.astype(np.float64)
+    eps = 1e-13 + 1e-14
+    ns, ni = np.sqrt((s64 ** 2).sum(1, keepdims=True)), np.sqrt((im64 ** 2).sum(1, keepdims=True))
+    sh, ih = s64 / (ns + eps), im64 / (ni + eps)
+    sim = sh @ ih.T
+    B = sim.shape[0]
+
+    def term(A):
+        P0 = softmax(A / temp, axis=0)
+        M = A * P0 * B
+        L = M - M.max(1, keepdims=True)
+        logp = L - np.log(np.exp(L).sum(1, keepdims=True))
+        loss = -np.trace(logp)
+        dM = np.exp(logp) - np.eye(B)
+        dP0 = B * A * dM
+        dA = B * P0 * dM + P0 * (dP0 - (P0 * dP0).sum(0, keepdims=True)) / temp
+        return loss, dA
+
+    l1, d1 = term(sim)
+    l2, d2 = term(sim.T)
+    loss = (l1 + l2) / 2
+    if not want_grad:
+        return loss
+    dsim = (d1 + d2.T) / 2
+    gs, gi = dsim @ ih, dsim.T @ sh
+    return loss, _l2norm_backward(s64, gs, eps), _l2norm_backward(im64, gi, eps)
 
 
 def margin_ranking_loss_with_score(score: np.ndarray, margin=0.0, max_violation=False, cost_style="sum",

@@ -20,19 +20,21 @@ from laff_b200 import synth  # noqa: E402
 SMALL = mg.SMALL
 
 
-def run_case(mm, tag, optimizer, lr, batch_norm, steps=3, B=16, D=256, H=8, seed=81):
+def run_case(mm, tag, optimizer, lr, batch_norm, steps=3, B=16, D=256, H=8, seed=81, with_ave=False, mul=False, loss="mrl"):
     import torch
     dims = SMALL
     vis_dims = {synth.VIS_CLIP_FT: dims["clip"], synth.VIS_TF: dims["tf"], synth.VIS_X3D: dims["x3d"], synth.VIS_IRCSN: dims["ircsn"]}
-    cfg = mg.make_config("laff", D, H, vis_dims, dims)
+    cfg = mg.make_config("laff", D, H, vis_dims, dims, with_ave, mul)
     cfg.dropout = 0.0
     cfg.batch_norm = batch_norm
     cfg.optimizer, cfg.lr = optimizer, lr
+    cfg.loss = loss
     torch.manual_seed(0)
     model = mm.W2VVPP_MultiHeadAttention(cfg)
-    sd0 = mg.load_synth_state(model, seed)
+    sd0 = mg.load_synth_state(model, seed, omega=0.6 if with_ave else 1.0)
     model.train()
-    out = {"meta": np.array([B, D, H, steps, seed, int(batch_norm)]), "optimizer": np.array(optimizer), "lr": np.float64(lr),
+    out = {"meta": np.array([B, D, H, steps, seed, int(batch_norm), 0, int(with_ave), int(mul)]), "loss_kind": np.array(loss),
+           "optimizer": np.array(optimizer), "lr": np.float64(lr),
            "grad_clip": np.float64(cfg.grad_clip), "vis_names": np.array(list(vis_dims.keys()))}
     for k, v in sd0.items():
         out["sd0/" + k] = v
@@ -124,6 +126,11 @@ def main():
     for tag, optimizer, lr, bn in (("rmsprop", "rmsprop", 1e-3, False), ("adam", "adam", 1e-3, False), ("rmsprop_bn", "rmsprop", 1e-3, True)):
         if not only or tag in only:
             np.savez_compressed(os.path.join(HERE, "train_%s.npz" % tag), **run_case(mm, tag, optimizer, lr, bn))
+    if not only or "rmsprop_ave_mul" in only:
+        np.savez_compressed(os.path.join(HERE, "train_rmsprop_ave_mul.npz"),
+                            **run_case(mm, "rmsprop_ave_mul", "rmsprop", 1e-3, False, with_ave=True, mul=True))
+    if not only or "adam_dsl" in only:
+        np.savez_compressed(os.path.join(HERE, "train_adam_dsl.npz"), **run_case(mm, "adam_dsl", "adam", 1e-3, False, loss="dsl"))
     if not only or "frame_rmsprop" in only:
         np.savez_compressed(os.path.join(HERE, "train_frame_rmsprop.npz"), **run_frame_case(mm, "frame_rmsprop", "rmsprop", 1e-3))
 

@@ -24,7 +24,10 @@ SMALL = dict(clip=32, gru=40, bow=56, w2v=20, x3d=40, ircsn=48, tf=24, c3d=40)
 
 
 def build_model(g, sd, H, D):
-    c = cfg.laff_config(D, H, SMALL)
+    from test_train_cpu import variant
+    with_ave, mul, loss_kind = variant(g)
+    c = cfg.laff_config(D, H, SMALL, with_ave=with_ave, mul=mul)
+    c.loss = loss_kind
     c.dropout = 0.0
     c.batch_norm = bool(int(g["meta"][5]))
     c.optimizer, c.lr, c.grad_clip = str(g["optimizer"]), float(g["lr"]), float(g["grad_clip"])
@@ -38,7 +41,7 @@ def train_data(vis_in, txt_in):
             "captions_task2": None, "vis_frame_feat_dict": {}, "vis_origin_frame_tuple": None}
 
 
-@pytest.mark.parametrize("tag", ["rmsprop", "adam", "rmsprop_bn"])
+@pytest.mark.parametrize("tag", ["rmsprop", "adam", "rmsprop_bn", "rmsprop_ave_mul", "adam_dsl"])
 def test_train_steps_match_reference(tag):
     g, sd, H, steps = load_case(tag)
     D = int(g["meta"][1])
@@ -204,3 +207,27 @@ def test_laff_ml_train_steps_match_reference():
                 assert np.abs(got - ref).max() <= 1e-4 * max(1e-3, np.abs(ref).max()), (k, np.abs(got - ref).max())
         check_params({k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}, g, s, float(g["lr"]), tight0=5e-5, frac=0.97)
     assert model._graph is not None
+
+
+def test_dual_softmax_loss_kernel_vs_reference_autograd():
+    """laff_dsl_forward_backward (loss.py:291-310) against the reference's value and autograd gradients."""
+    from laff_b200 import loss as L
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dsl.npz"))
+    for tag in ("small", "b128"):
+        txt, vis = torch.from_numpy(d[tag + "/txt"]).cuda(), torch.from_numpy(d[tag + "/vis"]).cuda()
+        loss, d_txt, d_vis = ops.dsl_forward_backward(txt, vis, 1000.0)
+        ref = float(d[tag + "/loss"])
+        assert abs(loss.item() - ref) <= 1e-5 * abs(ref), (tag, loss.item(), ref)
+        for got, key in ((d_txt, "/d_txt"), (d_vis, "/d_vis")):
+            r = d[tag + key]
+            assert np.abs(got.cpu().numpy() - r).max() <= 1e-4 * np.abs(r).max(), (tag, key)
+        for temp in (1.0, 0.05):
+            l2, a, b = ops.dsl_forward_backward(txt[:, 0].contiguous(), vis[:, 0].contiguous(), temp)
+            r = float(d["%s/temp%g/loss" % (tag, temp)])
+            assert abs(l2.item() - r) <= 2e-5 * abs(r)
+            assert np.abs(a.cpu().numpy()[:, 0] - d["%s/temp%g/d_txt" % (tag, temp)]).max() <= 2e-4 * np.abs(d["%s/temp%g/d_txt" % (tag, temp)]).max()
+        # module surface + autograd plumbing
+        t = txt.clone().requires_grad_(True)
+        out = L.DualSoftmaxLoss()(t, vis)
+        out.backward()
+        assert abs(out.item() - ref) <= 1e-5 * abs(ref) and torch.equal(t.grad, d_txt)

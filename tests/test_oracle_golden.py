@@ -195,3 +195,26 @@ def test_retrieve_cpu_matches_tie_rule():
     np.testing.assert_array_equal(rank0, O.tie_rule_rank(s, gt))
     np.testing.assert_array_equal(topk, O.tie_rule_topk(s, 5)[1])
     assert m == O.metrics_from_rank0(rank0)
+
+
+def test_dual_softmax_loss_oracle_matches_reference_autograd():
+    """DualSoftmaxLoss (loss.py:291-310): value and autograd gradients of the unmodified reference (tests/golden/dsl.npz)."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dsl.npz"))
+    for tag in ("small", "b128"):
+        txt, vis = d[tag + "/txt"], d[tag + "/vis"]
+        total, gt_, gv_ = 0.0, np.zeros_like(txt, dtype=np.float64), np.zeros_like(vis, dtype=np.float64)
+        for h in range(txt.shape[1]):
+            l, a, b = O.dual_softmax_loss(txt[:, h], vis[:, h], 1000.0, want_grad=True)
+            assert abs(l - d[tag + "/per_head"][h]) <= 1e-5 * abs(d[tag + "/per_head"][h])
+            total += l
+            gt_[:, h], gv_[:, h] = a, b
+        assert abs(total - float(d[tag + "/loss"])) <= 1e-5 * abs(float(d[tag + "/loss"]))
+        for got, key in ((gt_, "/d_txt"), (gv_, "/d_vis")):
+            ref = d[tag + key]
+            assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
+        for temp in (1.0, 0.05):
+            l, a, b = O.dual_softmax_loss(txt[:, 0], vis[:, 0], temp, want_grad=True)
+            assert abs(l - float(d["%s/temp%g/loss" % (tag, temp)])) <= 1e-5 * abs(float(d["%s/temp%g/loss" % (tag, temp)]))
+            assert np.abs(a - d["%s/temp%g/d_txt" % (tag, temp)]).max() <= 1e-4 * np.abs(d["%s/temp%g/d_txt" % (tag, temp)]).max()
+            assert np.abs(b - d["%s/temp%g/d_vis" % (tag, temp)]).max() <= 1e-4 * np.abs(d["%s/temp%g/d_vis" % (tag, temp)]).max()

@@ -40,14 +40,22 @@ def check_params(sd, g, s, lr, tight0=3e-5, frac=0.99):
             assert bad <= max(1, int((1 - frac) * err.size)), (k, s, bad, err.size)
 
 
-@pytest.mark.parametrize("tag", ["rmsprop", "adam", "rmsprop_bn"])
+def variant(g):
+    """(with_ave, mul, loss kind) of a golden training case (older files: the shipped setting)."""
+    m = [int(x) for x in g["meta"]]
+    return (bool(m[7]), bool(m[8]), str(g["loss_kind"])) if len(m) > 8 else (False, False, "mrl")
+
+
+@pytest.mark.parametrize("tag", ["rmsprop", "adam", "rmsprop_bn", "rmsprop_ave_mul", "adam_dsl"])
 def test_oracle_train_steps_match_reference(tag):
     g, sd, H, steps = load_case(tag)
     state = {}
     opt, lr, clip = str(g["optimizer"]), float(g["lr"]), float(g["grad_clip"])
+    with_ave, mul, loss_kind = variant(g)
     for s in range(steps):
         vis_in, txt_in = step_inputs(g, s)
-        loss, grads, total = O.laff_train_step(sd, vis_in, txt_in, state, H, [synth.VIS_CLIP_FT], opt, lr, clip)
+        loss, grads, total = O.laff_train_step(sd, vis_in, txt_in, state, H, [synth.VIS_CLIP_FT], opt, lr, clip, with_ave=with_ave,
+                                               mul=mul, loss_kind=loss_kind)
         assert abs(loss - g["losses"][s]) <= 2e-5 * abs(g["losses"][s]), (tag, s, loss, g["losses"][s])
         if s == 0:
             ref_keys = [k[6:] for k in g.files if k.startswith("grad0/")]
