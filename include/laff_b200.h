@@ -194,6 +194,19 @@ int laff_gather_rows(const float* table, long long ld_table, long long n_table, 
 int laff_gru_cell(const float* gi, long long ld_gi, const float* gh, long long ld_gh, const float* h_prev,
                   const int32_t* lengths, int t, int B, int H, float* h_out, float* sum, float* last, void* stream);
 int laff_mean_over_length(float* x, const int32_t* lengths, int B, int H, void* stream);
+/* Training the GRU sentence encoder (backward through time; the reference leaves it to autograd, model/model.py:340-387):
+ *   laff_gru_cell_backward  one step of BPTT.  dh_carry [B, H] (in/out): gradient reaching h_t through the z * h path;
+ *                           dh_gemm (nullable): the part through W_hh (dGh_{t+1} @ W_hh, a GEMM of the caller);
+ *                           dmean / dlast (nullable): d loss / d pooled output for 'mean' (divided by the length here)
+ *                           and 'last' pooling.  Writes dgi_t, dgh_t [B, 3H]; sequences with lengths[b] <= t pass dh on.
+ *   laff_scatter_add_rows   nn.Embedding backward: table_grad[ids[i]] += dx[i] (caller zeroes table_grad).
+ *   laff_column_sum         out[c] = sum_r x[r, c] in a fixed order (bias gradients). */
+int laff_gru_cell_backward(const float* gi, long long ld_gi, const float* gh, long long ld_gh, const float* h_prev,
+                           const float* dmean, const float* dlast, const float* dh_gemm, const int32_t* lengths, int t, int B,
+                           int H, float* dh_carry, float* dgi, long long ld_dgi, float* dgh, long long ld_dgh, void* stream);
+int laff_scatter_add_rows(const float* dx, long long ld, const int32_t* ids, long long n, int dim, long long n_table,
+                          float* table_grad, long long ld_table, void* stream);
+int laff_column_sum(const float* x, long long ld, long long rows, int cols, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * F1  TransformNet.forward (model/model.py:257-276): y = BN(act(x W^T + b)), eval mode (dropout = identity,

@@ -115,6 +115,9 @@ SIGNATURES = {
     "laff_gather_rows": (_i, [_vp, _ll, _ll, _vp, _ll, _i, _vp, _ll, _vp]),
     "laff_gru_cell": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "laff_mean_over_length": (_i, [_vp, _vp, _i, _i, _vp]),
+    "laff_gru_cell_backward": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _vp]),
+    "laff_scatter_add_rows": (_i, [_vp, _ll, _vp, _ll, _i, _ll, _vp, _ll, _vp]),
+    "laff_column_sum": (_i, [_vp, _ll, _ll, _i, _vp, _vp]),
     "laff_label_metrics": (_i, [_vp, _i, _i, _ll, _vp, _vp, _vp, _vp]),
     "laff_project": (_i, [_vp, _vp, _ll, _i, _i, _ll, _ll, _i, _vp, _i, _vp, _vp, _vp, _ll, _vp]),
     "laff_bn_fold": (_i, [_vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _vp]),

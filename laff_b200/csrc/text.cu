@@ -81,6 +81,80 @@ __global__ void gru_cell_kernel(const float* __restrict__ gi, long long ld_gi, c
   if (last && t == len - 1) last[i] = h;
 }
 
+// Backward of one GRU step (BPTT).  dh_carry [B, H] holds d loss / d h_t flowing in from step t + 1 through the
+// z * h path, dh_gemm (may be NULL) the part that came through W_hh (dGh_{t+1} @ W_hh, computed by the GEMM engine).
+// The pooling's own contribution is added here: mean -> dout / len for t < len, last -> dlast at t == len - 1.
+// Outputs: dgi_t, dgh_t [B, 3H] (gate order r, z, n) and the new dh_carry (= dh * z, or dh unchanged on frozen steps).
+__global__ void gru_cell_bwd_kernel(const float* __restrict__ gi, long long ld_gi, const float* __restrict__ gh, long long ld_gh,
+                                    const float* __restrict__ h_prev, const float* __restrict__ dmean, const float* __restrict__ dlast,
+                                    const float* __restrict__ dh_gemm, const int32_t* __restrict__ lengths, int t, int B, int H,
+                                    float* __restrict__ dh_carry, float* __restrict__ dgi, long long ld_dgi, float* __restrict__ dgh,
+                                    long long ld_dgh) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * H) return;
+  const int b = static_cast<int>(i / H), j = static_cast<int>(i - static_cast<long long>(b) * H);
+  const int len = lengths[b];
+  float dh = dh_carry[i] + (dh_gemm ? dh_gemm[i] : 0.f);
+  float* dgib = dgi + b * ld_dgi;
+  float* dghb = dgh + b * ld_dgh;
+  if (t >= len) {  // the state was carried through unchanged
+    dgib[j] = dgib[H + j] = dgib[2 * H + j] = 0.f;
+    dghb[j] = dghb[H + j] = dghb[2 * H + j] = 0.f;
+    dh_carry[i] = dh;
+    return;
+  }
+  if (dmean) dh += dmean[i] / static_cast<float>(len);
+  if (dlast && t == len - 1) dh += dlast[i];
+  const float* gib = gi + b * ld_gi;
+  const float* ghb = gh + b * ld_gh;
+  const float r = sigmoid_acc(gib[j] + ghb[j]);
+  const float z = sigmoid_acc(gib[H + j] + ghb[H + j]);
+  const float ghn = ghb[2 * H + j];
+  const float n = tanhf(gib[2 * H + j] + r * ghn);
+  const float hp = h_prev[i];
+  const float dn = dh * (1.0f - z);
+  const float dz = dh * (hp - n);
+  const float dpre_n = dn * (1.0f - n * n);
+  const float dpre_z = dz * z * (1.0f - z);
+  const float dpre_r = dpre_n * ghn * r * (1.0f - r);
+  dgib[j] = dpre_r;
+  dgib[H + j] = dpre_z;
+  dgib[2 * H + j] = dpre_n;
+  dghb[j] = dpre_r;
+  dghb[H + j] = dpre_z;
+  dghb[2 * H + j] = dpre_n * r;
+  dh_carry[i] = dh * z;
+}
+
+// nn.Embedding backward: table_grad[ids[i], :] += dx[i, :]  (table_grad zeroed by the caller; fp32 atomics)
+__global__ void scatter_add_rows_kernel(const float* __restrict__ dx, long long ld, const int32_t* __restrict__ ids, long long n,
+                                        int dim, long long n_table, float* __restrict__ table_grad, long long ld_t) {
+  const long long row = blockIdx.x;
+  if (row >= n) return;
+  const long long id = ids[row];
+  if (id < 0 || id >= n_table) return;
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+    const float v = dx[row * ld + c];
+    if (v != 0.f) atomicAdd(table_grad + id * ld_t + c, v);
+  }
+}
+
+// out[c] = sum_r x[r, c] in a fixed order (bias gradients)
+__global__ void column_sum_kernel(const float* __restrict__ x, long long ld, long long rows, int cols, float* __restrict__ out) {
+  __shared__ double sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0;
+  if (c < cols)
+    for (long long r = threadIdx.y; r < rows; r += 8) s += x[r * ld + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+    out[c] = static_cast<float>(t);
+  }
+}
+
 __global__ void scale_rows_by_length_kernel(float* __restrict__ x, const int32_t* __restrict__ lengths, int B, int H) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(B) * H) return;
@@ -150,6 +224,51 @@ extern "C" int laff_gru_cell(const float* gi, long long ld_gi, const float* gh, 
   const long long n = static_cast<long long>(B) * H;
   gru_cell_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       gi, ld_gi, gh, ld_gh, h_prev, lengths, t, B, H, h_out, sum, last);
+  count_launch();
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}
+
+extern "C" int laff_gru_cell_backward(const float* gi, long long ld_gi, const float* gh, long long ld_gh, const float* h_prev,
+                                      const float* dmean, const float* dlast, const float* dh_gemm, const int32_t* lengths, int t,
+                                      int B, int H, float* dh_carry, float* dgi, long long ld_dgi, float* dgh, long long ld_dgh,
+                                      void* stream) {
+  if (B == 0) return LAFF_OK;
+  LAFF_REQUIRE(gi && gh && h_prev && lengths && dh_carry && dgi && dgh && B > 0 && H > 0 && t >= 0 && ld_gi >= 3LL * H &&
+                   ld_gh >= 3LL * H && ld_dgi >= 3LL * H && ld_dgh >= 3LL * H,
+               LAFF_EINVAL, "laff_gru_cell_backward: bad arguments");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const long long n = static_cast<long long>(B) * H;
+  gru_cell_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      gi, ld_gi, gh, ld_gh, h_prev, dmean, dlast, dh_gemm, lengths, t, B, H, dh_carry, dgi, ld_dgi, dgh, ld_dgh);
+  count_launch();
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}
+
+extern "C" int laff_scatter_add_rows(const float* dx, long long ld, const int32_t* ids, long long n, int dim, long long n_table,
+                                     float* table_grad, long long ld_table, void* stream) {
+  if (n == 0) return LAFF_OK;
+  LAFF_REQUIRE(dx && ids && table_grad && n > 0 && n < (1LL << 31) && dim > 0 && ld >= dim && ld_table >= dim && n_table > 0,
+               LAFF_EINVAL, "laff_scatter_add_rows: bad arguments");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  scatter_add_rows_kernel<<<static_cast<unsigned>(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(dx, ld, ids, n, dim, n_table,
+                                                                                                 table_grad, ld_table);
+  count_launch();
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}
+
+extern "C" int laff_column_sum(const float* x, long long ld, long long rows, int cols, float* out, void* stream) {
+  LAFF_REQUIRE(x && out && rows >= 0 && cols > 0 && ld >= cols, LAFF_EINVAL, "laff_column_sum: bad arguments");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  column_sum_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(x, ld, rows, cols, out);
   count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;

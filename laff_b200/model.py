@@ -438,7 +438,8 @@ class GruTxtEncoder(TxtEncoder):
     def forward(self, caption_feat_dict, task3=False):
         from . import text as _text
         if self.training:
-            raise NotImplementedError("train-mode GRU (backward through time) is SURVEY §8f N4; call .eval()")
+            raise NotImplementedError("in train mode the GRU runs inside the model's training step (model(train_data)), which "
+                                      "keeps what backward-through-time needs; call .eval() for a plain forward")
         txt_input = caption_feat_dict["caption"]
         idx_vecs = [self.t2v_idx.encoding(c) for c in txt_input]
         lengths = [len(v) for v in idx_vecs]
@@ -674,8 +675,24 @@ class W2VVPP(nn.Module):
     def _stage_train_inputs(self, train_data, dev):
         """Device fp32 tensors of one batch: ({text encoder name: feature}, {video feature name: feature}).  String
         front-ends (BoW / word2vec) run here, before anything that a CUDA graph captures."""
-        txt = {n: self.txt_net._feature(train_data["captions"], n).to(dev, non_blocking=True).float()
-               for n in self.txt_net.encoder_name_list}
+        caps = train_data["captions"]
+        fronts = dict(self.txt_net.encoder.named_children())
+        txt = {}
+        for n in self.txt_net.encoder_name_list:
+            precomputed = any(k in caps for k in dict(_TXT_ENCODERS)[n])
+            if n == "rnn_encoder" and not precomputed and "rnn_encoder" in fronts and "caption" in caps:
+                # the GRU front-end trains with the model: token ids go to the device, the recurrence and its backward
+                # through time run inside the step (laff_b200.text.gru_encode_train / gru_backward)
+                enc = fronts["rnn_encoder"]
+                idx_vecs = [enc.t2v_idx.encoding(c) for c in caps["caption"]]
+                lengths = [len(v) for v in idx_vecs]
+                ids = np.zeros((len(idx_vecs), max(lengths)), dtype=np.int32)
+                for i, v in enumerate(idx_vecs):
+                    ids[i, : lengths[i]] = v
+                txt["rnn_ids"] = torch.from_numpy(ids).to(dev, non_blocking=True)
+                txt["rnn_len"] = torch.tensor(lengths, dtype=torch.int32).to(dev, non_blocking=True)
+                continue
+            txt[n] = self.txt_net._feature(caps, n).to(dev, non_blocking=True).float()
         if isinstance(self.vis_net, VisMutiTransformNetPlusFrameFeat):
             frames = train_data.get("vis_frame_feat_dict") or {}
             names = [n for n in self.vis_net.vis_net_space_dict.keys() if n not in self.vis_net.frame_attention]
@@ -693,7 +710,17 @@ class W2VVPP(nn.Module):
         from .train import FusionTrainStep
         self._seed_dev.add_(1)
         tmods = dict(self.txt_net.transform_layer.named_children())
-        tfeats = [(txt[n], tmods[n + "_transform"]) for n in self.txt_net.encoder_name_list]
+        tfeats, gru_cache, gru_idx = [], None, None
+        for n in self.txt_net.encoder_name_list:
+            if n == "rnn_encoder" and "rnn_ids" in txt:
+                from . import text as _text
+                enc = dict(self.txt_net.encoder.named_children())["rnn_encoder"]
+                feat, gru_cache = _text.gru_encode_train(enc.we.weight, enc.rnn.weight_ih_l0, enc.rnn.weight_hh_l0, enc.rnn.bias_ih_l0,
+                                                         enc.rnn.bias_hh_l0, txt["rnn_ids"], txt["rnn_len"], enc.pooling)
+                gru_idx = len(tfeats)
+                tfeats.append((feat, tmods[n + "_transform"], True))
+            else:
+                tfeats.append((txt[n], tmods[n + "_transform"]))
         frame_ml = isinstance(self.vis_net, VisMutiTransformNetPlusFrameFeat)
         pooled = {}
         if frame_ml:
@@ -728,7 +755,14 @@ class W2VVPP(nn.Module):
             loss, d_txt, d_vis = ops.dsl_forward_backward(outs["txt"], outs["vis"], 1000.0)
         else:
             loss, d_txt, d_vis = ops.mrl_forward_backward(outs["txt"], outs["vis"], c.margin, c.max_violation, c.direction, c.cost_style)
-        self._steps["txt"].backward(d_txt)
+        dxt = self._steps["txt"].backward(d_txt)
+        if gru_cache is not None:
+            from . import text as _text
+            from .train import _grad_buffer
+            enc = dict(self.txt_net.encoder.named_children())["rnn_encoder"]
+            grads = {"we": _grad_buffer(enc.we.weight), "w_ih": _grad_buffer(enc.rnn.weight_ih_l0), "w_hh": _grad_buffer(enc.rnn.weight_hh_l0),
+                     "b_ih": _grad_buffer(enc.rnn.bias_ih_l0), "b_hh": _grad_buffer(enc.rnn.bias_hh_l0)}
+            _text.gru_backward(gru_cache, dxt[gru_idx], enc.we.weight, enc.rnn.weight_ih_l0, enc.rnn.weight_hh_l0, grads)
         dxs = self._steps["vis"].backward(d_vis)
         for idx, (name, frames) in pooled.items():
             lin = self.vis_net.frame_attention[name][0].embedding_common[0]
@@ -777,11 +811,12 @@ class W2VVPP(nn.Module):
             self._seed_base = int(getattr(opt, "seed", 0) or 0) << 20
             self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
             self._frame_grads = {}
-            self._graph = None
+            self._graph, self._graphs = None, {}
         txt, vis = self._stage_train_inputs(train_data, dev)
         sig = (precision,) + tuple((k, tuple(v.shape)) for k, v in list(txt.items()) + list(vis.items()))
-        g = self._graph
-        if g is not None and g["sig"] == sig:
+        g = self._graphs.get(sig) if self._graphs else None
+        self._graph = g
+        if g is not None:
             self.optimizer.sync_lr()
             for k, v in txt.items():
                 g["txt"][k].copy_(v, non_blocking=True)
@@ -792,7 +827,9 @@ class W2VVPP(nn.Module):
         else:
             loss = self._train_step_device(txt, vis, precision)
             if self.use_cuda_graph and self.iters >= 3 and all(st.capturable for st in self._steps.values()):
-                self._graph = self._capture_train_graph(txt, vis, precision, sig)
+                if len(self._graphs) >= 16:  # caption lengths vary: keep the graphs of the most recent shapes
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graph = self._graphs[sig] = self._capture_train_graph(txt, vis, precision, sig)
         _PARAM_EPOCH += 1  # parameters changed behind torch's version counters: drop the eval-mode operand caches
         return {"triplet_loss": loss}
 
@@ -806,7 +843,7 @@ class W2VVPP(nn.Module):
         return {"graph": graph, "txt": st_txt, "vis": st_vis, "loss": loss, "sig": sig}
 
     def train(self, mode: bool = True):
-        self._graph = None  # BatchNorm / dropout behaviour is baked into a captured step
+        self._graph, self._graphs = None, {}  # BatchNorm / dropout behaviour is baked into a captured step
         return super().train(mode)
 
     def predict(self, txt_loader, vis_loader, measure, record_emb=False):

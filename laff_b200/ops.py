@@ -661,3 +661,31 @@ def frame_pool_backward(frames: torch.Tensor, att_weight: torch.Tensor, dout: to
     dc_part = torch.empty(B, dtype=torch.float32, device=frames.device)
     _capi.call("laff_frame_pool_backward", _ptr(frames), B, F, dim, _ptr(att_weight), _ptr(dout), dout.stride(0), float(norm_eps),
                _ptr(dw_part), _ptr(dc_part), _ptr(dw), _ptr(dc), _stream(frames))
+
+
+def gru_cell_backward(gi, gh, h_prev, dmean, dlast, dh_gemm, lengths, t: int, dh_carry, dgi, dgh) -> None:
+    """One BPTT step of the GRU (laff_gru_cell_backward); gi / gh / dgi / dgh are [B, 3H] views with contiguous rows."""
+    _need_cuda(gi, gh, h_prev, dmean, dlast, dh_gemm, lengths, dh_carry, dgi, dgh)
+    B, H = h_prev.shape
+    _capi.call("laff_gru_cell_backward", _ptr(gi), gi.stride(0), _ptr(gh), gh.stride(0), _ptr(h_prev), _ptr(dmean), _ptr(dlast),
+               _ptr(dh_gemm), _ptr(lengths), int(t), B, H, _ptr(dh_carry), _ptr(dgi), dgi.stride(0), _ptr(dgh), dgh.stride(0),
+               _stream(h_prev))
+
+
+def scatter_add_rows(dx: torch.Tensor, ids: torch.Tensor, table_grad: torch.Tensor) -> None:
+    """nn.Embedding backward: table_grad[ids[i]] += dx[i] (laff_scatter_add_rows); table_grad must be zeroed by the caller."""
+    _need_cuda(dx, ids, table_grad)
+    dx = _rowmajor(dx)
+    ids = ids.to(torch.int32).contiguous().view(-1)
+    _capi.call("laff_scatter_add_rows", _ptr(dx), dx.stride(0), _ptr(ids), ids.numel(), dx.shape[1], table_grad.shape[0],
+               _ptr(table_grad), table_grad.stride(0), _stream(dx))
+
+
+def column_sum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[c] = sum_r x[r, c], fixed order (laff_column_sum)."""
+    _need_cuda(x, out)
+    x = _rowmajor(x)
+    if out is None:
+        out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    _capi.call("laff_column_sum", _ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(out), _stream(x))
+    return out

@@ -276,3 +276,72 @@ def gru_encode(we: torch.Tensor, w_ih: torch.Tensor, w_hh: torch.Tensor, b_ih: t
     if pooling == "last":
         return last
     return torch.cat((acc, last), dim=1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GRU sentence encoder: training (forward that keeps what BPTT needs, and the backward)
+# ----------------------------------------------------------------------------------------------------------------
+def _split_ops(x: torch.Tensor, side: int) -> torch.Tensor:
+    return ops.split3_16(x, side, torch.bfloat16)
+
+
+def gru_encode_train(we, w_ih, w_hh, b_ih, b_hh, ids: torch.Tensor, lengths: torch.Tensor, pooling: str = "mean"):
+    """gru_encode that keeps the per-step pre-activations and states.  Returns (pooled features, cache)."""
+    B, T = ids.shape
+    H = w_hh.shape[1]
+    dev = we.device
+    if pooling not in ("mean", "last", "mean_last"):
+        raise Exception("pooling %s is invalid" % pooling)
+    lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
+    ids = ids.to(dev).to(torch.int32).contiguous()
+    wih16, whh16 = _split_ops(w_ih.detach().float(), 1), _split_ops(w_hh.detach().float(), 1)
+    x = ops.gather_rows(we.detach(), ids.reshape(-1))
+    gi = ops.project(_split_ops(x, 0), wih16, b_ih.detach().float().contiguous(), "none").view(B, T, 3 * H)
+    h_all = torch.zeros((T + 1, B, H), dtype=torch.float32, device=dev)
+    gh_all = torch.empty((T, B, 3 * H), dtype=torch.float32, device=dev)
+    acc = torch.zeros((B, H), dtype=torch.float32, device=dev) if pooling != "last" else None
+    last = torch.zeros((B, H), dtype=torch.float32, device=dev) if pooling != "mean" else None
+    bhh = b_hh.detach().float().contiguous()
+    for t in range(T):
+        ops.project(_split_ops(h_all[t], 0), whh16, bhh, "none", out=gh_all[t])
+        ops.gru_cell(gi[:, t], gh_all[t], h_all[t], lengths, t, h_all[t + 1], acc, last)
+    if acc is not None:
+        ops.mean_over_length(acc, lengths)
+    out = acc if pooling == "mean" else last if pooling == "last" else torch.cat((acc, last), dim=1)
+    cache = {"x": x, "ids": ids, "lengths": lengths, "gi": gi, "gh_all": gh_all, "h_all": h_all, "pooling": pooling, "B": B, "T": T,
+             "H": H}
+    return out, cache
+
+
+def gru_backward(cache: dict, dout: torch.Tensor, we, w_ih, w_hh, grads: dict) -> None:
+    """Backward through time of gru_encode_train.  dout: d loss / d pooled features.  Writes into the preallocated
+    gradient tensors grads = {'we', 'w_ih', 'w_hh', 'b_ih', 'b_hh'} (shapes of the parameters; 'we' is zeroed here).
+    Per step: one elementwise kernel + one tcgen05 GEMM (dGh_t @ W_hh); afterwards three GEMMs over K = B*T for dW_hh,
+    dW_ih and the embedding gradients."""
+    B, T, H = cache["B"], cache["T"], cache["H"]
+    dev = dout.device
+    pooling = cache["pooling"]
+    dout = dout.reshape(B, -1).float().contiguous()
+    dmean = dout[:, :H].contiguous() if pooling != "last" else None
+    dlast = (dout[:, H:] if pooling == "mean_last" else dout).contiguous() if pooling != "mean" else None
+    whhT16 = ops.transpose_16(w_hh.detach().float(), torch.bfloat16, 3, 1)       # [H, 3 * 3H]: K-major W_hh^T
+    dgi_all = torch.empty((B, T, 3 * H), dtype=torch.float32, device=dev)
+    dgh_all = torch.empty((T, B, 3 * H), dtype=torch.float32, device=dev)
+    carry = torch.zeros((B, H), dtype=torch.float32, device=dev)
+    through = None
+    buf = torch.empty((B, H), dtype=torch.float32, device=dev)
+    for t in range(T - 1, -1, -1):
+        ops.gru_cell_backward(cache["gi"][:, t], cache["gh_all"][t], cache["h_all"][t], dmean, dlast, through, cache["lengths"], t,
+                              carry, dgi_all[:, t], dgh_all[t])
+        if t > 0:
+            through = ops.project(_split_ops(dgh_all[t], 0), whhT16, None, "none", out=buf)
+    dgi2 = dgi_all.view(B * T, 3 * H)
+    dgh2 = dgh_all.view(T * B, 3 * H)
+    hprev2 = cache["h_all"][:T].reshape(T * B, H)
+    ops.sim_dense(ops.transpose_16(dgh2, torch.bfloat16, 3, 0), ops.transpose_16(hprev2, torch.bfloat16, 3, 1), 1.0, out=grads["w_hh"])
+    ops.column_sum(dgh2, grads["b_hh"])
+    ops.sim_dense(ops.transpose_16(dgi2, torch.bfloat16, 3, 0), ops.transpose_16(cache["x"], torch.bfloat16, 3, 1), 1.0, out=grads["w_ih"])
+    ops.column_sum(dgi2, grads["b_ih"])
+    dx = ops.project(_split_ops(dgi2, 0), ops.transpose_16(w_ih.detach().float(), torch.bfloat16, 3, 1), None, "none")
+    grads["we"].zero_()
+    ops.scatter_add_rows(dx, cache["ids"].reshape(-1), grads["we"])

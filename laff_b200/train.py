@@ -14,8 +14,8 @@ Here the same step is an explicit forward / backward over the C ABI — no autog
 Operand precision of the GEMMs: '3-term bf16 split' by default (fp32-grade products — the reference trains in fp32
 unless `config.float16`), or plain bf16 / fp16 via `precision=`.  Dropout uses a counter-based mask (seed per step and
 feature), not torch's generator: with p > 0 the step is statistically, not bitwise, the reference's.
-Restrictions (raise NotImplementedError): attention variants with the mean residual / product, the score-matrix loss
-branch (`multi_space = False`), and training the GRU text encoder (its features must arrive precomputed).
+Restrictions (raise NotImplementedError): the score-matrix loss branch (`multi_space = False`) and the negation-aware
+branch.  The GRU sentence encoder trains with the model (laff_b200.text.gru_encode_train / gru_backward).
 """
 from __future__ import annotations
 
@@ -122,6 +122,10 @@ class FusionTrainStep:
                                               it["si"], dgamma=dgamma, dbeta=dbeta, dbias=dbias)
             terms = 3 if self.precision == "bf16x3" else 1
             dt = torch.float16 if self.precision == "fp16" else torch.bfloat16
+            if it["want_dx"]:  # the input is itself computed (GRU sentence feature): dx = dz @ W
+                wT16 = ops.transpose_16(tn.fc1.weight.detach(), dt, terms, 1)
+                dz16 = ops.split3_16(dz, 0, torch.bfloat16) if terms == 3 else ops.cast_pad_16(dz, dt)
+                dxs[idx] = ops.project(dz16, wT16, None, "none")
             ops.sim_dense(ops.transpose_16(dz, dt, terms, 0), ops.transpose_16(it["x"], dt, terms, 1), 1.0,
                           out=_grad_buffer(tn.fc1.weight))
         self.cache = None

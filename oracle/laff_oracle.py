@@ -379,6 +379,7 @@ def fusion_train_backward(cache: dict, dout: np.ndarray, sd: Mapping[str, np.nda
             dz = d * _act_grad(it["a"], cache["activation"])
             grads[pre + "fc1.weight"] = dz.T @ it["x"]
             grads[pre + "fc1.bias"] = dz.sum(0)
+            cache["dx"][it["name"]] = dz @ sd[pre + "fc1.weight"].astype(np.float64)   # needed when x is computed (GRU feature)
         else:  # tiled feature: x.repeat(1, heads) backward (needed when x is itself computed, LAFF-ml)
             cache["dx"][it["name"]] = d.reshape(B, H, -1).sum(1)
     return grads
@@ -429,11 +430,14 @@ def clip_and_step(sd: dict, grads: Mapping[str, np.ndarray], state: dict, optimi
 
 def laff_train_step(sd: dict, vis_in: Mapping[str, np.ndarray], txt_in: Mapping[str, np.ndarray], state: dict, heads: int,
                     vis_no_transform: Sequence[str], optimizer="rmsprop", lr=1e-4, grad_clip=2.0, margin=0.2, adam_eps=1e-4,
-                    with_ave=False, mul=False, loss_kind="mrl"):
+                    with_ave=False, mul=False, loss_kind="mrl", gru_tokens: Optional[Sequence[np.ndarray]] = None):
     """W2VVPP_MultiHeadAttention.forward(train_data) (model/model.py:964-1001 with :2021-2048): one step on the full
     model state dict (keys 'vis_net.*' / 'txt_net.*'), dropout 0.  Returns (loss, clipped gradients, grad norm)."""
     vfe = [(n, x) for n, x in vis_in.items()]
     vpre = {n: "vis_net.VisMutiTransformNet.%s." % n for n in vis_in}
+    gru_prefix = "txt_net.encoder.rnn_encoder."
+    if gru_tokens is not None:  # the GRU front-end trains with the model (token ids instead of a precomputed 'gru' feature)
+        txt_in = dict(txt_in, gru=gru_train(gru_tokens, sd, gru_prefix))
     tfe = [(TXT_FEATURE_KEY[e], txt_in[TXT_FEATURE_KEY[e]]) for e in TXT_ENCODER_ORDER if TXT_FEATURE_KEY[e] in txt_in]
     tpre = {TXT_FEATURE_KEY[e]: "txt_net.transform_layer.%s_transform." % e for e in TXT_ENCODER_ORDER}
     t_emb, tc = fusion_train_forward(tfe, sd, tpre, "txt_net.attention_layer.", heads, ["clip"], with_ave=with_ave, mul=mul)
@@ -449,11 +453,58 @@ def laff_train_step(sd: dict, vis_in: Mapping[str, np.ndarray], txt_in: Mapping[
     grads = {}
     grads.update(fusion_train_backward(tc, d_txt, sd))
     grads.update(fusion_train_backward(vc, d_vis, sd))
+    if gru_tokens is not None:
+        grads.update(gru_train(gru_tokens, sd, gru_prefix, tc["dx"]["gru"]))
     total = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values())))
     coef = min(1.0, grad_clip / (total + 1e-6)) if grad_clip and grad_clip > 0 else 1.0
     clipped = {k: (g * coef) for k, g in grads.items()}
     clip_and_step(sd, grads, state, optimizer, lr, grad_clip, eps=(adam_eps if optimizer == "adam" else None))
     return float(loss), clipped, total
+
+
+def gru_train(idx_vecs: Sequence[np.ndarray], sd: Mapping[str, np.ndarray], prefix: str, dout: Optional[np.ndarray] = None):
+    """GruTxtEncoder in train mode with 'mean' pooling (model/model.py:340-369) in float64.  Without dout: the pooled
+    features [B, H].  With dout [B, H]: the gradients of we.weight / rnn.{weight,bias}_{ih,hh}_l0 by backward through time."""
+    we, w_ih, w_hh = (sd[prefix + k].astype(np.float64) for k in ("we.weight", "rnn.weight_ih_l0", "rnn.weight_hh_l0"))
+    b_ih, b_hh = sd[prefix + "rnn.bias_ih_l0"].astype(np.float64), sd[prefix + "rnn.bias_hh_l0"].astype(np.float64)
+    H = w_hh.shape[1]
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))
+    outs, tapes = [], []
+    for ids in idx_vecs:
+        h = np.zeros(H)
+        tape = []
+        for tok in ids:
+            x = we[tok]
+            gi, gh = w_ih @ x + b_ih, w_hh @ h + b_hh
+            r, z = sig(gi[:H] + gh[:H]), sig(gi[H:2 * H] + gh[H:2 * H])
+            n = np.tanh(gi[2 * H:] + r * gh[2 * H:])
+            hn = (1 - z) * n + z * h
+            tape.append((tok, x, h, r, z, n, gh[2 * H:]))
+            h = hn
+        tapes.append(tape)
+        hs = [(1 - t[4]) * t[5] + t[4] * t[2] for t in tape]
+        outs.append(np.mean(hs, axis=0))
+    if dout is None:
+        return np.stack(outs)
+    g = {k: np.zeros_like(v) for k, v in (("we.weight", we), ("rnn.weight_ih_l0", w_ih), ("rnn.weight_hh_l0", w_hh),
+                                          ("rnn.bias_ih_l0", b_ih), ("rnn.bias_hh_l0", b_hh))}
+    for b, tape in enumerate(tapes):
+        L = len(tape)
+        dh_next = np.zeros(H)
+        for tok, x, hp, r, z, n, ghn in reversed(tape):
+            dh = dh_next + dout[b] / L
+            dn, dz = dh * (1 - z), dh * (hp - n)
+            dpn, dpz = dn * (1 - n * n), dz * z * (1 - z)
+            dpr = dpn * ghn * r * (1 - r)
+            dgi = np.concatenate([dpr, dpz, dpn])
+            dgh = np.concatenate([dpr, dpz, dpn * r])
+            g["rnn.weight_ih_l0"] += np.outer(dgi, x)
+            g["rnn.weight_hh_l0"] += np.outer(dgh, hp)
+            g["rnn.bias_ih_l0"] += dgi
+            g["rnn.bias_hh_l0"] += dgh
+            g["we.weight"][tok] += w_ih.T @ dgi
+            dh_next = dh * z + w_hh.T @ dgh
+    return {prefix + k: v for k, v in g.items()}
 
 
 def laff_ml_train_step(sd: dict, vis_in: Mapping[str, np.ndarray], frames: np.ndarray, frame_feat: str,

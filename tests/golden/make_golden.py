@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 from laff_b200 import synth  # noqa: E402
 
 
+REAL_GRU_ENCODER = None
+
+
 def install_shims():
     os.environ.setdefault("HOME", "/tmp")
     for name in ("ftfy", "prefetch_generator"):
@@ -76,7 +79,10 @@ def import_reference():
     def pt(key):
         return type("PassThrough_" + key, (PassThrough,), {"key": key})
 
+    global REAL_GRU_ENCODER
+    REAL_GRU_ENCODER = getattr(mm.GruTxtEncoder, "_laff_real", mm.GruTxtEncoder)   # the reference's own class (make_golden_train)
     mm.GruTxtEncoder = pt("gru")
+    mm.GruTxtEncoder._laff_real = REAL_GRU_ENCODER
     mm.BoWTxtEncoder = pt("bow")
     mm.W2VTxtEncoder = pt("w2v")
     mm.CLIPEncoder = pt("clip")

@@ -65,6 +65,66 @@ def run_case(mm, tag, optimizer, lr, batch_norm, steps=3, B=16, D=256, H=8, seed
     return out
 
 
+def run_gru_case(mm, tag, optimizer, lr, steps=3, B=12, D=256, H=8, seed=95):
+    """'LAFF' with the reference's real GruTxtEncoder (trainable embedding + GRU, backward through time by autograd) on
+    the synthetic vocabulary of tests/golden/text; BoW / word2vec / CLIP features stay pass-through inputs."""
+    import json
+    import torch
+    import txt2vec
+    dims = dict(SMALL, gru=24)
+    vis_dims = {synth.VIS_CLIP_FT: dims["clip"], synth.VIS_TF: dims["tf"], synth.VIS_X3D: dims["x3d"], synth.VIS_IRCSN: dims["ircsn"]}
+    cfg = mg.make_config("laff", D, H, vis_dims, dims)
+    cfg.dropout = 0.0
+    cfg.optimizer, cfg.lr = optimizer, lr
+    cfg.t2v_idx = txt2vec.IndexVec(os.path.join(HERE, "text", "vocab_gru.pkl"))
+    cfg.we_dim, cfg.rnn_layer = 12, 1
+    cfg.we = torch.zeros(len(cfg.t2v_idx.vocab), cfg.we_dim)
+    real_gru = mg.REAL_GRU_ENCODER
+    saved = mm.GruTxtEncoder
+    mm.GruTxtEncoder = real_gru
+    try:
+        torch.manual_seed(0)
+        model = mm.W2VVPP_MultiHeadAttention(cfg)
+    finally:
+        mm.GruTxtEncoder = saved
+    sd0 = mg.load_synth_state(model, seed)
+    model.train()
+    meta = json.load(open(os.path.join(HERE, "text", "meta.json")))
+    words = meta["bow_words"]
+    out = {"meta": np.array([B, D, H, steps, seed, 0, 0, 0, 0]), "loss_kind": np.array("mrl"), "optimizer": np.array(optimizer),
+           "lr": np.float64(lr), "grad_clip": np.float64(cfg.grad_clip), "vis_names": np.array(list(vis_dims.keys())),
+           "gru_dim": np.int64(dims["gru"]), "we_dim": np.int64(cfg.we_dim)}
+    for k, v in sd0.items():
+        out["sd0/" + k] = v
+    losses = []
+    for s in range(steps):
+        r = synth.rng_for(seed + s, "captions")
+        caps = [" ".join(r.choice(words + ["zebra", "the"], size=r.randint(1, 9))) for _ in range(B)]
+        vis_in = {n: synth.feature(seed + s, "vis/" + n, B, d, "dense" if n == synth.VIS_CLIP_FT else "relu") for n, d in vis_dims.items()}
+        txt_in = {"bow": synth.feature(seed + s, "txt/bow", B, dims["bow"], "bow"), "w2v": synth.feature(seed + s, "txt/w2v", B, dims["w2v"]),
+                  "clip": synth.feature(seed + s, "txt/clip", B, dims["clip"])}
+        for k, v in vis_in.items():
+            out["step%d/vin/%s" % (s, k)] = v
+        for k, v in txt_in.items():
+            out["step%d/tin/%s" % (s, k)] = v
+        out["step%d/captions" % s] = np.array(caps)
+        captions = {k: torch.from_numpy(v) for k, v in txt_in.items()}
+        captions["caption"] = caps
+        train_data = {"vis_feats": {k: torch.from_numpy(v) for k, v in vis_in.items()}, "captions": captions, "captions_task2": None,
+                      "vis_frame_feat_dict": {}, "vis_origin_frame_tuple": None}
+        items = model(train_data, epoch=0)
+        losses.append(float(items["triplet_loss"]))
+        if s == 0:
+            for k, p in model.named_parameters():
+                if p.grad is not None:
+                    out["grad0/" + k] = p.grad.detach().numpy().copy()
+        for k, v in model.state_dict().items():
+            out["sd%d/%s" % (s + 1, k)] = v.detach().numpy().copy()
+    out["losses"] = np.array(losses)
+    print(tag, "losses", losses)
+    return out
+
+
 def run_frame_case(mm, tag, optimizer, lr, steps=3, B=16, D=256, H=8, F=6, seed=91):
     """'FrameLAFF' (LAFF-ml, W2VVPP_MutiVisFrameFeat): frame-level attention + BatchNorm on every projected feature."""
     import torch
@@ -131,6 +191,8 @@ def main():
                             **run_case(mm, "rmsprop_ave_mul", "rmsprop", 1e-3, False, with_ave=True, mul=True))
     if not only or "adam_dsl" in only:
         np.savez_compressed(os.path.join(HERE, "train_adam_dsl.npz"), **run_case(mm, "adam_dsl", "adam", 1e-3, False, loss="dsl"))
+    if not only or "gru_rmsprop" in only:
+        np.savez_compressed(os.path.join(HERE, "train_gru_rmsprop.npz"), **run_gru_case(mm, "gru_rmsprop", "rmsprop", 1e-3))
     if not only or "frame_rmsprop" in only:
         np.savez_compressed(os.path.join(HERE, "train_frame_rmsprop.npz"), **run_frame_case(mm, "frame_rmsprop", "rmsprop", 1e-3))
 

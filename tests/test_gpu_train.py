@@ -231,3 +231,47 @@ def test_dual_softmax_loss_kernel_vs_reference_autograd():
         out = L.DualSoftmaxLoss()(t, vis)
         out.backward()
         assert abs(out.item() - ref) <= 1e-5 * abs(ref) and torch.equal(t.grad, d_txt)
+
+
+def test_gru_front_end_trains_with_the_model():
+    """Token ids in, backward through time on the device: the LAFF model with the trainable GRU sentence encoder
+    against three steps of the unmodified reference (its GruTxtEncoder under autograd), then graph replays."""
+    from laff_b200 import text as T
+    from test_train_cpu import check_params
+    g, sd, H, steps = load_case("gru_rmsprop")
+    D = int(g["meta"][1])
+    dims = dict(SMALL, gru=int(g["gru_dim"]))
+    c = cfg.laff_config(D, H, dims)
+    c.dropout = 0.0
+    c.optimizer, c.lr, c.grad_clip = str(g["optimizer"]), float(g["lr"]), float(g["grad_clip"])
+    c.t2v_idx = T.IndexVec(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "text", "vocab_gru.pkl"))
+    c.we_dim, c.rnn_layer, c.we = int(g["we_dim"]), 1, None
+    model = M.get_model("LAFF", torch.device("cuda"), c)
+    load_numpy_state(model, sd)
+    model.train()
+    for s in range(steps + 4):
+        k = s % steps
+        vis_in = {str(n): g["step%d/vin/%s" % (k, n)] for n in g["vis_names"]}
+        caps = {n: torch.from_numpy(g["step%d/tin/%s" % (k, n)]) for n in ("bow", "w2v", "clip")}
+        caps["caption"] = [str(x) for x in g["step%d/captions" % k]]
+        td = {"vis_feats": {n: torch.from_numpy(v) for n, v in vis_in.items()}, "captions": caps, "captions_task2": None,
+              "vis_frame_feat_dict": {}, "vis_origin_frame_tuple": None}
+        loss = float(model(td, epoch=0)["triplet_loss"])
+        if s >= steps:
+            assert np.isfinite(loss)
+            continue
+        assert abs(loss - g["losses"][s]) <= (2e-5 if s == 0 else 5e-4) * abs(g["losses"][s]), (s, loss, g["losses"][s])
+        if s == 0:
+            grads = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+            ref_keys = [n[6:] for n in g.files if n.startswith("grad0/")]
+            assert sorted(ref_keys) == sorted(grads.keys())
+            for n in ref_keys:
+                ref = g["grad0/" + n]
+                got = grads[n].cpu().numpy().reshape(ref.shape)
+                assert np.abs(got - ref).max() <= 1e-4 * max(1e-3, np.abs(ref).max()), (n, np.abs(got - ref).max())
+        check_params({n: v.detach().cpu().numpy() for n, v in model.state_dict().items()}, g, s, float(g["lr"]), tight0=5e-5, frac=0.97)
+    assert len(model._graphs) >= 1        # caption lengths differ between batches: one graph per shape
+    model.eval()                          # and the eval path sees the trained GRU
+    out = model.txt_net({"caption": ["a dog runs"], "bow": torch.zeros(1, SMALL["bow"]), "w2v": torch.zeros(1, SMALL["w2v"]),
+                         "clip": torch.zeros(1, SMALL["clip"])})
+    assert out.shape == (1, H, D // H) and bool(torch.isfinite(out).all())

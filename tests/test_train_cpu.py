@@ -83,3 +83,31 @@ def test_oracle_laff_ml_train_steps_match_reference():
                 ref = g["grad0/" + k]
                 np.testing.assert_allclose(grads[k].reshape(ref.shape), ref, rtol=0, atol=2e-5 * max(1e-3, np.abs(ref).max()), err_msg=k)
         check_params(sd, g, s, lr)
+
+
+def gru_tokens_of(g, s):
+    """Token ids of step s's captions under the test vocabulary (IndexVec: <start> words <end>, unknown -> <unk>)."""
+    from laff_b200 import text as T
+    idx = T.IndexVec(os.path.join(HERE, "golden", "text", "vocab_gru.pkl"))
+    return [idx.encoding(str(c)) for c in g["step%d/captions" % s]]
+
+
+def test_oracle_gru_front_end_training_matches_reference():
+    """The reference's real GruTxtEncoder (embedding + GRU, trained through autograd BPTT) inside the LAFF model."""
+    g, sd, H, steps = load_case("gru_rmsprop")
+    assert "txt_net.encoder.rnn_encoder.rnn.weight_hh_l0" in sd and "grad0/txt_net.encoder.rnn_encoder.we.weight" in g.files
+    state = {}
+    lr, clip = float(g["lr"]), float(g["grad_clip"])
+    for s in range(steps):
+        vis_in = {str(n): g["step%d/vin/%s" % (s, n)] for n in g["vis_names"]}
+        txt_in = {k: g["step%d/tin/%s" % (s, k)] for k in ("bow", "w2v", "clip")}
+        loss, grads, total = O.laff_train_step(sd, vis_in, txt_in, state, H, [synth.VIS_CLIP_FT], str(g["optimizer"]), lr, clip,
+                                               gru_tokens=gru_tokens_of(g, s))
+        assert abs(loss - g["losses"][s]) <= 2e-5 * abs(g["losses"][s]), (s, loss, g["losses"][s])
+        if s == 0:
+            ref_keys = [k[6:] for k in g.files if k.startswith("grad0/")]
+            assert sorted(ref_keys) == sorted(grads.keys())
+            for k in ref_keys:
+                ref = g["grad0/" + k]
+                np.testing.assert_allclose(grads[k].reshape(ref.shape), ref, rtol=0, atol=2e-5 * max(1e-3, np.abs(ref).max()), err_msg=k)
+        check_params(sd, g, s, lr)
