@@ -846,6 +846,9 @@ class W2VVPP(nn.Module):
         self._graph, self._graphs = None, {}  # BatchNorm / dropout behaviour is baked into a captured step
         return super().train(mode)
 
+    def _encode_vis(self, output_dict, out16_dtype=None):
+        return self.vis_net.encode(output_dict["vis_feat_dict"], out16_dtype)
+
     def predict(self, txt_loader, vis_loader, measure, record_emb=False):
         """Dense score matrix for small galleries; same return contract as the reference:
         (scores ndarray [Q, V] float32, txt_ids, vis_ids).  Video embeddings stay on the device (the reference parks

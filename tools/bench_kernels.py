@@ -153,6 +153,36 @@ def main():
     emit("LAFF training step B=128 (train-mode forward, loss, backward, clip + RMSprop; %.1f M parameters)" % (n_par / 1e6), ms,
          note="%d kernel launches of this library per step; latency-bound (14.6 GFLOP of GEMM work)" % launches)
 
+    # N2: text front-end at query-batch scale: 10 000 captions of 4..16 words over a 4 096-word vocabulary
+    import tempfile
+    from laff_b200 import text as T
+    from laff_b200.bigfile import write_bigfile
+    rs = np.random.RandomState(0)
+    words = ["w%04d" % i for i in range(4096)]
+    caps = [" ".join(rs.choice(words, size=rs.randint(4, 17))) for _ in range(10000)]
+    vocab_b, vocab_g = T.Vocabulary("bow"), T.Vocabulary("gru")
+    for w in ["<pad>", "<start>", "<end>", "<unk>"]:
+        vocab_g.add(w)
+    for w in words:
+        vocab_b.add(w)
+        vocab_g.add(w)
+    with tempfile.TemporaryDirectory() as td:
+        write_bigfile(td, words, rs.standard_normal((4096, 500)).astype(np.float32))
+        bow, w2v = T.BowVec(None, vocab=vocab_b), T.W2Vec(td)
+        idx = T.IndexVec(None, vocab=vocab_g)
+        import types
+        opt = types.SimpleNamespace(t2v_idx=idx, rnn_layer=1, we_dim=500, rnn_size=1024, pooling="mean", we=None, t2v_bow=bow, t2v_w2v=w2v)
+        gru = M.GruTxtEncoder(opt).to(dev).eval()
+        import time
+        t0 = time.perf_counter()
+        tok = [idx.encoding(c_) for c_ in caps]
+        host_ms = (time.perf_counter() - t0) * 1e3
+        for name, fn in (("BoW counts (laff_bow_counts)", lambda: bow.encode_batch(caps)), ("word2vec means (laff_gather_mean)", lambda: w2v.encode_batch(caps)),
+                         ("GRU 500->1024, mean pooling (embedding + %d-step recurrence on the GEMM engine)" % max(len(t_) for t_ in tok),
+                          lambda: gru({"caption": caps}))):
+            ms = timeit(fn, iters=5, warmup=2)
+            emit("text front-end, 10000 captions: " + name, ms, note="includes host tokenisation (%.0f ms for the GRU's token ids)" % host_ms)
+
 
 if __name__ == "__main__":
     main()
