@@ -185,6 +185,22 @@ int laff_label_metrics(const uint8_t* label, int Q, int V, long long ld, int32_t
  *                     (gate order r, z, n); sequences with lengths[b] <= t keep h.  sum += h_t (for 'mean' pooling) and
  *                     last = h at t == len - 1 are optional outputs (model/model.py:361-383).
  *   laff_mean_over_length  x[b, :] /= lengths[b]. */
+/* Host half of the front-end (no GPU work): batch tokenisation + vocabulary lookup, the equivalent of
+ * TextTool.tokenize(clean=True, 'en') (textlib.py:27-47) followed by the per-word dict lookups of BowVec / W2Vec / IndexVec.
+ *   laff_vocab_create   words: concatenated UTF-8 bytes with n_words + 1 offsets; ids: id per word or NULL (= position).
+ *                       Returns NULL on error (laff_last_error).  Also used for the stop-word set.
+ *   laff_tokenize_lookup  captions: concatenated UTF-8 bytes with n_caps + 1 offsets; stopwords may be NULL.
+ *       mode 0 (IndexVec): start_id, every token (unknown -> unk_id), end_id   (start/end skipped when negative)
+ *       mode 1 (BowVec):   in-vocabulary tokens in order
+ *       mode 2 (W2Vec):    distinct in-vocabulary ids, ascending (bigfile.py:204-211)
+ *     Writes CSR offsets [n_caps + 1] and up to `capacity` ids; returns the number of ids (> capacity: call again). */
+typedef struct laff_vocab laff_vocab;
+laff_vocab* laff_vocab_create(const char* words_blob, const long long* offsets, const int32_t* ids, int n_words);
+void laff_vocab_destroy(laff_vocab* v);
+long long laff_tokenize_lookup(const char* text_blob, const long long* cap_offsets, int n_caps, const laff_vocab* vocab,
+                               const laff_vocab* stopwords, int mode, int unk_id, int start_id, int end_id,
+                               long long* out_offsets, int32_t* out_ids, long long capacity);
+
 int laff_bow_counts(const long long* tok_offsets, const int32_t* tok_ids, int rows, int ndims, float* out, long long ld,
                     void* stream);
 int laff_gather_mean(const float* table, long long ld_table, long long n_table, const long long* offsets,

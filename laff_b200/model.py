@@ -440,15 +440,10 @@ class GruTxtEncoder(TxtEncoder):
         if self.training:
             raise NotImplementedError("in train mode the GRU runs inside the model's training step (model(train_data)), which "
                                       "keeps what backward-through-time needs; call .eval() for a plain forward")
-        txt_input = caption_feat_dict["caption"]
-        idx_vecs = [self.t2v_idx.encoding(c) for c in txt_input]
-        lengths = [len(v) for v in idx_vecs]
-        ids = np.zeros((len(txt_input), max(lengths)), dtype=np.int32)
-        for i, v in enumerate(idx_vecs):
-            ids[i, : lengths[i]] = v
+        ids, lengths = self.t2v_idx.encoding_batch(caption_feat_dict["caption"])
         dev = _cuda_device(self.we.weight.device)
         out = _text.gru_encode(self.we.weight, self.rnn.weight_ih_l0, self.rnn.weight_hh_l0, self.rnn.bias_ih_l0,
-                               self.rnn.bias_hh_l0, torch.from_numpy(ids).to(dev), torch.tensor(lengths, dtype=torch.int32, device=dev),
+                               self.rnn.bias_hh_l0, torch.from_numpy(ids).to(dev), torch.from_numpy(lengths).to(dev),
                                self.pooling, self._prepared)
         return {"text_features": out}
 
@@ -683,14 +678,9 @@ class W2VVPP(nn.Module):
             if n == "rnn_encoder" and not precomputed and "rnn_encoder" in fronts and "caption" in caps:
                 # the GRU front-end trains with the model: token ids go to the device, the recurrence and its backward
                 # through time run inside the step (laff_b200.text.gru_encode_train / gru_backward)
-                enc = fronts["rnn_encoder"]
-                idx_vecs = [enc.t2v_idx.encoding(c) for c in caps["caption"]]
-                lengths = [len(v) for v in idx_vecs]
-                ids = np.zeros((len(idx_vecs), max(lengths)), dtype=np.int32)
-                for i, v in enumerate(idx_vecs):
-                    ids[i, : lengths[i]] = v
+                ids, lengths = fronts["rnn_encoder"].t2v_idx.encoding_batch(caps["caption"])
                 txt["rnn_ids"] = torch.from_numpy(ids).to(dev, non_blocking=True)
-                txt["rnn_len"] = torch.tensor(lengths, dtype=torch.int32).to(dev, non_blocking=True)
+                txt["rnn_len"] = torch.from_numpy(lengths).to(dev, non_blocking=True)
                 continue
             txt[n] = self.txt_net._feature(caps, n).to(dev, non_blocking=True).float()
         if isinstance(self.vis_net, VisMutiTransformNetPlusFrameFeat):

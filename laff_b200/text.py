@@ -127,6 +127,69 @@ def _device(device=None) -> torch.device:
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# native batch tokenisation + vocabulary lookup (csrc/tokenize.cu; host code of the C ABI, no GPU involved)
+# ----------------------------------------------------------------------------------------------------------------
+def _blob(strings: Sequence[str]):
+    enc = [s.encode("utf-8") for s in strings]
+    offsets = np.zeros(len(enc) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in enc], out=offsets[1:])
+    return b"".join(enc), offsets
+
+
+class NativeVocab:
+    """A word -> id table inside the C library (open-addressing hash); also used as the stop-word set."""
+
+    def __init__(self, words: Sequence[str], ids: Optional[Sequence[int]] = None):
+        from . import _capi
+        self._lib = _capi.lib()
+        blob, offsets = _blob(words)
+        idarr = None if ids is None else np.ascontiguousarray(ids, dtype=np.int32)
+        self._keep = (blob, offsets, idarr)
+        self.handle = self._lib.laff_vocab_create(blob, offsets.ctypes.data, None if idarr is None else idarr.ctypes.data, len(words))
+        if not self.handle:
+            raise LaffError("laff_vocab_create failed: %s" % (self._lib.laff_last_error() or b"?").decode())
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                self._lib.laff_vocab_destroy(h)
+            except Exception:
+                pass
+
+
+_STOP_NATIVE = {}
+
+
+def _native_stopwords() -> NativeVocab:
+    stop = TextTool.stopwords()
+    nv = _STOP_NATIVE.get(id(stop))
+    if nv is None or nv[0] is not stop:
+        _STOP_NATIVE.clear()
+        nv = _STOP_NATIVE[id(stop)] = (stop, NativeVocab(sorted(stop)))
+    return nv[1]
+
+
+def tokenize_lookup(captions: Sequence[str], vocab: NativeVocab, mode: int, remove_stopword: bool = False, unk_id: int = -1,
+                    start_id: int = -1, end_id: int = -1):
+    """TextTool.tokenize(clean=True) + vocabulary lookup for a batch, natively (laff_tokenize_lookup).
+    mode 0: every token (unknown -> unk_id) between start_id / end_id; 1: known tokens in order; 2: distinct known ids,
+    ascending.  Returns CSR (offsets int64 [n + 1], ids int32)."""
+    from . import _capi
+    lib = _capi.lib()
+    blob, offsets = _blob(captions)
+    stop = _native_stopwords().handle if remove_stopword else None
+    cap = len(blob) // 2 + 3 * len(captions) + 8          # an upper bound on the number of tokens (+ start / end)
+    out_off = np.empty(len(captions) + 1, dtype=np.int64)
+    out_ids = np.empty(cap, dtype=np.int32)
+    n = lib.laff_tokenize_lookup(blob, offsets.ctypes.data, len(captions), vocab.handle, stop, int(mode), int(unk_id), int(start_id),
+                                 int(end_id), out_off.ctypes.data, out_ids.ctypes.data, cap)
+    if n < 0 or n > cap:
+        raise LaffError("laff_tokenize_lookup failed (%d): %s" % (n, (lib.laff_last_error() or b"?").decode()))
+    return out_off, out_ids[:n]
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # txt2vec
 # ----------------------------------------------------------------------------------------------------------------
 class Txt2Vec:
@@ -165,10 +228,22 @@ class BowVec(Txt2Vec):
     def token_ids(self, query) -> List[int]:
         return [i for i in (self.vocab.find(w) for w in self._preprocess(query)) if i >= 0]
 
+    def token_csr(self, captions):
+        """CSR token ids of a batch: the native tokeniser when clean=True (the reference's default), else per caption."""
+        if not self.clean:
+            lists = [self.token_ids(c) for c in captions]
+            off = np.zeros(len(lists) + 1, dtype=np.int64)
+            np.cumsum([len(l) for l in lists], out=off[1:])
+            return off, np.fromiter((i for l in lists for i in l), dtype=np.int32, count=int(off[-1]))
+        if getattr(self, "_native", None) is None:
+            words = list(self.vocab.word2idx.keys())
+            self._native = NativeVocab(words, [self.vocab.word2idx[w] for w in words])
+        return tokenize_lookup(captions, self._native, 1, self.remove_stopword)
+
     def encode_batch(self, captions, device=None):
         dev = _device(device)
-        offsets, ids = _csr([self.token_ids(c) for c in captions], dev)
-        return ops.bow_counts(offsets, ids, self.ndims)
+        off, ids = self.token_csr(captions)
+        return ops.bow_counts(torch.from_numpy(off).to(dev), torch.from_numpy(ids).to(dev), self.ndims)
 
     def __len__(self):
         return self.ndims
@@ -199,10 +274,20 @@ class W2Vec(Txt2Vec):
         n2i = self.w2v.name2index
         return sorted({n2i[w] for w in self._preprocess(query) if w in n2i})
 
+    def word_csr(self, captions):
+        if not self.clean:
+            lists = [self.word_ids(c) for c in captions]
+            off = np.zeros(len(lists) + 1, dtype=np.int64)
+            np.cumsum([len(l) for l in lists], out=off[1:])
+            return off, np.fromiter((i for l in lists for i in l), dtype=np.int32, count=int(off[-1]))
+        if getattr(self, "_native", None) is None:
+            self._native = NativeVocab(self.w2v.names)           # id = row in the vector file
+        return tokenize_lookup(captions, self._native, 2, self.remove_stopword)
+
     def encode_batch(self, captions, device=None):
         dev = _device(device)
-        offsets, ids = _csr([self.word_ids(c) for c in captions], dev)
-        return ops.gather_mean(self.table(dev), offsets, ids)
+        off, ids = self.word_csr(captions)
+        return ops.gather_mean(self.table(dev), torch.from_numpy(off).to(dev), torch.from_numpy(ids).to(dev))
 
 
 class W2VecNSW(W2Vec):
@@ -223,6 +308,28 @@ class IndexVec(Txt2Vec):
 
     def encoding(self, query):
         return np.array([self.vocab(word) for word in self._preprocess(query)])
+
+    def encoding_batch(self, captions):
+        """(ids int32 [B, T] zero padded, lengths int32 [B]) of a batch — what GruTxtEncoder.forward assembles caption by
+        caption (model/model.py:345-352), natively."""
+        if not self.clean:
+            vecs = [self.encoding(c) for c in captions]
+            lengths = np.array([len(v) for v in vecs], dtype=np.int32)
+            ids = np.zeros((len(vecs), int(lengths.max()) if len(vecs) else 0), dtype=np.int32)
+            for i, v in enumerate(vecs):
+                ids[i, : lengths[i]] = v
+            return ids, lengths
+        if getattr(self, "_native", None) is None:
+            words = list(self.vocab.word2idx.keys())
+            self._native = NativeVocab(words, [self.vocab.word2idx[w] for w in words])
+        unk = self.vocab.word2idx.get("<unk>", -1) if "gru" in self.vocab.encoding else -1
+        off, flat = tokenize_lookup(captions, self._native, 0, False, unk, self.vocab("<start>"), self.vocab("<end>"))
+        if (flat < 0).any():  # textlib.py:107: only a 'gru' vocabulary maps unknown words to <unk>
+            raise Exception("word out of vocab")
+        lengths = np.diff(off).astype(np.int32)
+        ids = np.zeros((len(captions), int(lengths.max()) if len(captions) else 0), dtype=np.int32)
+        ids[np.arange(ids.shape[1])[None, :] < lengths[:, None]] = flat
+        return ids, lengths
 
 
 NAME_TO_T2V = {"bow": BowVec, "bow_nsw": BowVecNSW, "w2v": W2Vec, "w2v_nsw": W2VecNSW, "idxvec": IndexVec}

@@ -87,3 +87,26 @@ def test_oracle_gru_matches_reference():
 def test_norm_other_than_zero_fails_like_the_reference():
     with pytest.raises(AttributeError):
         T.BowVec(os.path.join(D, "vocab_bow_nsw.pkl"), norm=2)
+
+
+def test_native_batch_tokeniser_equals_the_python_path():
+    """csrc/tokenize.cu (host code of the C ABI) against TextTool.tokenize + the dict lookups, on the golden captions and
+    on awkward inputs: non-ASCII text, digits, empty and all-separator strings, very long words, repeated words."""
+    bow = T.BowVecNSW(os.path.join(D, "vocab_bow_nsw.pkl"))
+    w2v = T.W2VecNSW(os.path.join(D, "w2v"))
+    idx = T.IndexVec(os.path.join(D, "vocab_gru.pkl"))
+    caps = list(META["captions"]) + ["", "   ", "?!--", "Dog dog DOG d0g", "café naïve 狗 dog", "x" * 5000 + " guitar",
+                                     "the-man_playing\tguitar\r\nand 42"]
+    off, ids = bow.token_csr(caps)
+    assert [ids[off[i]:off[i + 1]].tolist() for i in range(len(caps))] == [bow.token_ids(c) for c in caps]
+    off, ids = w2v.word_csr(caps)
+    assert [ids[off[i]:off[i + 1]].tolist() for i in range(len(caps))] == [w2v.word_ids(c) for c in caps]
+    mat, lengths = idx.encoding_batch(caps)
+    for i, c in enumerate(caps):
+        ref = idx.encoding(c).tolist()
+        assert lengths[i] == len(ref) and mat[i, : lengths[i]].tolist() == ref and not mat[i, lengths[i]:].any()
+    for c, ref in zip(META["captions"], META["index"]):                   # and against the reference itself
+        assert idx.encoding_batch([c])[0][0].tolist() == ref
+    bow_plain = T.BowVec(None, vocab=T.load_vocab(os.path.join(D, "vocab_bow_nsw.pkl")))   # a non-'gru' vocabulary has no <unk>
+    with pytest.raises(Exception, match="word out of vocab"):
+        T.IndexVec(None, vocab=bow_plain.vocab).encoding_batch(["zebra"])
