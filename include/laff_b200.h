@@ -67,6 +67,8 @@ int laff_get_tuning(int* cta_group, int* chunk_tiles, int* m_group);
  * 1 = cta_group::1 MMAs in 2-CTA clusters (all SMs), 2 = cta_group::2 MMA pairs in 4-CTA clusters (fewer bytes per
  * SM per k-block; 33 clusters fit a 148-SM B200).  Results are identical; only the speed differs. */
 int laff_set_fuse_variant(int cta_group);
+/* Debug: cycle counters of the fused kernel's epilogue phases (zeros unless built with -DLAFF_FUSE_PROFILE). */
+int laff_debug_fuse_profile(unsigned long long* out8, int reset);
 int laff_get_fuse_variant(void);
 
 /* ---------------------------------------------------------------------------------------------------------------

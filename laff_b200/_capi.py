@@ -82,6 +82,7 @@ SIGNATURES = {
     "laff_launch_count": (C.c_longlong, [_i]),
     "laff_set_tuning": (_i, [_i, _i, _i]),
     "laff_get_tuning": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "laff_debug_fuse_profile": (_i, [_vp, _i]),
     "laff_set_fuse_variant": (_i, [_i]),
     "laff_get_fuse_variant": (_i, []),
     "laff_l2norm_quantize": (_i, [_vp, _ll, _i, _i, _ll, _d, _i, _vp, _ll, _vp]),

@@ -58,7 +58,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            extra = os.environ.get("LAFF_NVCC_EXTRA", "").split()   # e.g. -DLAFF_FUSE_PROFILE for tools/profile_fuse_phases.py
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
 
     def run(cmd):

@@ -36,6 +36,12 @@ constexpr int kFuseBarBytes = 256;
 constexpr int kFuseParamBufs = 3;                          // see the staging protocol in the epilogue
 constexpr int kFuseParamFloats = kFuseParamBufs * 4 * kBlockN;  // per buffer: {bias, scale, shift, w_h} x 256 columns
 constexpr int kFuseXchgFloats = 2 * 4 * kBlockM;            // [parity][partial][row]
+// Warp-private 32-row x 64-byte transposition tiles (one per epilogue warp).  An epilogue thread owns a ROW, so its
+// natural global accesses are 16 bytes at 32 different rows per warp instruction (32 half-used sectors).  Through the
+// tile a warp instruction moves 8 rows x 64 contiguous bytes instead: 4x fewer lines, every sector fully used.
+constexpr int kFuseTileRowBytes = 64;
+constexpr int kFuseTileWarpBytes = 32 * kFuseTileRowBytes;
+constexpr int kFuseTileBytes = kEpiWarps * kFuseTileWarpBytes;
 template <int CG>
 struct FuseCfg {
   static constexpr int kStages = (CG == 2) ? 6 : 4;
@@ -45,7 +51,8 @@ struct FuseCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTxBytes = kStageBytes * CG;              // bytes landing per stage on the MMA issuer's barrier
   static constexpr int kCluster = 2 * CG;
-  static constexpr int kSmem = kStages * kStageBytes + kFuseBarBytes + (kFuseParamFloats + kFuseXchgFloats) * 4 + 1024;
+  static constexpr int kSmem = kStages * kStageBytes + kFuseBarBytes + (kFuseParamFloats + kFuseXchgFloats) * 4 +
+                               kFuseTileBytes + 1024;
   static_assert(kSmem <= 227 * 1024, "fused kernel shared memory budget");
 };
 
@@ -78,6 +85,17 @@ struct FuseParams {
   uint32_t idesc;
   int total_units;
 };
+
+#ifdef LAFF_FUSE_PROFILE
+// Phase timers of the epilogue (cycles, one sampling thread: CTA 0, warp 4, lane 0); read by laff_debug_fuse_profile.
+__device__ unsigned long long g_fuse_prof[8];
+#define LAFF_PROF_T(var) const long long var = clock64()
+#define LAFF_PROF_ADD(slot, a, b) \
+  if (blockIdx.x == 0 && threadIdx.x == 128) atomicAdd(&g_fuse_prof[slot], static_cast<unsigned long long>((b) - (a)))
+#else
+#define LAFF_PROF_T(var)
+#define LAFF_PROF_ADD(slot, a, b)
+#endif
 
 namespace fptx {
 __device__ __forceinline__ void setmaxnreg_dec56() { asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory"); }
@@ -217,6 +235,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
       reinterpret_cast<volatile uint32_t*>(smem + kFuseStages * kFuseStageBytes + 8 * (2 * kFuseStages + 6));
   float* s_param = reinterpret_cast<float*>(smem + kFuseStages * kFuseStageBytes + kFuseBarBytes);
   float* s_xchg = s_param + kFuseParamFloats;
+  uint8_t* s_tiles = reinterpret_cast<uint8_t*>(s_xchg + kFuseXchgFloats);
   const uint32_t s_xchg_addr = bar0 + kFuseBarBytes + kFuseParamFloats * 4;
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -334,6 +353,11 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t xchg_count = 0;  // exchanges done so far: parity = count & 1, phase = (count >> 1) & 1
+    // transposition tile of this warp: 16-byte piece c (0..3) of row r sits at r * 64 + 16 * (c ^ ((r >> 1) & 3)), which
+    // makes both the row-per-thread accesses and the 4-lanes-per-row accesses bank-conflict free
+    uint8_t* tile = s_tiles + (warp - 4) * kFuseTileWarpBytes;
+    auto tile_at = [&](int r, int c) -> uint4* { return reinterpret_cast<uint4*>(tile + r * kFuseTileRowBytes + 16 * (c ^ ((r >> 1) & 3))); };
+    const int t_row = lane >> 2, t_piece = lane & 3;   // coalesced side: lane handles piece t_piece of rows t_row + 8 i
 
     // All-to-all of one float per (row, partial) among the 4 owners of a row (2 column halves x 2 CTAs); returns the
     // sum in a fixed order, identical in all four threads.  post() publishes, collect() waits: independent work placed
@@ -439,28 +463,56 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           const float* xrow = p.tiled_x[l] + (row_ok ? row : 0) * p.tiled_ld[l];
           const int xoff = (colbase + mycol) % p.tiled_in_dim[l];  // in_dim is a multiple of 128: 128 consecutive columns never wrap
           float part = 0.f;
+          LAFF_PROF_T(pt0);
           if (f == 0) {
             // First feature of the row: its weight is exp(0) = 1 whatever its logit turns out to be, so y goes
             // straight into g and no second pass is needed.
+            // 16-column chunks: 4 coalesced loads per lane (8 rows x 64 bytes per warp instruction), next chunk in flight
+            const long long row0 = static_cast<long long>(row_tile) * kUnitRows + row_sub * kBlockM + quad * 32;
+            auto load_chunk = [&](int k, float4 (&v)[4]) {
 #pragma unroll
-            for (int cc = 0; cc < kEpiCols; cc += 4) {
-              const float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(xrow + xoff + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float4 sc4 = *reinterpret_cast<const float4*>(p1 + cc);
-              const float4 sh4 = *reinterpret_cast<const float4*>(p2 + cc);
-              const float4 w4 = *reinterpret_cast<const float4*>(pw + cc);
-              g[cc] = fmaf(v.x, sc4.x, sh4.x);
-              g[cc + 1] = fmaf(v.y, sc4.y, sh4.y);
-              g[cc + 2] = fmaf(v.z, sc4.z, sh4.z);
-              g[cc + 3] = fmaf(v.w, sc4.w, sh4.w);
-              part = fmaf(w4.x, g[cc], part);
-              part = fmaf(w4.y, g[cc + 1], part);
-              part = fmaf(w4.z, g[cc + 2], part);
-              part = fmaf(w4.w, g[cc + 3], part);
+              for (int i = 0; i < 4; ++i) {
+                const long long rr = row0 + t_row + 8 * i;
+                v[i] = rr < p.rows ? __ldg(reinterpret_cast<const float4*>(p.tiled_x[l] + rr * p.tiled_ld[l] + xoff + 16 * k + 4 * t_piece))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            };
+            float4 cur[4], nxt[4];
+            load_chunk(0, cur);
+#pragma unroll
+            for (int k = 0; k < kEpiCols / 16; ++k) {
+              if (k + 1 < kEpiCols / 16) load_chunk(k + 1, nxt);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(tile_at(t_row + 8 * i, t_piece)) = cur[i];
+              __syncwarp();
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int cc = 16 * k + 4 * c;
+                const float4 v = *reinterpret_cast<const float4*>(tile_at(lane, c));
+                const float4 sc4 = *reinterpret_cast<const float4*>(p1 + cc);
+                const float4 sh4 = *reinterpret_cast<const float4*>(p2 + cc);
+                const float4 w4 = *reinterpret_cast<const float4*>(pw + cc);
+                g[cc] = fmaf(v.x, sc4.x, sh4.x);
+                g[cc + 1] = fmaf(v.y, sc4.y, sh4.y);
+                g[cc + 2] = fmaf(v.z, sc4.z, sh4.z);
+                g[cc + 3] = fmaf(v.w, sc4.w, sh4.w);
+                part = fmaf(w4.x, g[cc], part);
+                part = fmaf(w4.y, g[cc + 1], part);
+                part = fmaf(w4.z, g[cc + 2], part);
+                part = fmaf(w4.w, g[cc + 3], part);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
             }
+            LAFF_PROF_T(ptm);
             if (has_next) store_params(next_buf, nextp);
             post(part);
             m_ref = collect() + __ldg(p.att_b + head);
             stage_buf = next_buf;
+            LAFF_PROF_T(pt1);
+            LAFF_PROF_ADD(5, pt0, ptm);   // loads + math of the first tiled feature
+            LAFF_PROF_ADD(2, ptm, pt1);   // its exchange goes to the 'post' slot (debug only)
             continue;
           }
 #pragma unroll 1
@@ -497,8 +549,10 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 
         // ---------------- projected feature: the accumulator of its GEMM is in TMEM buffer `acc` ----------------
         const ActCoef ak = make_act(p.act[l]);
+        LAFF_PROF_T(q0);
         ptx::mbar_wait(tfull_bar(acc), acc_phase, 15);
         ptx::tcgen05_fence_after();
+        LAFF_PROF_T(q1);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * kBlockN + mycol);
         // ---- pass A: y = BN(act(acc + b)) written back to TMEM in place, partial logit over my 128 columns.  The
         //      TMEM load of chunk c + 1 is in flight while chunk c is computed. ----
@@ -522,10 +576,13 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           }
           ptx::tmem_st_wait();
         }
+        LAFF_PROF_T(q2);
         if (has_next) store_params(next_buf, nextp);
         post(part);
+        LAFF_PROF_T(q3);
         // ---- pass B: g += exp(e - m_ref) * y (the softmax denominator cancels under the final L2 norm) ----
         const float pe = rebase(collect() + __ldg(p.att_b + head));
+        LAFF_PROF_T(q4);
         {
           uint32_t ra[kFuseChunk], rb[kFuseChunk];
           ptx::tmem_ld_32x32b_x16(taddr, ra);
@@ -548,50 +605,82 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
           else ptx::mbar_arrive_remote(tempty_bar(acc), leader);
         }
+        LAFF_PROF_T(q5);
+        LAFF_PROF_ADD(0, q0, q1);
+        LAFF_PROF_ADD(1, q1, q2);
+        LAFF_PROF_ADD(2, q2, q3);
+        LAFF_PROF_ADD(3, q3, q4);
+        LAFF_PROF_ADD(4, q4, q5);
+        LAFF_PROF_ADD(7, 0, 1);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         stage_buf = next_buf;
       }
+      LAFF_PROF_T(fin0);
       // ---- L2 normalise over the whole head (4 partial sums of squares per row) and write ----
       float ss = 0.f;
 #pragma unroll
       for (int j = 0; j < kEpiCols; ++j) ss = fmaf(g[j], g[j], ss);
+      LAFF_PROF_T(fin_a);
       post(ss);
       const float den = sqrtf(collect()) + p.norm_eps;
+      LAFF_PROF_T(fin_b);
+      LAFF_PROF_ADD(3, fin_a, fin_b);     // exchange of the final normalisation goes to the 'collect' slot (debug only)
       const float inv = 1.0f / den;  // one IEEE division per row; x * (1/den) is within 1 ulp of x / den
 #pragma unroll
       for (int j = 0; j < kEpiCols; ++j) g[j] *= inv;
-      if (row_ok) {
+      {
         const long long c0 = colbase + mycol;
-        if (p.out) {
-          float* o = p.out + row * p.ld_out + c0;
+        const long long row0 = static_cast<long long>(row_tile) * kUnitRows + row_sub * kBlockM + quad * 32;
+        if (p.out) {  // fp32: 16 columns (64 bytes) of every row per round
 #pragma unroll
-          for (int j = 0; j < kEpiCols; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+          for (int k = 0; k < kEpiCols / 16; ++k) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<float4*>(tile_at(lane, c)) = make_float4(g[16 * k + 4 * c], g[16 * k + 4 * c + 1], g[16 * k + 4 * c + 2],
+                                                                         g[16 * k + 4 * c + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const long long rr = row0 + t_row + 8 * i;
+              if (rr < p.rows) *reinterpret_cast<uint4*>(p.out + rr * p.ld_out + c0 + 16 * k + 4 * t_piece) = *tile_at(t_row + 8 * i, t_piece);
+            }
+            __syncwarp();
+          }
         }
-        if (p.out16) {
-          uint16_t* o = static_cast<uint16_t*>(p.out16) + row * p.ld_out16 + c0;
-          if (p.out16_dtype == LAFF_BF16) {
+        if (p.out16) {  // 16-bit: 32 columns (64 bytes) of every row per round
+          uint16_t* o16 = static_cast<uint16_t*>(p.out16);
 #pragma unroll
-            for (int j = 0; j < kEpiCols; j += 8) {
-              __nv_bfloat162 a0 = __floats2bfloat162_rn(g[j], g[j + 1]), a1 = __floats2bfloat162_rn(g[j + 2], g[j + 3]);
-              __nv_bfloat162 a2 = __floats2bfloat162_rn(g[j + 4], g[j + 5]), a3 = __floats2bfloat162_rn(g[j + 6], g[j + 7]);
-              uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
-              pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
-              *reinterpret_cast<uint4*>(o + j) = pk;
-            }
-          } else {
+          for (int k = 0; k < kEpiCols / 32; ++k) {
 #pragma unroll
-            for (int j = 0; j < kEpiCols; j += 8) {
-              __half2 a0 = __floats2half2_rn(g[j], g[j + 1]), a1 = __floats2half2_rn(g[j + 2], g[j + 3]);
-              __half2 a2 = __floats2half2_rn(g[j + 4], g[j + 5]), a3 = __floats2half2_rn(g[j + 6], g[j + 7]);
+            for (int c = 0; c < 4; ++c) {
+              const int j = 32 * k + 8 * c;
               uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
-              pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
-              *reinterpret_cast<uint4*>(o + j) = pk;
+              if (p.out16_dtype == LAFF_BF16) {
+                __nv_bfloat162 a0 = __floats2bfloat162_rn(g[j], g[j + 1]), a1 = __floats2bfloat162_rn(g[j + 2], g[j + 3]);
+                __nv_bfloat162 a2 = __floats2bfloat162_rn(g[j + 4], g[j + 5]), a3 = __floats2bfloat162_rn(g[j + 6], g[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
+                pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+              } else {
+                __half2 a0 = __floats2half2_rn(g[j], g[j + 1]), a1 = __floats2half2_rn(g[j + 2], g[j + 3]);
+                __half2 a2 = __floats2half2_rn(g[j + 4], g[j + 5]), a3 = __floats2half2_rn(g[j + 6], g[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
+                pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+              }
+              *tile_at(lane, c) = pk;
             }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const long long rr = row0 + t_row + 8 * i;
+              if (rr < p.rows) *reinterpret_cast<uint4*>(o16 + rr * p.ld_out16 + c0 + 32 * k + 8 * t_piece) = *tile_at(t_row + 8 * i, t_piece);
+            }
+            __syncwarp();
           }
         }
       }
+      LAFF_PROF_T(fin1);
+      LAFF_PROF_ADD(6, fin_b, fin1);      // scale + stores
+      LAFF_PROF_ADD(4, fin0, fin_a);      // sum of squares goes to the 'pass B' slot (debug only)
     }
   }
 
@@ -658,6 +747,23 @@ int fuse_launch(const FuseTmaps& tm, const FuseParams& p, int clusters, cudaStre
 }
 
 }  // namespace
+
+// Debug: phase cycle counters of the fused kernel's epilogue (all zero unless the library was built with
+// -DLAFF_FUSE_PROFILE): [wait accumulator, pass A, post, collect, pass B, first tiled feature, normalise + store, #features].
+extern "C" int laff_debug_fuse_profile(unsigned long long* out8, int reset) {
+  LAFF_REQUIRE(out8, LAFF_EINVAL, "laff_debug_fuse_profile: bad arguments");
+#ifdef LAFF_FUSE_PROFILE
+  LAFF_CUDA(cudaMemcpyFromSymbol(out8, g_fuse_prof, sizeof(unsigned long long) * 8));
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    LAFF_CUDA(cudaMemcpyToSymbol(g_fuse_prof, z, sizeof(z)));
+  }
+#else
+  (void)reset;
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+#endif
+  return LAFF_OK;
+}
 
 extern "C" int laff_set_fuse_variant(int cta_group) {
   LAFF_REQUIRE(cta_group >= 0 && cta_group <= 2, LAFF_EINVAL, "laff_set_fuse_variant: cta_group must be 0 (auto), 1 or 2");
