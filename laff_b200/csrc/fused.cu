@@ -167,6 +167,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
 constexpr int kFuseChunk = 16;
 __device__ __forceinline__ float pass_a_chunk(uint32_t (&r)[kFuseChunk], const float* p0, const float* p1, const float* p2,
                                               const float* pw, const ActCoef& ak, float part) {
+  auto act1 = [&](uint32_t acc, float n, float a, float c) -> float {
+    return fmaf(a, rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(acc), ak.neg_s, n))), c);
+  };
   if (ak.sigm) {
 #pragma unroll
     for (int j = 0; j < kFuseChunk; j += 4) {
@@ -174,10 +177,10 @@ __device__ __forceinline__ float pass_a_chunk(uint32_t (&r)[kFuseChunk], const f
       const float4 a4 = *reinterpret_cast<const float4*>(p1 + j);
       const float4 c4 = *reinterpret_cast<const float4*>(p2 + j);
       const float4 w4 = *reinterpret_cast<const float4*>(pw + j);
-      const float y0 = fmaf(a4.x, rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(r[j]), ak.neg_s, n4.x))), c4.x);
-      const float y1 = fmaf(a4.y, rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(r[j + 1]), ak.neg_s, n4.y))), c4.y);
-      const float y2 = fmaf(a4.z, rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(r[j + 2]), ak.neg_s, n4.z))), c4.z);
-      const float y3 = fmaf(a4.w, rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(r[j + 3]), ak.neg_s, n4.w))), c4.w);
+      const float y0 = act1(r[j], n4.x, a4.x, c4.x);
+      const float y1 = act1(r[j + 1], n4.y, a4.y, c4.y);
+      const float y2 = act1(r[j + 2], n4.z, a4.z, c4.z);
+      const float y3 = act1(r[j + 3], n4.w, a4.w, c4.w);
       part = fmaf(w4.x, y0, part);
       part = fmaf(w4.y, y1, part);
       part = fmaf(w4.z, y2, part);
@@ -467,23 +470,24 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           if (f == 0) {
             // First feature of the row: its weight is exp(0) = 1 whatever its logit turns out to be, so y goes
             // straight into g and no second pass is needed.
-            // 16-column chunks: 4 coalesced loads per lane (8 rows x 64 bytes per warp instruction), next chunk in flight
+            // 16-column chunks: 4 coalesced loads per lane (8 rows x 64 bytes per warp instruction).  All 8 chunks are
+            // requested before the first one is used -- g is still empty, so the 128 registers are free -- and the
+            // global-load latency is paid once per unit instead of once per chunk.
             const long long row0 = static_cast<long long>(row_tile) * kUnitRows + row_sub * kBlockM + quad * 32;
-            auto load_chunk = [&](int k, float4 (&v)[4]) {
+            float4 xv[kEpiCols / 16][4];
+#pragma unroll
+            for (int k = 0; k < kEpiCols / 16; ++k) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const long long rr = row0 + t_row + 8 * i;
-                v[i] = rr < p.rows ? __ldg(reinterpret_cast<const float4*>(p.tiled_x[l] + rr * p.tiled_ld[l] + xoff + 16 * k + 4 * t_piece))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[k][i] = rr < p.rows ? __ldg(reinterpret_cast<const float4*>(p.tiled_x[l] + rr * p.tiled_ld[l] + xoff + 16 * k + 4 * t_piece))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
               }
-            };
-            float4 cur[4], nxt[4];
-            load_chunk(0, cur);
+            }
 #pragma unroll
             for (int k = 0; k < kEpiCols / 16; ++k) {
-              if (k + 1 < kEpiCols / 16) load_chunk(k + 1, nxt);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(tile_at(t_row + 8 * i, t_piece)) = cur[i];
+              for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(tile_at(t_row + 8 * i, t_piece)) = xv[k][i];
               __syncwarp();
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
@@ -502,8 +506,6 @@ __global__ void __launch_bounds__(kNumThreads, 1)
                 part = fmaf(w4.w, g[cc + 3], part);
               }
               __syncwarp();
-#pragma unroll
-              for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
             }
             LAFF_PROF_T(ptm);
             if (has_next) store_params(next_buf, nextp);
@@ -583,6 +585,8 @@ __global__ void __launch_bounds__(kNumThreads, 1)
         // ---- pass B: g += exp(e - m_ref) * y (the softmax denominator cancels under the final L2 norm) ----
         const float pe = rebase(collect() + __ldg(p.att_b + head));
         LAFF_PROF_T(q4);
+        //      (Measured: requesting 48 columns at a time -- x32 + x16 loads in flight -- is slower than this x16 ping-pong,
+        //      2.6 k against 2.0 k cycles per feature in the pair variant, where the MMAs keep the TMEM port busy.)
         {
           uint32_t ra[kFuseChunk], rb[kFuseChunk];
           ptx::tmem_ld_32x32b_x16(taddr, ra);
@@ -820,8 +824,15 @@ extern "C" int laff_fuse_forward(const laff_fuse_desc* d, long long rows, float*
   p.n_tiled = d->n_tiled;
   p.heads = d->heads;
   p.rows = rows;
+  // Processing order of the projected features: widest first (stable).  The pooled sum does not depend on the order
+  // beyond rounding, but the pipeline does: the MMAs of feature l + 2 can only start once the epilogue has released
+  // the TMEM buffer of feature l, so a wide GEMM placed last in a unit leaves the epilogue waiting for it.
+  int order[LAFF_FUSE_MAX_FC];
+  for (int l = 0; l < d->n_fc; ++l) order[l] = l;
+  for (int a = 1; a < d->n_fc; ++a)
+    for (int b = a; b > 0 && d->fc[order[b]].K > d->fc[order[b - 1]].K; --b) { const int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t; }
   for (int l = 0; l < d->n_fc; ++l) {
-    const auto& f = d->fc[l];
+    const auto& f = d->fc[order[l]];
     LAFF_REQUIRE(f.x16 && f.w16 && f.K > 0 && f.K % 8 == 0 && f.ldx % 8 == 0 && f.ldw % 8 == 0 && f.ldx >= f.K && f.ldw >= f.K,
                  LAFF_EINVAL, "laff_fuse_forward: fc feature %d: K and pitches must be multiples of 8", l);
     LAFF_REQUIRE((f.bn_scale == nullptr) == (f.bn_shift == nullptr) && f.activation >= 0 && f.activation <= 3, LAFF_EINVAL,

@@ -542,7 +542,7 @@ class MultiScaleTxtEncoderAttention(nn.Module):
             return front(caption_feat_dict)["text_features"]
         raise KeyError("caption_feat_dict has no feature for %s (expected one of %s)" % (enc, dict(_TXT_ENCODERS)[enc]))
 
-    def encode(self, caption_feat_dict, out16_dtype=None, precision=None, want_att=False):
+    def encode(self, caption_feat_dict, out16_dtype=None, precision=None, want_att=False, want_f32=True):
         precision = precision or _loss.get_precision()
         dev = _cuda_device(self.attention_layer.layer_norm.weight.device)
         if self.training:
@@ -550,7 +550,7 @@ class MultiScaleTxtEncoderAttention(nn.Module):
         mods = dict(self.transform_layer.named_children())
         feats = [(self._feature(caption_feat_dict, n).to(dev, non_blocking=True).float(), mods[n + "_transform"])
                  for n in self.encoder_name_list]
-        return _fuse(feats, self.attention_layer, dev, precision, out16_dtype, want_att)
+        return _fuse(feats, self.attention_layer, dev, precision, out16_dtype, want_att, want_f32)
 
     def forward(self, caption_feat_dict, visual_emb=None, task3=False):
         return self.encode(caption_feat_dict)[0]
