@@ -27,6 +27,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm (rank 0 only) is meant to use all host cores, and
+# the BLAS behind numpy reads the variable when it is imported -- so this has to happen before the imports below.
+if "reference" in sys.argv[1:] and os.environ.get("RANK", "0") == "0":
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+# stdout carries exactly one JSON line: keep NCCL's version banner out of it (NCCL_DEBUG=VERSION -- from the environment
+# or an nccl.conf, which the environment overrides -- prints it to stdout)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -366,8 +376,9 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = Q / (e2e_ms / args.steps * 1e-3)
     n_local = hi - lo
     achieved = Q * n_local * FLOP_PER_PAIR / (sweep_avg_ms * 1e-3) / 1e12
-    h2d = sum(v.numel() * v.element_size() for v in feats_host.values()) + gt_host.numel() * 4
-    d2h = Q * 4 + Q * TOPK * 8 + 8 * 8
+    # summed over the ranks: every rank copies its 1/W slice of the query features and the whole ground-truth vector
+    h2d = sum(v.numel() * v.element_size() for v in feats_host.values()) + world * gt_host.numel() * 4
+    d2h = world * (Q * 4 + Q * TOPK * 8 + 8 * 8)   # every rank reads the (replicated) ranks, top-k lists and metrics back
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

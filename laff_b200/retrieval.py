@@ -182,26 +182,39 @@ class Retriever:
         self.index = index
         self.out16_dtype = out16_dtype
 
+    def query_slice(self, Q: int):
+        """Rows [lo, hi) of a Q-query batch that this rank fuses, and the per-rank slot size of the all-gather."""
+        W, r = self.index.world_size, self.index.rank
+        per = (Q + W - 1) // W
+        return min(Q, r * per), min(Q, (r + 1) * per), per
+
     @torch.no_grad()
-    def encode_queries(self, caption_feat_dict) -> torch.Tensor:
+    def encode_queries(self, caption_feat_dict, total: Optional[int] = None) -> torch.Tensor:
         """Fused 16-bit query embeddings [Q, H*d_h], replicated on every rank.  With W > 1 ranks each rank fuses only
         its 1/W slice of the queries (the fusion is data-parallel per item) and the slices are all-gathered over
-        NVLink, so the replicated part of a step shrinks with W."""
+        NVLink, so the replicated part of a step shrinks with W.  `total` = Q says that caption_feat_dict already holds
+        only this rank's slice (query_slice(Q)) of a Q-query batch -- host callers then copy 1/W of the features."""
         idx = self.index
-        W, r = idx.world_size, idx.rank
+        W = idx.world_size
         if W == 1:
             _, q16 = self.txt_net.encode(caption_feat_dict, out16_dtype=self.out16_dtype)
             return q16.reshape(q16.shape[0], -1)
-        Q = next(iter(caption_feat_dict.values())).shape[0]
-        per = (Q + W - 1) // W
-        lo, hi = min(Q, r * per), min(Q, (r + 1) * per)
-        part = {k: v[lo:hi] for k, v in caption_feat_dict.items()}
-        _, q16 = self.txt_net.encode(part, out16_dtype=self.out16_dtype)
-        q16 = q16.reshape(hi - lo, -1)
-        D = q16.shape[1]
-        buf = torch.zeros((per, D), dtype=q16.dtype, device=q16.device)
-        buf[: hi - lo] = q16
-        out = torch.empty((W * per, D), dtype=q16.dtype, device=q16.device)
+        if total is None:
+            Q = next(iter(caption_feat_dict.values())).shape[0]
+            lo, hi, per = self.query_slice(Q)
+            part = {k: v[lo:hi] for k, v in caption_feat_dict.items()}
+        else:
+            Q = int(total)
+            lo, hi, per = self.query_slice(Q)
+            part = caption_feat_dict
+            if next(iter(part.values())).shape[0] != hi - lo:
+                raise ValueError("encode_queries(total=%d): expected this rank's %d rows" % (Q, hi - lo))
+        D = idx.g16.shape[1]
+        buf = torch.zeros((per, D), dtype=idx.g16.dtype if self.out16_dtype is None else self.out16_dtype, device=idx.g16.device)
+        if hi > lo:
+            _, q16 = self.txt_net.encode(part, out16_dtype=self.out16_dtype)
+            buf[: hi - lo] = q16.reshape(hi - lo, -1)
+        out = torch.empty((W * per, D), dtype=buf.dtype, device=buf.device)
         dist.all_gather_into_tensor(out, buf, group=idx.group)
         return out[:Q]
 
@@ -233,17 +246,18 @@ class Retriever:
         with torch.cuda.stream(cs):
             for lo in range(0, Q, per):
                 hi = min(Q, lo + per)
-                part = {name: v[lo:hi].to(dev, non_blocking=True) for name, v in caption_feat_dict.items()}
+                a, b, _ = self.query_slice(hi - lo)         # this rank fuses rows [lo + a, lo + b) of the piece
+                part = {name: v[lo + a:lo + b].to(dev, non_blocking=True) for name, v in caption_feat_dict.items()}
                 g = gt_global[lo:hi].to(dev, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cs)
-                staged.append((part, g, ev))
+                staged.append((part, g, ev, hi - lo))
         outs = []
-        for part, g, ev in staged:
+        for part, g, ev, n in staged:
             main.wait_event(ev)
             for t in list(part.values()) + [g]:
                 t.record_stream(main)
-            q16 = self.encode_queries(part)
+            q16 = self.encode_queries(part, total=n)
             res = self.index.search(q16, g, k)
             outs.append(res)
         rank0 = torch.cat([r.rank0 for r in outs])

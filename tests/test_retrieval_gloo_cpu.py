@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from laff_b200 import synth
-from laff_b200.retrieval import GalleryIndex, shard_bounds
+from laff_b200.retrieval import GalleryIndex, Retriever, shard_bounds
 from oracle import laff_oracle as O
 
 
@@ -75,6 +75,16 @@ def _problem(Q=48, V=301, H=4, dh=16):
     return synth.bf16_round(q), synth.bf16_round(g), gt, H
 
 
+class _StubTxtNet:
+    """Stands in for MultiScaleTxtEncoderAttention.encode on CPU: a fixed per-row map to [rows, H, d_h] 16-bit."""
+
+    def encode(self, feats, out16_dtype=None, **kw):
+        x = feats["x"].float()
+        H = 4
+        y = torch.tanh(x * 3.0 + 0.25).reshape(x.shape[0], H, -1)
+        return y, y.to(out16_dtype)
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -84,8 +94,23 @@ def _worker(rank, world, port, out):
         idx = GalleryIndex(torch.from_numpy(g[lo:hi]).to(torch.bfloat16), g.shape[0], H, rank, world, backend=NumpyBackend())
         res = idx.search(torch.from_numpy(q).to(torch.bfloat16), torch.from_numpy(gt), k=7)
         lv, li = idx.ranked_lists(torch.from_numpy(q).to(torch.bfloat16), k=150, query_chunk=20)
+        # query fusion is sharded too: every rank encodes 1/W of the queries and the slices are all-gathered; a host
+        # caller may hand over only its own slice (total=Q) -- both must reproduce the unsharded embeddings, also when
+        # the last ranks get short or empty slices (Q = 5, W = 3)
+        retr = Retriever(_StubTxtNet(), idx)
+        enc_ok = True
+        for Qs in (q.shape[0], 5, 1):
+            feats = {"x": torch.from_numpy(q[:Qs]).clone()}
+            want = _StubTxtNet().encode(feats, out16_dtype=torch.bfloat16)[1].reshape(Qs, -1)
+            a, b, _ = retr.query_slice(Qs)
+            full = retr.encode_queries(feats)
+            pre = retr.encode_queries({"x": feats["x"][a:b]}, total=Qs)
+            enc_ok = enc_ok and torch.equal(full, want) and torch.equal(pre, want)
+        oks = [None] * world
+        dist.all_gather_object(oks, bool(enc_ok))
         if rank == 0:
-            torch.save({"rank0": res.rank0, "tv": res.topk_val, "ti": res.topk_idx, "m": res.metrics, "lv": lv, "li": li}, out)
+            torch.save({"rank0": res.rank0, "tv": res.topk_val, "ti": res.topk_idx, "m": res.metrics, "lv": lv, "li": li,
+                        "enc_ok": all(oks)}, out)
     finally:
         dist.destroy_process_group()
 
@@ -98,6 +123,7 @@ def test_sharded_search_equals_single_shard(world, tmp_path):
     q, g, gt, H = _problem()
     single = GalleryIndex(torch.from_numpy(g).to(torch.bfloat16), g.shape[0], H, backend=NumpyBackend())
     ref = single.search(torch.from_numpy(q).to(torch.bfloat16), torch.from_numpy(gt), k=7)
+    assert got["enc_ok"]
     assert torch.equal(got["rank0"], ref.rank0)
     assert torch.equal(got["ti"], ref.topk_idx)
     assert torch.allclose(got["tv"], ref.topk_val, atol=0, rtol=0)

@@ -16,7 +16,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from laff_b200 import synth  # noqa: E402
-from laff_b200.retrieval import GalleryIndex, shard_bounds  # noqa: E402
+from laff_b200.retrieval import GalleryIndex, Retriever, shard_bounds  # noqa: E402
 
 
 def main():
@@ -37,13 +37,23 @@ def main():
     lo, hi = shard_bounds(V, world, rank)
     res = GalleryIndex(g16[lo:hi].contiguous(), V, H, rank, world).search(q16, gt.to(torch.int32), k)
     lv, li = GalleryIndex(g16[lo:hi].contiguous(), V, H, rank, world).ranked_lists(q16[:300], 500, query_chunk=128)
+    # the public query path: pinned host features in 3 pieces, each rank copies and fuses only its slice of every piece
+    import bench  # noqa: E402  (synthetic text net + query features of the bench)
+    txt_net = bench.build_txt_net(dev)
+    feats = bench.query_features(1001, pinned=True)
+    gt2 = ((torch.arange(1001) * 97) % V).to(torch.int32)
+    rr = Retriever(txt_net, GalleryIndex(g16[lo:hi].contiguous(), V, H, rank, world)).rank(feats, gt2.pin_memory(), k, chunks=3)
     torch.cuda.synchronize()
     ok = True
+    if rank == 0:
+        r1 = Retriever(txt_net, GalleryIndex(g16, V, H)).rank({n: v.to(dev) for n, v in feats.items()}, gt2.to(dev), k)
+        ok = torch.equal(rr.rank0, r1.rank0) and torch.equal(rr.topk_idx, r1.topk_idx) and torch.equal(rr.topk_val, r1.topk_val)
+        print("sharded query fusion + chunked host copies vs single process: %s" % ("OK" if ok else "MISMATCH"), flush=True)
     if rank == 0:
         single = GalleryIndex(g16, V, H)
         ref = single.search(q16, gt.to(torch.int32), k)
         rv, ri = single.ranked_lists(q16[:300], 500, query_chunk=128)
-        ok = (torch.equal(res.rank0, ref.rank0) and torch.equal(res.topk_idx, ref.topk_idx)
+        ok = ok and (torch.equal(res.rank0, ref.rank0) and torch.equal(res.topk_idx, ref.topk_idx)
               and torch.equal(res.topk_val, ref.topk_val) and torch.equal(res.metrics, ref.metrics)
               and torch.equal(li, ri) and torch.equal(lv, rv) and torch.equal(ri[:, :k], ref.topk_idx[:300]))
         print("multi-GPU parity world=%d: %s  R@1=%.2f R@10=%.2f MedR=%.0f" % (
