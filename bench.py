@@ -32,10 +32,9 @@ sys.path.insert(0, ROOT)
 if "reference" in sys.argv[1:] and os.environ.get("RANK", "0") == "0":
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(os.cpu_count() or 1)
-# stdout carries exactly one JSON line: keep NCCL's version banner out of it (NCCL_DEBUG=VERSION -- from the environment
-# or an nccl.conf, which the environment overrides -- prints it to stdout)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line: NCCL writes its version banner / warnings (NCCL_DEBUG=VERSION|WARN|INFO, from the
+# environment or an nccl.conf) to stdout unless told otherwise
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -430,9 +429,14 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode-b-steps", type=int, default=2, help="timed steps of the mode-B leg (0 = skip it)")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="query pieces whose H2D copies overlap the sweep (e2e leg)")
+    ap.add_argument("--e2e-chunks", type=int, default=0,
+                    help="query pieces whose H2D copies overlap the sweep in the e2e leg (0 = by world size: 4 / 2 / 1 / 1 "
+                         "at 1 / 2 / 4 / 8 GPUs -- a piece costs a fixed ~0.7 ms of launches and collectives, worth it "
+                         "only while the per-rank copy is a visible share of the step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.e2e_chunks <= 0:
+        args.e2e_chunks = max(1, 4 // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

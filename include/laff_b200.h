@@ -98,6 +98,15 @@ int laff_cast_pad_16(const float* x, long long rows, int cols, long long ldx, in
 int laff_sim_dense(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
                    float scale, float* out, long long ld_out, void* stream);
 
+/* N1 at gallery scale (predictor.py:53-88: the top-2000 / top-500 lists per query) without the dense Q x V matrix:
+ *     the same tcgen05 sweep as laff_sim_dense, but only the scores s = scale * <q_i, g_j> with s >= thr[i] are kept,
+ *     appended unordered to query i's candidate list: cand_val / cand_idx [Q, cap] (global index = j + col_offset; unused
+ *     slots -inf / -1), count[i] = number of such scores (may exceed cap: the list is then truncated).  The call
+ *     initialises count and the lists.  The k best of a list are the k best of the row whenever k <= count[i] <= cap. */
+int laff_sim_collect(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                     float scale, const float* thr, int col_offset, int cap, int32_t* count, float* cand_val,
+                     int32_t* cand_idx, void* stream);
+
 /* Diagnostics: run the GEMM mainloop of laff_sim_* with a null epilogue (mode 1 drains TMEM, mode < 0 only sets the
  * TMA L2 eviction hints used by later laff_sim_* calls; hint codes 0 default, 1 normal, 2 evict-first, 3 evict-last). */
 int laff_debug_gemm(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,

@@ -221,6 +221,61 @@ struct EpiRank {
   }
 };
 
+// N1 (writer lists, k up to 2048) without the dense matrix: every score >= the query's threshold is appended, unordered,
+// to the query's candidate list.  With a threshold a little below the k-th best (estimated from a sample of the
+// gallery) ~2k of the V scores survive, so the Q x V matrix is never written and the exact top-k is a sort of the
+// survivors.  count may end above cap (list truncated) or below k: the caller checks both and falls back.
+struct EpiCollect {
+  struct Params {
+    const float* thr;     // [M] threshold on the scaled score
+    int32_t* count;       // [M] number of scores >= thr seen so far
+    float* cand_val;      // [M, cap]
+    int32_t* cand_idx;    // [M, cap] global gallery index
+    int cap;
+    int M, N;
+    int col_offset;
+    float scale;
+  };
+  static constexpr int kSmemBytes = 0;
+  Params p;
+  float t;
+  __device__ EpiCollect(const Params& p_, uint8_t*, int) : p(p_) {}
+  __device__ __forceinline__ void unit_begin(int row, const Unit&) { t = row < p.M ? __ldg(p.thr + row) : INFINITY; }
+  __device__ __forceinline__ void unit_end(int, const Unit&) {}
+  __device__ __forceinline__ void chunk(const uint32_t (&r)[32], int row, int col0) {
+    uint32_t hit = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[j]) * p.scale >= t) ? (1u << j) : 0u;
+    if (col0 + 32 > p.N) hit &= (col0 >= p.N) ? 0u : (0xffffffffu >> (32 - (p.N - col0)));  // columns past the gallery read as zero
+    if (hit == 0) return;
+    const int n = __popc(hit);
+    const int base = atomicAdd(p.count + row, n);
+    float* cv = p.cand_val + static_cast<long long>(row) * p.cap;
+    int32_t* ci = p.cand_idx + static_cast<long long>(row) * p.cap;
+    int o = base;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if ((hit >> j) & 1u) {
+        if (o < p.cap) {
+          cv[o] = __uint_as_float(r[j]) * p.scale;
+          ci[o] = col0 + j + p.col_offset;
+        }
+        ++o;
+      }
+    }
+  }
+};
+
+__global__ void collect_init_kernel(int32_t* count, float* cand_val, int32_t* cand_idx, int Q, long long total) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  if (i < Q) count[i] = 0;
+  for (long long j = i; j < total; j += stride) {
+    cand_val[j] = -INFINITY;
+    cand_idx[j] = -1;
+  }
+}
+
 __global__ void rank_init_kernel(int32_t* count, int32_t* thr_key, long long* slots, int Q, int kmax) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Q) {
@@ -628,6 +683,25 @@ int laff_debug_gemm(const void* q, const void* g, int Q, int V, int D, long long
   const Sched s = make_sched(Q, V, op.cg, t.chunk_tiles, t.m_group, 0);
   EpiNull::Params ep{sink, mode};
   return launch_gemm<EpiNull>(op, s, ep, static_cast<cudaStream_t>(stream));
+}
+
+int laff_sim_collect(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                     float scale, const float* thr, int col_offset, int cap, int32_t* count, float* cand_val,
+                     int32_t* cand_idx, void* stream) {
+  LAFF_REQUIRE(q && g && thr && count && cand_val && cand_idx, LAFF_EINVAL, "laff_sim_collect: null pointer");
+  LAFF_REQUIRE(cap > 0, LAFF_EINVAL, "laff_sim_collect: cap must be positive (got %d)", cap);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Tuning t = get_tuning();
+  GemmOperands op;
+  int rc = prepare_operands(&op, q, g, Q, V, D, ldq, ldg, dtype, t.cta_group);
+  if (rc) return rc;
+  const long long total = static_cast<long long>(Q) * cap;
+  int blocks = static_cast<int>((total + 255) / 256 < op.sms * 8 ? (total + 255) / 256 : op.sms * 8);
+  collect_init_kernel<<<blocks, 256, 0, st>>>(count, cand_val, cand_idx, Q, total); laff::count_launch();
+  LAFF_CUDA(cudaGetLastError());
+  const Sched s = make_sched(Q, V, op.cg, t.chunk_tiles, t.m_group, 0);
+  EpiCollect::Params ep{thr, count, cand_val, cand_idx, cap, Q, V, col_offset, scale};
+  return launch_gemm<EpiCollect>(op, s, ep, st);
 }
 
 size_t laff_sim_gt_workspace_bytes(int Q, int D) {

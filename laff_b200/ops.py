@@ -145,6 +145,24 @@ def sim_dense(q: torch.Tensor, g: torch.Tensor, scale: float = 1.0, out: Optiona
     return out
 
 
+def sim_collect(q: torch.Tensor, g: torch.Tensor, thr: torch.Tensor, cap: int, scale: float = 1.0, col_offset: int = 0):
+    """Candidates of long ranked lists without the dense matrix (laff_sim_collect): every score scale * <q_i, g_j> >=
+    thr[i], unordered.  -> (count int32 [Q], cand_val fp32 [Q, cap], cand_idx int32 [Q, cap] global indices, -inf / -1
+    in unused slots).  count[i] > cap means query i's list was truncated."""
+    q, g = _check_operands(q, g)
+    Q, D = q.shape
+    _need_cuda(thr)
+    thr = thr.to(torch.float32).contiguous()
+    if thr.numel() != Q:
+        raise LaffError("sim_collect: thr must have one entry per query")
+    count = torch.empty(Q, dtype=torch.int32, device=q.device)
+    cv = torch.empty((Q, cap), dtype=torch.float32, device=q.device)
+    ci = torch.empty((Q, cap), dtype=torch.int32, device=q.device)
+    _capi.call("laff_sim_collect", _ptr(q), _ptr(g), Q, g.shape[0], D, q.stride(0), g.stride(0), _DT[q.dtype], float(scale),
+               _ptr(thr), int(col_offset), int(cap), _ptr(count), _ptr(cv), _ptr(ci), _stream(q))
+    return count, cv, ci
+
+
 def sim_gt_scores(q: torch.Tensor, g: torch.Tensor, gt_local: torch.Tensor) -> torch.Tensor:
     """Raw (unscaled) accumulator of <q_i, g_{gt_local[i]}>; 0 where gt_local[i] < 0."""
     q, g = _check_operands(q, g)

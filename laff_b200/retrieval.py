@@ -48,11 +48,52 @@ class CudaBackend:
     def metrics(self, rank0):
         return ops.rank_metrics(rank0)
 
+    dense_rows = 256          # queries per dense chunk: 256 x 1 M fp32 scores = 1 GB
+    collect_cap = 8192        # candidate slots per query of the threshold path (sorted whole in shared memory)
+    collect_sample = 65536    # gallery rows the threshold is estimated from
+
+    def _dense_topk(self, q16, g16, k, scale, col_offset):
+        outs = []
+        for lo in range(0, q16.shape[0], self.dense_rows):
+            s = ops.sim_dense(q16[lo:lo + self.dense_rows], g16, scale)
+            tv, ti = ops.topk_dense(s, k)
+            outs.append((tv, torch.where(ti >= 0, ti + col_offset, ti)))
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+
+    @classmethod
+    def collect_plan(cls, V: int, k: int):
+        """Sample rank whose score serves as the threshold of the collect path, or None when the dense path is the
+        better choice.  The threshold is the r-th best score among the first n_s gallery rows; the number of scores
+        above it in the whole shard then has mean ~ r V / n_s and relative spread ~ 1 / sqrt(r): r is the smallest rank
+        with mean - 6 sigma >= k, and the plan is dropped if mean + 6 sigma would not fit the candidate slots."""
+        n_s = cls.collect_sample
+        if V < 8 * n_s or k < 1:
+            return None
+        ratio = V / n_s
+        r = max(16, int(k / ratio))
+        while r * ratio * (1.0 - 6.0 / r ** 0.5) < k:
+            r += max(1, r // 16)
+        if r * ratio * (1.0 + 6.0 / r ** 0.5) > cls.collect_cap or r > 2048:
+            return None
+        return n_s, r
+
     def dense_topk(self, q16, g16, k, scale, col_offset):
-        """Ranked list of the k best local videos per query: dense scores of the chunk, then laff_topk_dense."""
-        s = ops.sim_dense(q16, g16, scale)
-        tv, ti = ops.topk_dense(s, k)
-        return tv, torch.where(ti >= 0, ti + col_offset, ti)
+        """Ranked list of the k best local videos per query (k <= 2048).  Large shards: a threshold just below the k-th
+        best is read off a sample of the shard, one sweep keeps the scores above it (laff_sim_collect, ~2k of V per
+        query; no Q x V matrix) and the survivors are sorted; if a query ends with fewer than k or more than the slot
+        count (a gallery whose first rows are not representative) the chunk is redone densely.  Small shards: dense
+        scores of 256-query chunks + laff_topk_dense.  Both give the tie-rule order of the full row."""
+        V = g16.shape[0]
+        plan = self.collect_plan(V, k)
+        if plan is None:
+            return self._dense_topk(q16, g16, k, scale, col_offset)
+        n_s, r = plan
+        sv, _ = ops.topk_dense(ops.sim_dense(q16, g16[:n_s], scale), r)
+        thr = sv[:, r - 1].contiguous()
+        count, cv, ci = ops.sim_collect(q16, g16, thr, self.collect_cap, scale, col_offset)
+        if bool(((count < k) | (count > self.collect_cap)).any()):       # one host read per chunk
+            return self._dense_topk(q16, g16, k, scale, col_offset)
+        return ops.topk_dense(cv, k, idx_in=ci)
 
     def merge_lists(self, vals, idx, k):
         """vals/idx [Q, n] candidates carrying global indices (-1 = empty) -> the k best by the tie rule."""
@@ -141,10 +182,10 @@ class GalleryIndex:
             tv, ti = be.merge(torch.stack(vals, 0), torch.stack(idxs, 0), k)
         return SearchResult(count, tv, ti, be.metrics(count))
 
-    def ranked_lists(self, q16: torch.Tensor, k: int, query_chunk: int = 256):
+    def ranked_lists(self, q16: torch.Tensor, k: int, query_chunk: int = 2048):
         """The k best videos of every query over the whole (sharded) gallery, k up to 2048: the lists the reference
         writes to id.sent.score.txt (top 2000) and t2v.pkl (top 500), predictor.py:53-88.  Queries are processed
-        `query_chunk` at a time so the dense chunk of scores stays bounded (256 x 1 M fp32 = 1 GB); with W > 1 shards
+        `query_chunk` at a time (the backend bounds its own scratch: candidate lists, or dense 256-query pieces); with W > 1 shards
         every rank extracts its local lists and one all_gather + merge per chunk yields the global ones.
         Returns (values fp32 [Q, k], global indices int32 [Q, k]) on the device, -inf / -1 beyond the gallery size."""
         be = self.backend

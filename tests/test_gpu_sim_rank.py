@@ -224,6 +224,57 @@ def test_ranked_lists_at_gallery_scale_match_stable_argsort():
     assert torch.equal(res.topk_idx, li[:, :16])
 
 
+def test_ranked_lists_threshold_path_equals_dense_path(monkeypatch):
+    """Large shards take the threshold path (sample -> threshold -> laff_sim_collect -> sort of the survivors, no Q x V
+    matrix): its lists must be the dense path's lists, entry for entry, including exact ties at and around the
+    threshold, a ragged last column tile, and -- for a gallery whose first rows are not representative, so that the
+    estimated threshold is far too low or too high -- through the fallback."""
+    from laff_b200 import _capi
+    from laff_b200.retrieval import CudaBackend, GalleryIndex
+    monkeypatch.setattr(CudaBackend, "collect_sample", 4096)
+    monkeypatch.setattr(CudaBackend, "collect_cap", 1024)
+    Q, V, H, dh, k = 150, 40009, 4, 64, 100
+    assert CudaBackend.collect_plan(V, k) is not None and CudaBackend.collect_plan(1000, k) is None
+    q, g, gt = synth.retrieval_embeddings(92, Q, V, H, dh, sigma=1.0)
+    for j in range(40):                      # exact duplicates spread over the gallery: ties inside the lists
+        g[(j * 977 + 13) % V] = g[gt[j]]
+    g[V - 1] = g[gt[3]]
+    q16 = torch.from_numpy(synth.bf16_round(q)).cuda().to(torch.bfloat16)
+    g16 = torch.from_numpy(synth.bf16_round(g)).cuda().to(torch.bfloat16)
+    be = CudaBackend()
+    lib = _capi.lib()
+    dv, di = be._dense_topk(q16, g16, k, 1.0 / H, 7)
+    lib.laff_launch_count(1)
+    cv, ci = be.dense_topk(q16, g16, k, 1.0 / H, 7)
+    n_collect = lib.laff_launch_count(1)
+    assert torch.equal(ci, di) and torch.equal(cv, dv)
+    s = ops.sim_dense(q16, g16, 1.0 / H).cpu().numpy()
+    rv, ri = O.tie_rule_topk(s, k)
+    assert np.array_equal(ci.cpu().numpy().astype(np.int64), ri + 7) and np.array_equal(cv.cpu().numpy(), rv)
+    # the candidate lists themselves: every score >= thr, nothing else, counted exactly
+    thr = torch.from_numpy(np.sort(s, axis=1)[:, -300].copy()).cuda()
+    cnt, lv, li = ops.sim_collect(q16, g16, thr, 1024, 1.0 / H, 0)
+    want = (s >= thr.cpu().numpy()[:, None])
+    assert np.array_equal(cnt.cpu().numpy(), want.sum(1))
+    for i in (0, 17, Q - 1):
+        got = li[i][li[i] >= 0].cpu().numpy()
+        assert sorted(got.tolist()) == np.nonzero(want[i])[0].tolist()
+        assert np.array_equal(lv[i][: len(got)].cpu().numpy(), s[i][got])
+    # gallery sorted by similarity to query 0, both ways: the sample misleads, the answer must not change
+    order = np.argsort(s[0])
+    for perm in (order, order[::-1].copy()):
+        gp = g16[torch.from_numpy(perm.copy()).cuda()]
+        a_v, a_i = be.dense_topk(q16, gp, k, 1.0 / H, 0)
+        b_v, b_i = be._dense_topk(q16, gp, k, 1.0 / H, 0)
+        assert torch.equal(a_i, b_i) and torch.equal(a_v, b_v)
+    # through the index (one shard), lists longer than the plan allows fall back to the dense path on their own
+    idx = GalleryIndex(g16, V, H)
+    lv2, li2 = idx.ranked_lists(q16, 900, query_chunk=64)
+    rv2, ri2 = O.tie_rule_topk(s, 900)
+    assert np.array_equal(li2.cpu().numpy().astype(np.int64), ri2) and np.array_equal(lv2.cpu().numpy(), rv2)
+    assert n_collect < 12
+
+
 @pytest.mark.parametrize("V", [1000000])
 def test_full_size_properties(V):
     """BASELINE config C5 (10 000 queries x 1 000 000 videos): properties that do not need the 40 GB score matrix."""

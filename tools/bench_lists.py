@@ -25,7 +25,7 @@ def main():
     x = torch.randn(Q, 8, 512, generator=gen, device=dev)
     q16 = (x / x.norm(dim=2, keepdim=True)).reshape(Q, -1).to(torch.bfloat16)
     idx = GalleryIndex(g16, V, 8)
-    for chunk in (128, 256, 512):
+    for chunk in (256, 1024, 2048):
         idx.ranked_lists(q16[:chunk], k, query_chunk=chunk)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
