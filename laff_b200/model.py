@@ -696,21 +696,42 @@ class W2VVPP(nn.Module):
         return txt, vis
 
     def _train_step_device(self, txt, vis, precision):
-        """forward (train mode) -> loss -> backward -> clip + optimizer step, all on the current stream, no host sync."""
+        """forward (train mode) -> loss -> backward -> clip + optimizer step, no host sync.  The text net and the
+        video net are independent until the loss and again after it, so the text side runs on a second stream (forked
+        from / joined into the current one with events: inside a CUDA-graph capture these become two parallel branches
+        of the graph) -- at B = 128 every kernel fills only a fraction of the SMs."""
         from .train import FusionTrainStep
         self._seed_dev.add_(1)
-        tmods = dict(self.txt_net.transform_layer.named_children())
-        tfeats, gru_cache, gru_idx = [], None, None
-        for n in self.txt_net.encoder_name_list:
-            if n == "rnn_encoder" and "rnn_ids" in txt:
-                from . import text as _text
-                enc = dict(self.txt_net.encoder.named_children())["rnn_encoder"]
-                feat, gru_cache = _text.gru_encode_train(enc.we.weight, enc.rnn.weight_ih_l0, enc.rnn.weight_hh_l0, enc.rnn.bias_ih_l0,
-                                                         enc.rnn.bias_hh_l0, txt["rnn_ids"], txt["rnn_len"], enc.pooling)
-                gru_idx = len(tfeats)
-                tfeats.append((feat, tmods[n + "_transform"], True))
-            else:
-                tfeats.append((txt[n], tmods[n + "_transform"]))
+        dev = self._seed_dev.device
+        main = torch.cuda.current_stream(dev)
+        side = getattr(self, "_side_stream", None)
+        if side is None or side.device != dev:
+            side = self._side_stream = torch.cuda.Stream(dev)
+        outs = {}
+
+        def run_step(key, feats, att):
+            step = self._steps.get(key)
+            if step is None or step.att is not att or step.precision != precision:
+                step = self._steps[key] = FusionTrainStep(att, precision)
+            outs[key] = step.forward(feats, self._seed_base * 2 + (key == "vis"), self._seed_dev)
+
+        # ---- forward: text side on the second stream ----
+        gru_cache, gru_idx = None, None
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            tmods = dict(self.txt_net.transform_layer.named_children())
+            tfeats = []
+            for n in self.txt_net.encoder_name_list:
+                if n == "rnn_encoder" and "rnn_ids" in txt:
+                    from . import text as _text
+                    enc = dict(self.txt_net.encoder.named_children())["rnn_encoder"]
+                    feat, gru_cache = _text.gru_encode_train(enc.we.weight, enc.rnn.weight_ih_l0, enc.rnn.weight_hh_l0, enc.rnn.bias_ih_l0,
+                                                             enc.rnn.bias_hh_l0, txt["rnn_ids"], txt["rnn_len"], enc.pooling)
+                    gru_idx = len(tfeats)
+                    tfeats.append((feat, tmods[n + "_transform"], True))
+                else:
+                    tfeats.append((txt[n], tmods[n + "_transform"]))
+            run_step("txt", tfeats, self.txt_net.attention_layer)
         frame_ml = isinstance(self.vis_net, VisMutiTransformNetPlusFrameFeat)
         pooled = {}
         if frame_ml:
@@ -734,25 +755,25 @@ class W2VVPP(nn.Module):
             # train-mode quirk of the reference: an all-zero video feature becomes noise (model/model.py:1819-1821).
             # Selected on the device: the reference's `torch.nonzero(...)` costs a host synchronisation per feature per step.
             vfeats = [(torch.where((x != 0).any(), x, torch.randn_like(x)), vmods[n]) for n, x in vis.items()]
-        outs = {}
-        for key, feats, att in (("txt", tfeats, self.txt_net.attention_layer), ("vis", vfeats, vis_att)):
-            step = self._steps.get(key)
-            if step is None or step.att is not att or step.precision != precision:
-                step = self._steps[key] = FusionTrainStep(att, precision)
-            outs[key] = step.forward(feats, self._seed_base * 2 + (key == "vis"), self._seed_dev)
+        run_step("vis", vfeats, vis_att)
+        main.wait_stream(side)
+        # ---- loss (both embeddings) ----
         c = self.criterion
         if isinstance(c, DualSoftmaxLoss):
             loss, d_txt, d_vis = ops.dsl_forward_backward(outs["txt"], outs["vis"], 1000.0)
         else:
             loss, d_txt, d_vis = ops.mrl_forward_backward(outs["txt"], outs["vis"], c.margin, c.max_violation, c.direction, c.cost_style)
-        dxt = self._steps["txt"].backward(d_txt)
-        if gru_cache is not None:
-            from . import text as _text
-            from .train import _grad_buffer
-            enc = dict(self.txt_net.encoder.named_children())["rnn_encoder"]
-            grads = {"we": _grad_buffer(enc.we.weight), "w_ih": _grad_buffer(enc.rnn.weight_ih_l0), "w_hh": _grad_buffer(enc.rnn.weight_hh_l0),
-                     "b_ih": _grad_buffer(enc.rnn.bias_ih_l0), "b_hh": _grad_buffer(enc.rnn.bias_hh_l0)}
-            _text.gru_backward(gru_cache, dxt[gru_idx], enc.we.weight, enc.rnn.weight_ih_l0, enc.rnn.weight_hh_l0, grads)
+        # ---- backward: text side (and the GRU's backward through time) on the second stream ----
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            dxt = self._steps["txt"].backward(d_txt)
+            if gru_cache is not None:
+                from . import text as _text
+                from .train import _grad_buffer
+                enc = dict(self.txt_net.encoder.named_children())["rnn_encoder"]
+                grads = {"we": _grad_buffer(enc.we.weight), "w_ih": _grad_buffer(enc.rnn.weight_ih_l0), "w_hh": _grad_buffer(enc.rnn.weight_hh_l0),
+                         "b_ih": _grad_buffer(enc.rnn.bias_ih_l0), "b_hh": _grad_buffer(enc.rnn.bias_hh_l0)}
+                _text.gru_backward(gru_cache, dxt[gru_idx], enc.we.weight, enc.rnn.weight_ih_l0, enc.rnn.weight_hh_l0, grads)
         dxs = self._steps["vis"].backward(d_vis)
         for idx, (name, frames) in pooled.items():
             lin = self.vis_net.frame_attention[name][0].embedding_common[0]
@@ -761,6 +782,7 @@ class W2VVPP(nn.Module):
                 bufs = self._frame_grads[name] = (torch.zeros_like(lin.weight), torch.zeros_like(lin.bias))
             lin.weight.grad, lin.bias.grad = bufs
             ops.frame_pool_backward(frames, lin.weight, dxs[idx], bufs[0], bufs[1])
+        main.wait_stream(side)
         self.last_grad_norm = self.optimizer.step()
         return loss
 

@@ -58,25 +58,35 @@ class FusionTrainStep:
         att = self.att
         H, dh = att.multi_heads, att.dim_per_head
         D = H * dh
+        # Every feature's chain (operand casts -> projection GEMM -> dropout / BatchNorm) is independent of the others
+        # and, at B = 128, fills a fraction of the SMs: each runs on its own stream, forked from and joined into the
+        # current one (inside a graph capture: parallel branches).
+        dev = features[0][0].device
+        cur = torch.cuda.current_stream(dev)
+        lanes = self._lanes(dev, len(features))
         items = []
         for i, f in enumerate(features):
             x, tn = f[0], f[1]
             p = float(tn.dropout_p or 0.0)
             it = {"x": x, "tn": tn, "p": p, "want_dx": len(f) > 2 and bool(f[2])}
-            if tn.fc1 is not None:
-                w16 = _operands(tn.fc1.weight.detach(), self.precision, 1)
-                a = ops.project(_operands(x, self.precision, 0), w16, tn.fc1.bias.detach(), tn.activation_name)
-                it["a"] = a
-                if p > 0 or tn.bn1 is not None:
-                    y, mask, sm, si = ops.transform_train_forward(a, D, p, seed * 131 + i, tn.bn1, seed_dev=seed_dev)
+            lanes[i].wait_stream(cur)
+            with torch.cuda.stream(lanes[i]):
+                if tn.fc1 is not None:
+                    w16 = _operands(tn.fc1.weight.detach(), self.precision, 1)
+                    a = ops.project(_operands(x, self.precision, 0), w16, tn.fc1.bias.detach(), tn.activation_name)
+                    it["a"] = a
+                    if p > 0 or tn.bn1 is not None:
+                        y, mask, sm, si = ops.transform_train_forward(a, D, p, seed * 131 + i, tn.bn1, seed_dev=seed_dev)
+                    else:
+                        y, mask, sm, si = a, None, None, None
                 else:
-                    y, mask, sm, si = a, None, None, None
-            else:
-                y, mask, sm, si = ops.transform_train_forward(x, D, p, seed * 131 + i, tn.bn1, seed_dev=seed_dev)
-            if tn.bn1 is not None:
-                tn.bn1.num_batches_tracked += 1
+                    y, mask, sm, si = ops.transform_train_forward(x, D, p, seed * 131 + i, tn.bn1, seed_dev=seed_dev)
+                if tn.bn1 is not None:
+                    tn.bn1.num_batches_tracked += 1
             it.update(y=y, mask=mask, sm=sm, si=si)
             items.append(it)
+        for i in range(len(features)):
+            cur.wait_stream(lanes[i])
         ps = [att.attention_layer[h].embedding_common[0] for h in range(H)]
         w = torch.cat([q.weight.detach().view(1, -1) for q in ps], 0).float().contiguous()
         b = torch.cat([q.bias.detach().view(1) for q in ps], 0).float().contiguous()
@@ -84,6 +94,37 @@ class FusionTrainStep:
         out, _, _ = ops.attention_pool([{"y": it["y"]} for it in items], w, b, H, dh, att.with_ave, att.mul, omega=omega)
         self.cache = {"items": items, "w": w, "b": b, "heads": ps, "omega": omega}
         return out
+
+    def _lanes(self, dev, n: int):
+        """n side streams on `dev`, one per feature chain (kept for the life of the step object)."""
+        ls = getattr(self, "_lane_streams", None)
+        if ls is None or len(ls) < n or ls[0].device != dev:
+            ls = self._lane_streams = [torch.cuda.Stream(dev) for _ in range(n)]
+        return ls
+
+    def _feature_backward(self, idx: int, it: dict, dy: torch.Tensor, dxs: Dict[int, torch.Tensor]) -> None:
+        """Backward of one feature chain down to its parameters (and its input when that is itself computed)."""
+        tn = it["tn"]
+        dgamma = _grad_buffer(tn.bn1.weight) if tn.bn1 is not None else None
+        dbeta = _grad_buffer(tn.bn1.bias) if tn.bn1 is not None else None
+        if tn.fc1 is None:
+            if tn.bn1 is not None or it["want_dx"]:
+                dzt = ops.transform_train_backward(dy, None, it["x"], it["mask"], it["p"], "none", tn.bn1, it["sm"], it["si"],
+                                                   want_dz=it["want_dx"], dgamma=dgamma, dbeta=dbeta)
+                if it["want_dx"]:
+                    dxs[idx] = ops.fold_tiles(dzt, it["x"].shape[1])
+            return
+        dbias = _grad_buffer(tn.fc1.bias)
+        dz = ops.transform_train_backward(dy, it["a"], None, it["mask"], it["p"], tn.activation_name, tn.bn1, it["sm"],
+                                          it["si"], dgamma=dgamma, dbeta=dbeta, dbias=dbias)
+        terms = 3 if self.precision == "bf16x3" else 1
+        dt = torch.float16 if self.precision == "fp16" else torch.bfloat16
+        if it["want_dx"]:  # the input is itself computed (GRU sentence feature): dx = dz @ W
+            wT16 = ops.transpose_16(tn.fc1.weight.detach(), dt, terms, 1)
+            dz16 = ops.split3_16(dz, 0, torch.bfloat16) if terms == 3 else ops.cast_pad_16(dz, dt)
+            dxs[idx] = ops.project(dz16, wT16, None, "none")
+        ops.sim_dense(ops.transpose_16(dz, dt, terms, 0), ops.transpose_16(it["x"], dt, terms, 1), 1.0,
+                      out=_grad_buffer(tn.fc1.weight))
 
     def backward(self, dout: torch.Tensor) -> Dict[int, torch.Tensor]:
         """Writes every parameter gradient of the net into `.grad`; returns {feature index: d loss / d x} for the
@@ -106,28 +147,14 @@ class FusionTrainStep:
             q.weight.grad = dw[h:h + 1]
             q.bias.grad = self._dc[h:h + 1]
         dxs: Dict[int, torch.Tensor] = {}
+        cur = torch.cuda.current_stream(dev)
+        lanes = self._lanes(dev, len(c["items"]))
         for idx, (it, dy) in enumerate(zip(c["items"], dys)):
-            tn = it["tn"]
-            dgamma = _grad_buffer(tn.bn1.weight) if tn.bn1 is not None else None
-            dbeta = _grad_buffer(tn.bn1.bias) if tn.bn1 is not None else None
-            if tn.fc1 is None:
-                if tn.bn1 is not None or it["want_dx"]:
-                    dzt = ops.transform_train_backward(dy, None, it["x"], it["mask"], it["p"], "none", tn.bn1, it["sm"], it["si"],
-                                                       want_dz=it["want_dx"], dgamma=dgamma, dbeta=dbeta)
-                    if it["want_dx"]:
-                        dxs[idx] = ops.fold_tiles(dzt, it["x"].shape[1])
-                continue
-            dbias = _grad_buffer(tn.fc1.bias)
-            dz = ops.transform_train_backward(dy, it["a"], None, it["mask"], it["p"], tn.activation_name, tn.bn1, it["sm"],
-                                              it["si"], dgamma=dgamma, dbeta=dbeta, dbias=dbias)
-            terms = 3 if self.precision == "bf16x3" else 1
-            dt = torch.float16 if self.precision == "fp16" else torch.bfloat16
-            if it["want_dx"]:  # the input is itself computed (GRU sentence feature): dx = dz @ W
-                wT16 = ops.transpose_16(tn.fc1.weight.detach(), dt, terms, 1)
-                dz16 = ops.split3_16(dz, 0, torch.bfloat16) if terms == 3 else ops.cast_pad_16(dz, dt)
-                dxs[idx] = ops.project(dz16, wT16, None, "none")
-            ops.sim_dense(ops.transpose_16(dz, dt, terms, 0), ops.transpose_16(it["x"], dt, terms, 1), 1.0,
-                          out=_grad_buffer(tn.fc1.weight))
+            lanes[idx].wait_stream(cur)
+            with torch.cuda.stream(lanes[idx]):
+                self._feature_backward(idx, it, dy, dxs)
+        for idx in range(len(c["items"])):
+            cur.wait_stream(lanes[idx])
         self.cache = None
         return dxs
 
