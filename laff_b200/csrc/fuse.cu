@@ -64,33 +64,74 @@ __global__ void l2norm_quantize_kernel(const float* __restrict__ x, long long ro
   }
 }
 
+// fp32 -> 16-bit operand copies.  HBM-bound: one thread moves 8 consecutive columns (two 16-byte loads, one 16-byte store
+// per output plane); VEC = false is the element-wise path for pitches / pointers that are not 16-byte aligned.
+__device__ __forceinline__ void load8(const float* __restrict__ src, int valid, bool vec, float (&v)[8]) {
+  if (vec && valid >= 8) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = j < valid ? __ldg(src + j) : 0.f;   // columns [cols, cols_pad) are zero
+  }
+}
+__device__ __forceinline__ uint4 pack8(const uint16_t (&h)[8]) {
+  uint4 o;
+  o.x = h[0] | (static_cast<uint32_t>(h[1]) << 16);
+  o.y = h[2] | (static_cast<uint32_t>(h[3]) << 16);
+  o.z = h[4] | (static_cast<uint32_t>(h[5]) << 16);
+  o.w = h[6] | (static_cast<uint32_t>(h[7]) << 16);
+  return o;
+}
+__device__ __forceinline__ void store8(uint16_t* __restrict__ dst, const uint16_t (&h)[8], bool vec) {
+  if (vec) {
+    *reinterpret_cast<uint4*>(dst) = pack8(h);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = h[j];
+  }
+}
+
+// cols_pad % 8 == 0 (the callers pad to TMA's 16-byte pitch granularity)
 __global__ void cast_pad_kernel(const float* __restrict__ x, long long rows, int cols, long long ldx, int out_dtype,
-                                uint16_t* __restrict__ out, int cols_pad, long long ld_out) {
-  const long long total = rows * cols_pad;
+                                uint16_t* __restrict__ out, int cols_pad, long long ld_out, int vec_in, int vec_out) {
+  const int gpr = cols_pad >> 3;
+  const long long total = rows * gpr;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / cols_pad;
-    const int c = static_cast<int>(i - r * cols_pad);
-    const float v = c < cols ? x[r * ldx + c] : 0.f;
-    out[r * ld_out + c] = to16(v, out_dtype);
+    const long long r = i / gpr;
+    const int c = static_cast<int>(i - r * gpr) << 3;
+    float v[8];
+    load8(x + r * ldx + c, cols - c, vec_in != 0, v);
+    uint16_t h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = to16(v[j], out_dtype);
+    store8(out + r * ld_out + c, h, vec_out != 0);
   }
 }
 
 __global__ void split3_kernel(const float* __restrict__ x, long long rows, int cols, long long ldx, int side,
-                              int out_dtype, uint16_t* __restrict__ out, int cols_pad, long long ld_out) {
-  const long long total = rows * cols_pad;
+                              int out_dtype, uint16_t* __restrict__ out, int cols_pad, long long ld_out, int vec_in,
+                              int vec_out) {
+  const int gpr = cols_pad >> 3;
+  const long long total = rows * gpr;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / cols_pad;
-    const int c = static_cast<int>(i - r * cols_pad);
-    const float v = c < cols ? x[r * ldx + c] : 0.f;
-    const uint16_t hi = to16(v, out_dtype);
-    const uint16_t lo = to16(v - from16(hi, out_dtype), out_dtype);
+    const long long r = i / gpr;
+    const int c = static_cast<int>(i - r * gpr) << 3;
+    float v[8];
+    load8(x + r * ldx + c, cols - c, vec_in != 0, v);
+    uint16_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hi[j] = to16(v[j], out_dtype);
+      lo[j] = to16(v[j] - from16(hi[j], out_dtype), out_dtype);
+    }
     uint16_t* o = out + r * ld_out + c;
     // left: [hi | lo | hi]   right: [hi | hi | lo]   =>  left . right = hi.hi + lo.hi + hi.lo
-    o[0] = hi;
-    o[cols_pad] = side == 0 ? lo : hi;
-    o[2 * static_cast<long long>(cols_pad)] = side == 0 ? hi : lo;
+    store8(o, hi, vec_out != 0);
+    store8(o + cols_pad, side == 0 ? lo : hi, vec_out != 0);
+    store8(o + 2 * static_cast<long long>(cols_pad), side == 0 ? hi : lo, vec_out != 0);
   }
 }
 
@@ -445,8 +486,11 @@ int laff_cast_pad_16(const float* x, long long rows, int cols, long long ldx, in
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
-  cast_pad_kernel<<<grid_for(rows * cols_pad, 256, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rows, cols, ldx, out_dtype, static_cast<uint16_t*>(out), cols_pad, ld_out); laff::count_launch();
+  LAFF_REQUIRE(cols_pad % 8 == 0, LAFF_EINVAL, "laff_cast_pad_16: cols_pad (%d) must be a multiple of 8", cols_pad);
+  const int vec_in = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ldx % 4 == 0;
+  const int vec_out = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && ld_out % 8 == 0;
+  cast_pad_kernel<<<grid_for(rows * (cols_pad / 8), 256, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, rows, cols, ldx, out_dtype, static_cast<uint16_t*>(out), cols_pad, ld_out, vec_in, vec_out); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }
@@ -459,8 +503,11 @@ int laff_split3_16(const float* x, long long rows, int cols, long long ldx, int 
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
-  split3_kernel<<<grid_for(rows * cols_pad, 256, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rows, cols, ldx, side, out_dtype, static_cast<uint16_t*>(out), cols_pad, ld_out); laff::count_launch();
+  LAFF_REQUIRE(cols_pad % 8 == 0, LAFF_EINVAL, "laff_split3_16: cols_pad (%d) must be a multiple of 8", cols_pad);
+  const int vec_in = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ldx % 4 == 0;
+  const int vec_out = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && ld_out % 8 == 0;
+  split3_kernel<<<grid_for(rows * (cols_pad / 8), 256, di.sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, rows, cols, ldx, side, out_dtype, static_cast<uint16_t*>(out), cols_pad, ld_out, vec_in, vec_out); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }

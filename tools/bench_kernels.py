@@ -98,6 +98,16 @@ def main():
     ms = timeit(lambda: ops.l2norm_quantize(e, 8, torch.bfloat16), flush=flush)
     emit("laff_l2norm_quantize rows=%d" % (rows * 4), ms, bytes_=rows * 4 * 4096 * 6)
 
+    # operand preparation: fp32 features -> 16-bit TMA operands (mode B casts 19.5 KB per video), 3-term split (training)
+    xc = torch.randn(131072, 2048, generator=g, device=dev)
+    scratch = torch.empty(131072, 2048, dtype=torch.bfloat16, device=dev)
+    ms = timeit(lambda: ops.cast_pad_16(xc, torch.bfloat16, out=scratch), flush=flush)
+    emit("laff_cast_pad_16 rows=131072 K=2048", ms, bytes_=131072 * 2048 * 6)
+    xw = torch.randn(4096, 3981, generator=g, device=dev)
+    ms = timeit(lambda: ops.split3_16(xw, 1, torch.bfloat16), flush=flush)
+    emit("laff_split3_16 rows=4096 K=3981 (weights of one training step)", ms, bytes_=4096 * (3981 * 4 + 3984 * 6))
+    del xc, scratch, xw
+
     # L1/L2 loss step (C3)
     txt = torch.randn(128, 8, 512, generator=g, device=dev)
     vis = torch.randn(128, 8, 512, generator=g, device=dev)
