@@ -32,8 +32,11 @@ sys.path.insert(0, ROOT)
 if "reference" in sys.argv[1:] and os.environ.get("RANK", "0") == "0":
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(os.cpu_count() or 1)
-# stdout carries exactly one JSON line: NCCL writes its version banner / warnings (NCCL_DEBUG=VERSION|WARN|INFO, from the
-# environment or an nccl.conf) to stdout unless told otherwise
+# stdout carries exactly one JSON line.  NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION (set on some boxes,
+# in the environment or an nccl.conf) and honours NCCL_DEBUG_FILE only above that level: raise VERSION to WARN and send
+# the debug stream to stderr.
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
