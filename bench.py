@@ -296,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step_e2e():
         res = retr.rank(feats_host, gt_host, TOPK, chunks=args.e2e_chunks)   # pinned host -> device copies inside
-        return res.rank0.cpu(), res.topk_val.cpu(), res.topk_idx.cpu(), res.metrics.cpu()
+        return res.to_host()                                                 # ranks, top-k lists, metrics: one D2H + sync
 
     # ---- device-resident inputs: `value` ------------------------------------------------------------------------
     for _ in range(args.warmup):

@@ -107,6 +107,22 @@ class SearchResult:
     topk_idx: torch.Tensor   # int32 [Q, k] global gallery indices, ordered by (score desc, index desc)
     metrics: torch.Tensor    # float64 [8]: R@1, R@5, R@10, MedR, MeanR, MIR, mAP, Q
 
+    def to_host(self) -> "SearchResult":
+        """The same result in host memory, fetched with ONE device->host copy and one synchronisation (four separate
+        `.cpu()` calls cost four round trips -- visible once a step is a few milliseconds, as at 8 GPUs)."""
+        if not self.rank0.is_cuda:
+            return self
+        parts = [self.rank0.to(torch.int32).reshape(-1), self.topk_val.float().reshape(-1).view(torch.int32),
+                 self.topk_idx.to(torch.int32).reshape(-1), self.metrics.double().reshape(-1).view(torch.int32)]
+        flat = torch.cat(parts)
+        host = torch.empty(flat.shape, dtype=torch.int32, pin_memory=True)
+        host.copy_(flat, non_blocking=True)
+        torch.cuda.current_stream(flat.device).synchronize()
+        n0, n1, n2 = parts[0].numel(), parts[1].numel(), parts[2].numel()
+        return SearchResult(host[:n0], host[n0:n0 + n1].view(torch.float32).reshape(self.topk_val.shape),
+                            host[n0 + n1:n0 + n1 + n2].reshape(self.topk_idx.shape),
+                            host[n0 + n1 + n2:].view(torch.float64))
+
 
 class GalleryIndex:
     """The local shard of a gallery of fused video embeddings, resident in HBM (the reference's record_emb=True cache,
@@ -175,11 +191,12 @@ class GalleryIndex:
             ti = torch.full((Q, k), -1, dtype=torch.int32, device=q16.device)
         count = self._all_reduce(count)
         if self.world_size > 1 and k > 0:
-            vals = [torch.empty_like(tv) for _ in range(self.world_size)]
-            idxs = [torch.empty_like(ti) for _ in range(self.world_size)]
-            dist.all_gather(vals, tv.contiguous(), group=self.group)
-            dist.all_gather(idxs, ti.contiguous(), group=self.group)
-            tv, ti = be.merge(torch.stack(vals, 0), torch.stack(idxs, 0), k)
+            # one collective for both halves of the lists: [score bits | index] per query, gathered into [W, Q, 2k]
+            mine = torch.cat([tv.contiguous().view(torch.int32), ti.to(torch.int32)], 1).contiguous()
+            flat = torch.empty((self.world_size * mine.shape[0], mine.shape[1]), dtype=torch.int32, device=mine.device)
+            dist.all_gather_into_tensor(flat, mine, group=self.group)
+            both = flat.view(self.world_size, mine.shape[0], mine.shape[1])
+            tv, ti = be.merge(both[:, :, :k].contiguous().view(torch.float32), both[:, :, k:].contiguous(), k)
         return SearchResult(count, tv, ti, be.metrics(count))
 
     def ranked_lists(self, q16: torch.Tensor, k: int, query_chunk: int = 2048):

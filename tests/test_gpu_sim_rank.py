@@ -222,6 +222,9 @@ def test_ranked_lists_at_gallery_scale_match_stable_argsort():
     assert np.array_equal(li.cpu().numpy().astype(np.int64), ri) and np.array_equal(lv.cpu().numpy(), rv)
     res = idx.search(q16, torch.from_numpy(gt).cuda().to(torch.int32), 16)
     assert torch.equal(res.topk_idx, li[:, :16])
+    h = res.to_host()                                    # one packed device->host copy
+    assert not h.rank0.is_cuda and torch.equal(h.rank0, res.rank0.cpu()) and torch.equal(h.topk_idx, res.topk_idx.cpu())
+    assert torch.equal(h.topk_val, res.topk_val.cpu()) and torch.equal(h.metrics, res.metrics.cpu())
 
 
 def test_ranked_lists_threshold_path_equals_dense_path(monkeypatch):
