@@ -326,3 +326,17 @@ def test_full_size_properties(V):
     m = res.metrics.cpu().numpy()
     np.testing.assert_array_equal(m[:4], O.metrics_from_rank0(rank0.cpu().numpy())[:4])
     assert 5.0 < m[0] < 95.0 and m[0] <= m[1] <= m[2]
+    # (6) the writer lists at full size (threshold path: no 10 000 x 1 000 000 matrix): ordered by the tie rule, unique,
+    #     their heads are the sweep's top-k, and a subsample equals the dense path entry for entry
+    from laff_b200.retrieval import CudaBackend, GalleryIndex
+    assert CudaBackend.collect_plan(V, 2000) is not None
+    idx = GalleryIndex(g16, V, H)
+    lv, li = idx.ranked_lists(q16[:2048], 2000)
+    assert torch.equal(li[:, :k], ti[:2048]) and torch.equal(lv[:, :k], tv[:2048])
+    assert bool((lv[:, :-1] >= lv[:, 1:]).all()) and int(li.min()) >= 0 and int(li.max()) < V
+    tie = lv[:, :-1] == lv[:, 1:]
+    assert bool((li[:, :-1][tie] > li[:, 1:][tie]).all())          # equal scores: higher index first
+    sl = torch.sort(li, 1).values
+    assert bool((sl[:, 1:] != sl[:, :-1]).all())
+    dv, di = CudaBackend()._dense_topk(q16[:64], g16, 2000, 1.0 / H, 0)
+    assert torch.equal(di, li[:64]) and torch.equal(dv, lv[:64])
