@@ -16,7 +16,7 @@ from laff_b200 import evaluation as E
 from laff_b200 import loss as L
 from laff_b200 import model as M
 from laff_b200 import ops, synth
-from laff_b200.retrieval import GalleryIndex, shard_bounds
+from laff_b200.retrieval import CudaBackend, GalleryIndex, shard_bounds
 from oracle import laff_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -209,7 +209,6 @@ def test_gallery_sharding_is_exact_on_one_gpu():
 def test_ranked_lists_at_gallery_scale_match_stable_argsort():
     """GalleryIndex.ranked_lists (dense chunk -> radix-select top-k, writer lists of predictor.py:53-88): indices equal
     the stable-argsort order of the device's own dense scores, and agree with the fused sweep's top-16."""
-    from laff_b200.retrieval import GalleryIndex
     Q, V, H, dh, k = 70, 40009, 8, 32, 777
     q, g, gt = synth.retrieval_embeddings(91, Q, V, H, dh, sigma=1.0)
     g[V - 1] = g[gt[0]]
@@ -233,7 +232,6 @@ def test_ranked_lists_threshold_path_equals_dense_path(monkeypatch):
     threshold, a ragged last column tile, and -- for a gallery whose first rows are not representative, so that the
     estimated threshold is far too low or too high -- through the fallback."""
     from laff_b200 import _capi
-    from laff_b200.retrieval import CudaBackend, GalleryIndex
     monkeypatch.setattr(CudaBackend, "collect_sample", 4096)
     monkeypatch.setattr(CudaBackend, "collect_cap", 1024)
     Q, V, H, dh, k = 150, 40009, 4, 64, 100
@@ -328,7 +326,6 @@ def test_full_size_properties(V):
     assert 5.0 < m[0] < 95.0 and m[0] <= m[1] <= m[2]
     # (6) the writer lists at full size (threshold path: no 10 000 x 1 000 000 matrix): ordered by the tie rule, unique,
     #     their heads are the sweep's top-k, and a subsample equals the dense path entry for entry
-    from laff_b200.retrieval import CudaBackend, GalleryIndex
     assert CudaBackend.collect_plan(V, 2000) is not None
     idx = GalleryIndex(g16, V, H)
     lv, li = idx.ranked_lists(q16[:2048], 2000)
