@@ -7,6 +7,7 @@
 //   laff_rank_metrics    : R@1/5/10, MedR, MeanR, MIR on device                             evaluation.py:81-89, :105-109
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 
 #include "gemm_engine.cuh"
@@ -766,9 +767,25 @@ int laff_sim_rank_topk(const void* q, const void* g, int Q, int V, int D, long l
   const int init_n = Q * LAFF_MAX_TOPK;
   rank_init_kernel<<<(init_n + 255) / 256, 256, 0, st>>>(count, thr_key, slots, Q, LAFF_MAX_TOPK); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
-  EpiRank<LAFF_MAX_TOPK>::Params ep{sgt_raw, gt_global, count, thr_key, slots, Q, V, col_offset, k};
-  rc = launch_gemm<EpiRank<LAFF_MAX_TOPK>>(op, s, ep, st);
-  if (rc) return rc;
+  // One launch per group of m_group row tiles (2560 queries): the groups are independent passes over the gallery anyway,
+  // and separate launches measured 4-5 % faster than one launch walking the groups back to back (10 000 x 1 M:
+  // 67.0 / 69.7 / 67.7 ms as one launch, 62.7 / 65.6 / 65.5 ms as four; profiles/r01_sched_experiments.md).
+  static const bool split_groups = [] { const char* e = getenv("LAFF_SWEEP_SPLIT"); return !e || atoi(e) != 0; }();
+  const int rows_per_launch = split_groups ? s.m_group * s.rows_per_mtile : Q;
+  for (int r0 = 0; r0 < Q; r0 += rows_per_launch) {
+    const int rows = Q - r0 < rows_per_launch ? Q - r0 : rows_per_launch;
+    GemmOperands ops = op;
+    if (r0 > 0 || rows < Q) {
+      rc = prepare_operands(&ops, static_cast<const uint16_t*>(q) + static_cast<long long>(r0) * ldq, g, rows, V, D, ldq, ldg, dtype,
+                            t.cta_group);
+      if (rc) return rc;
+    }
+    const Sched ss = make_sched(rows, V, ops.cg, t.chunk_tiles, t.m_group, 0);
+    EpiRank<LAFF_MAX_TOPK>::Params ep{sgt_raw + r0, gt_global + r0, count + r0, thr_key + r0,
+                                     slots + static_cast<long long>(r0) * LAFF_MAX_TOPK, rows, V, col_offset, k};
+    rc = launch_gemm<EpiRank<LAFF_MAX_TOPK>>(ops, ss, ep, st);
+    if (rc) return rc;
+  }
   if (k > 0) {
     topk_finalize_kernel<<<(Q + 127) / 128, 128, 0, st>>>(slots, Q, LAFF_MAX_TOPK, k, scale, topk_val, topk_idx); laff::count_launch();
     LAFF_CUDA(cudaGetLastError());
