@@ -318,6 +318,19 @@ __global__ void topk_finalize_kernel(const long long* __restrict__ slots, int Q,
 // ------------------------------------------------------------------------------------------------------------
 static uint64_t g_hint_override[2] = {0, 0};
 
+// Gallery column tiles per sweep launch.  The CTA pairs that share a gallery tile drift apart as a launch goes on (their
+// epilogue work is data dependent), the shared tile then misses L2 for the late ones, and on a power-capped kernel the
+// extra HBM traffic costs SM clock.  A kernel boundary re-aligns them: cutting a 1 M-video pass into 8 launches of ~480
+// column tiles measured 69.3 / 68.6 ms -> 60.8 ms per 10 k x 1 M sweep on the same box (2: 62.1, 4: 60.9, 16: 61.3;
+// profiles/r01_sched_experiments.md).  Launches stay >= 480 tiles (~65 waves of work units) so their tails remain small.
+// LAFF_SWEEP_COLSPLIT=n (read once) forces n launches per pass (diagnostics).
+static int sweep_tiles_per_launch(int tiles) {
+  static const int forced = [] { const char* e = getenv("LAFF_SWEEP_COLSPLIT"); return e ? atoi(e) : 0; }();
+  int split = forced > 0 ? forced : tiles / 480;
+  if (split < 1) split = 1;
+  return (tiles + split - 1) / split;
+}
+
 template <int CG, class Epi>
 static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, int num_kb, uint32_t idesc, const Sched& s,
                           const typename Epi::Params& ep, int sms, cudaStream_t st) {
@@ -700,9 +713,22 @@ int laff_sim_collect(const void* q, const void* g, int Q, int V, int D, long lon
   int blocks = static_cast<int>((total + 255) / 256 < op.sms * 8 ? (total + 255) / 256 : op.sms * 8);
   collect_init_kernel<<<blocks, 256, 0, st>>>(count, cand_val, cand_idx, Q, total); laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
-  const Sched s = make_sched(Q, V, op.cg, t.chunk_tiles, t.m_group, 0);
-  EpiCollect::Params ep{thr, count, cand_val, cand_idx, cap, Q, V, col_offset, scale};
-  return launch_gemm<EpiCollect>(op, s, ep, st);
+  const int tiles = (V + kBlockN - 1) / kBlockN;
+  const int tiles_per = sweep_tiles_per_launch(tiles);   // see there: launches of ~480 column tiles keep the CTAs aligned
+  for (int c0 = 0; c0 < V; c0 += tiles_per * kBlockN) {
+    const int cols = V - c0 < tiles_per * kBlockN ? V - c0 : tiles_per * kBlockN;
+    GemmOperands oc = op;
+    if (c0 > 0 || cols < V) {
+      rc = prepare_operands(&oc, q, static_cast<const uint16_t*>(g) + static_cast<long long>(c0) * ldg, Q, cols, D, ldq, ldg, dtype,
+                            t.cta_group);
+      if (rc) return rc;
+    }
+    const Sched s = make_sched(Q, cols, oc.cg, t.chunk_tiles, t.m_group, 0);
+    EpiCollect::Params ep{thr, count, cand_val, cand_idx, cap, Q, cols, col_offset + c0, scale};
+    rc = launch_gemm<EpiCollect>(oc, s, ep, st);
+    if (rc) return rc;
+  }
+  return LAFF_OK;
 }
 
 size_t laff_sim_gt_workspace_bytes(int Q, int D) {
@@ -780,11 +806,22 @@ int laff_sim_rank_topk(const void* q, const void* g, int Q, int V, int D, long l
                             t.cta_group);
       if (rc) return rc;
     }
-    const Sched ss = make_sched(rows, V, ops.cg, t.chunk_tiles, t.m_group, 0);
-    EpiRank<LAFF_MAX_TOPK>::Params ep{sgt_raw + r0, gt_global + r0, count + r0, thr_key + r0,
-                                     slots + static_cast<long long>(r0) * LAFF_MAX_TOPK, rows, V, col_offset, k};
-    rc = launch_gemm<EpiRank<LAFF_MAX_TOPK>>(ops, ss, ep, st);
-    if (rc) return rc;
+    const int tiles = (V + kBlockN - 1) / kBlockN;
+    const int tiles_per = sweep_tiles_per_launch(tiles);
+    for (int c0 = 0; c0 < V; c0 += tiles_per * kBlockN) {
+      const int cols = V - c0 < tiles_per * kBlockN ? V - c0 : tiles_per * kBlockN;
+      GemmOperands oc = ops;
+      if (c0 > 0 || cols < V) {
+        rc = prepare_operands(&oc, static_cast<const uint16_t*>(q) + static_cast<long long>(r0) * ldq,
+                              static_cast<const uint16_t*>(g) + static_cast<long long>(c0) * ldg, rows, cols, D, ldq, ldg, dtype, t.cta_group);
+        if (rc) return rc;
+      }
+      const Sched ss = make_sched(rows, cols, oc.cg, t.chunk_tiles, t.m_group, 0);
+      EpiRank<LAFF_MAX_TOPK>::Params ep{sgt_raw + r0, gt_global + r0, count + r0, thr_key + r0,
+                                       slots + static_cast<long long>(r0) * LAFF_MAX_TOPK, rows, cols, col_offset + c0, k};
+      rc = launch_gemm<EpiRank<LAFF_MAX_TOPK>>(oc, ss, ep, st);
+      if (rc) return rc;
+    }
   }
   if (k > 0) {
     topk_finalize_kernel<<<(Q + 127) / 128, 128, 0, st>>>(slots, Q, LAFF_MAX_TOPK, k, scale, topk_val, topk_idx); laff::count_launch();
