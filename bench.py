@@ -58,6 +58,16 @@ def peaks():
     return {"tensor_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}  # B200_PROFILING.md fallback (sustained)
 
 
+def sweep_launches(Q, V_local):
+    """Kernel launches per laff_sim_rank_topk call: one per group of 10 row tiles (2560 queries) and per ~480 gallery
+    column tiles (csrc/sim.cu: sweep_tiles_per_launch)."""
+    groups = (Q + 2559) // 2560
+    tiles = (V_local + 255) // 256
+    split = max(1, tiles // 480)
+    per = (tiles + split - 1) // split
+    return groups * ((tiles + per - 1) // per)
+
+
 def recorded_traffic():
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
@@ -400,7 +410,9 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_kernel<2, EpiRank<16>> (similarity sweep + rank + top-k)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_kernel<2, EpiRank<16>> (similarity sweep + rank + top-k; one sweep = one "
+                                                  "laff_sim_rank_topk call = %d back-to-back launches of this kernel, timed as a whole)"
+                                                  % sweep_launches(Q, n_local),
                      "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tensor_tflops"],
                      "peak_source": pk["source"] + " (bf16 dense sustained)",
                      "flop_per_launch": Q * n_local * FLOP_PER_PAIR, "avg_launch_ms": sweep_avg_ms,
