@@ -151,3 +151,25 @@ def test_shard_bounds_cover_the_gallery():
 def test_gallery_index_rejects_wrong_shard():
     with pytest.raises(ValueError):
         GalleryIndex(torch.zeros(5, 8), 100, 2, rank=0, world_size=2, backend=NumpyBackend())
+
+
+def test_collect_plan_keeps_its_statistical_margins():
+    """The threshold path of the writer lists takes the r-th best score of an n_s-row sample as its threshold: the number
+    of survivors in the whole shard then has mean r V / n_s and relative spread 1 / sqrt(r).  Whenever a plan is
+    returned, mean - 6 sigma must still cover k and mean + 6 sigma must fit the candidate slots; small shards and lists
+    too long for the slots must get no plan (dense path)."""
+    from laff_b200.retrieval import CudaBackend as B
+    assert B.collect_plan(100000, 500) is None and B.collect_plan(8 * B.collect_sample - 1, 10) is None
+    assert B.collect_plan(1000000, 0) is None
+    seen = 0
+    for V in (8 * B.collect_sample, 1000000, 3000000, 20000000):
+        for k in (1, 10, 100, 500, 1000, 2000, 2048):
+            plan = B.collect_plan(V, k)
+            if plan is None:
+                continue
+            n_s, r = plan
+            seen += 1
+            mean, rel = r * V / n_s, 6.0 / r ** 0.5
+            assert n_s == B.collect_sample and 1 <= r <= 2048
+            assert mean * (1 - rel) >= k and mean * (1 + rel) <= B.collect_cap
+    assert seen >= 10 and B.collect_plan(1000000, 2000) is not None and B.collect_plan(1000000, 500) is not None
