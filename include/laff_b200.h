@@ -62,8 +62,10 @@ long long laff_launch_count(int reset);
  *   m_group     number of query row-tiles that sweep the gallery together (L2 residency of the query block). */
 int laff_set_tuning(int cta_group, int chunk_tiles, int m_group);
 int laff_get_tuning(int* cta_group, int* chunk_tiles, int* m_group);
-/* laff_sim_rank_topk issues one launch per group of m_group row tiles (measured 4 % faster than one launch walking the
- * groups back to back); the environment variable LAFF_SWEEP_SPLIT=0, read once, restores the single launch (diagnostics). */
+/* laff_sim_rank_topk (and laff_sim_collect) cut a sweep into back-to-back launches: one per group of m_group row tiles and
+ * per ~480 gallery column tiles, which keeps the CTA pairs that share a gallery tile aligned (10 % faster than one launch,
+ * same results).  Diagnostics, environment variables read once: LAFF_SWEEP_SPLIT=0 (no row-group split),
+ * LAFF_SWEEP_COLSPLIT=n (n launches per gallery pass; 1 = no column split). */
 
 /* Which variant of the single-kernel fusion (laff_fuse_forward) runs: 0 = chosen per call from the row count,
  * 1 = cta_group::1 MMAs in 2-CTA clusters (all SMs), 2 = cta_group::2 MMA pairs in 4-CTA clusters (fewer bytes per
