@@ -375,7 +375,21 @@ int laff_dsl_forward_backward(const float* txt, const float* vis, int B, int H, 
  *     beta1, beta2, eps, bias correction at `step`), all tensors in one pass, no host synchronisation.  Tensors with
  *     grad == NULL are skipped like parameters without .grad.  blk_* come from laff_optimizer_blocks (host helper: call
  *     with NULL outputs for the count, then with buffers of that capacity).  step_dev / lr_dev (optional device words)
- *     override `step` / `lr`, so a captured CUDA graph of the whole training step can be replayed. */
+ *     override `step` / `lr`, so a captured CUDA graph of the whole training step can be replayed.
+ * laff_optimizer_step_scaled — the same step under the reference's float16 branch (model/model.py:970-989:
+ *     scaler.scale(loss).backward(); clip_grad_norm_ on the SCALED gradients; scaler.step(); scaler.update()), with the
+ *     GradScaler state in a device struct: clip coefficient min(1, max / (S*||g|| + 1e-6)); the step is skipped
+ *     when a gradient is non-finite or S*max|g| >= overflow_limit (65520: it would be inf in the reference's fp16
+ *     backward); then S *= backoff after a skipped step, S *= growth after growth_interval good ones.  step_dev is
+ *     advanced here, and only on a good step.  total_norm_dev receives S*||g|| (what clip_grad_norm_ returns there);
+ *     ctl_dev = {coef, skipped}.  No host synchronisation: graph-capturable. */
+typedef struct {
+  float scale;        /* S, torch default init 65536 */
+  int growth_tracker; /* good steps since the last change of S */
+  int found_inf;      /* 1 if the last step was skipped */
+  int skipped;        /* skipped steps so far */
+} laff_scaler_state;
+
 typedef struct {
   float* param;
   const float* grad;
@@ -412,6 +426,11 @@ int laff_optimizer_step(const laff_opt_tensor* tensors_dev, const int* blk_tenso
                         int n_blocks, int kind, float lr, float alpha_or_beta1, float beta2, float eps, long long step,
                         float max_grad_norm, double* partial_dev, double* total_norm_dev, const long long* step_dev,
                         const float* lr_dev, void* stream);
+int laff_optimizer_step_scaled(const laff_opt_tensor* tensors_dev, const int* blk_tensor_dev, const long long* blk_start_dev,
+                               int n_blocks, int kind, float alpha_or_beta1, float beta2, float eps, float max_grad_norm,
+                               double* partial_dev, float* partial_max_dev, double* total_norm_dev, long long* step_dev,
+                               const float* lr_dev, laff_scaler_state* scaler_dev, float growth_factor, float backoff_factor,
+                               int growth_interval, float overflow_limit, float* ctl_dev, void* stream);
 
 #ifdef __cplusplus
 }

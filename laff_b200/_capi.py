@@ -112,6 +112,8 @@ SIGNATURES = {
     "laff_frame_pool_backward": (_i, [_vp, _ll, _i, _i, _vp, _vp, _ll, _d, _vp, _vp, _vp, _vp, _vp]),
     "laff_optimizer_blocks": (_i, [_vp, _i, _vp, _vp, _i]),
     "laff_optimizer_step": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _ll, _f, _vp, _vp, _vp, _vp, _vp]),
+    "laff_optimizer_step_scaled": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _vp,
+                                        _vp]),
     "laff_vocab_create": (_vp, [_vp, _vp, _vp, _i]),
     "laff_vocab_destroy": (None, [_vp]),
     "laff_tokenize_lookup": (_ll, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _ll]),

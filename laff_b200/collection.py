@@ -66,7 +66,9 @@ def caption_features(config, text_dir: str, cap_ids: Sequence[str], captions: Ma
 
 def build_gallery(model, config, rootpath: str, collection: str, device, rank: int = 0, world_size: int = 1):
     """Gallery ids + the resident index of this rank's shard (predictor.py:190-214 + the vis loop of model.predict)."""
-    if getattr(config, "frame_feat_input", False) or getattr(config, "vid_frame_feats", None):
+    # base_config.py:171-173 ships a non-empty vid_frame_feats together with frame_feat_input = False: only the flag
+    # decides whether frame files are read (predictor.py:191)
+    if getattr(config, "frame_feat_input", False):
         raise NotImplementedError("frame-level feature files (FeatureData/frame) are not read yet: LAFF collections only")
     with open(os.path.join(rootpath, collection, "VideoSets", collection + ".txt")) as f:
         vis_ids = list(map(str.strip, f))

@@ -270,7 +270,7 @@ struct EpiCollect {
 __global__ void collect_init_kernel(int32_t* count, float* cand_val, int32_t* cand_idx, int Q, long long total) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  if (i < Q) count[i] = 0;
+  for (long long j = i; j < Q; j += stride) count[j] = 0;   // the grid is capped: Q may exceed it
   for (long long j = i; j < total; j += stride) {
     cand_val[j] = -INFINITY;
     cand_idx[j] = -1;

@@ -442,29 +442,46 @@ constexpr int kOptChunk = 256 * 8;  // elements one block of the optimizer kerne
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// partial[blk] = sum of squares of the block's gradient chunk; partial_max[blk] (optional, the loss-scaler variant) = the
+// largest |g| of the chunk (NaN-propagating: a non-finite gradient makes it non-finite).
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const laff_opt_tensor* __restrict__ ts, const int* __restrict__ blk_tensor,
-                                                          const long long* __restrict__ blk_start, double* __restrict__ partial) {
+                                                          const long long* __restrict__ blk_start, double* __restrict__ partial,
+                                                          float* __restrict__ partial_max) {
   const laff_opt_tensor t = ts[blk_tensor[blockIdx.x]];
   const long long s = blk_start[blockIdx.x];
   float part = 0.f;  // 8 squares per thread in fp32, everything above that in fp64
+  float mx = 0.f;
+  auto amax = [](float m, float v) { const float a = fabsf(v); return (a > m || a != a) ? a : m; };
   if (t.grad) {
     const long long j0 = s + threadIdx.x * 8;
     if (aligned16(t.grad) && j0 + 8 <= t.n) {
       const float4 a = *reinterpret_cast<const float4*>(t.grad + j0), b = *reinterpret_cast<const float4*>(t.grad + j0 + 4);
       part = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+      if (partial_max) mx = amax(amax(amax(amax(amax(amax(amax(amax(0.f, a.x), a.y), a.z), a.w), b.x), b.y), b.z), b.w);
     } else {
-      for (long long j = j0; j < j0 + 8 && j < t.n; ++j) part = fmaf(t.grad[j], t.grad[j], part);
+      for (long long j = j0; j < j0 + 8 && j < t.n; ++j) {
+        part = fmaf(t.grad[j], t.grad[j], part);
+        mx = amax(mx, t.grad[j]);
+      }
     }
   }
   const double acc = part;
   __shared__ double sh[256];
+  __shared__ float shm[256];
   sh[threadIdx.x] = acc;
+  shm[threadIdx.x] = mx;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    if (threadIdx.x < o) {
+      sh[threadIdx.x] += sh[threadIdx.x + o];
+      shm[threadIdx.x] = (shm[threadIdx.x] != shm[threadIdx.x]) ? shm[threadIdx.x] : amax(shm[threadIdx.x], shm[threadIdx.x + o]);
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = sh[0];
+    if (partial_max) partial_max[blockIdx.x] = shm[0];
+  }
 }
 
 __global__ void sqnorm_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
@@ -480,6 +497,66 @@ __global__ void sqnorm_final_kernel(const double* __restrict__ partial, int n, d
   if (threadIdx.x == 0) *out = sqrt(sh[0]);
 }
 
+// Loss-scaler variant (torch.cuda.amp.GradScaler as the reference drives it, model/model.py:970-989): the gradients the
+// reference clips are the SCALED ones, so clip_grad_norm_ sees S * ||g||; scaler.step() then unscales and skips the
+// optimizer step when a gradient is non-finite; scaler.update() halves S after a skipped step and doubles it after
+// `growth_interval` good ones.  Gradients here are fp32 and unscaled, so (a) the clip coefficient is
+// min(1, max_norm / (S ||g|| + 1e-6)) on the raw gradients (scale and unscale cancel), and (b) the fp16 overflow that
+// makes the reference skip is emulated on the parameter gradients, which all pass through fp16 in the reference's
+// autocast backward: a step is skipped when S * max|g| would round to inf in fp16 (>= overflow_limit = 65520) or a
+// gradient is non-finite.  One thread; writes ctl = {coef, skip flag}, the scaled norm, and advances S / the growth
+// tracker / the optimizer step count for the step kernel that follows.
+__global__ void scaler_final_kernel(const double* __restrict__ partial, const float* __restrict__ partial_max, int n, float max_norm,
+                                    laff_scaler_state* __restrict__ sc, float growth, float backoff, int interval,
+                                    float overflow_limit, double* __restrict__ norm_out, float* __restrict__ ctl,
+                                    long long* __restrict__ step_dev) {
+  __shared__ double sh[256];
+  __shared__ float shm[256];
+  double acc = 0.0;
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    acc += partial[i];
+    const float v = partial_max[i];
+    if (v != v || v > mx) mx = (mx != mx) ? mx : v;
+  }
+  sh[threadIdx.x] = acc;
+  shm[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[threadIdx.x] += sh[threadIdx.x + o];
+      const float a = shm[threadIdx.x], b = shm[threadIdx.x + o];
+      shm[threadIdx.x] = (a != a) ? a : ((b != b || b > a) ? b : a);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  const double S = static_cast<double>(sc->scale);
+  const double norm = sqrt(sh[0]) * S;   // what clip_grad_norm_ measures on the scaled gradients
+  const double gmax = static_cast<double>(shm[0]) * S;
+  const bool bad = !(norm == norm) || isinf(norm) || !(gmax == gmax) || gmax >= static_cast<double>(overflow_limit);
+  float coef = 1.0f;
+  if (max_norm > 0.f && !bad) {
+    const float c = static_cast<float>(static_cast<double>(max_norm) / (norm + 1e-6));
+    coef = c < 1.0f ? c : 1.0f;
+  }
+  ctl[0] = coef;
+  ctl[1] = bad ? 1.0f : 0.0f;
+  *norm_out = norm;
+  sc->found_inf = bad ? 1 : 0;
+  if (bad) {
+    sc->scale = static_cast<float>(S * backoff);
+    sc->growth_tracker = 0;
+    sc->skipped += 1;
+  } else {
+    if (step_dev) *step_dev += 1;   // optimizer.step() only runs (and Adam's step only advances) on a good step
+    if (++sc->growth_tracker >= interval) {
+      sc->scale = static_cast<float>(S * growth);
+      sc->growth_tracker = 0;
+    }
+  }
+}
+
 // kind 0: RMSprop (torch defaults: no momentum, not centered), kind 1: Adam.  The clip coefficient is derived on the
 // device from the total gradient norm (clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1), so the step
 // needs no host round trip.
@@ -487,9 +564,10 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const laff_opt_tensor* __
                                                        const long long* __restrict__ blk_start, const double* __restrict__ total_norm,
                                                        float max_norm, int kind, float lr, float alpha_or_beta1, float beta2, float eps,
                                                        float bias_c1, float bias_c2, const long long* __restrict__ step_dev,
-                                                       const float* __restrict__ lr_dev) {
+                                                       const float* __restrict__ lr_dev, const float* __restrict__ ctl) {
   const laff_opt_tensor t = ts[blk_tensor[blockIdx.x]];
   if (!t.grad) return;
+  if (ctl && ctl[1] != 0.f) return;   // loss-scaler variant: overflow step, the optimizer is skipped
   if (lr_dev) lr = *lr_dev;
   if (step_dev && kind == 1) {  // graph replays: the step count lives on the device
     const double st = static_cast<double>(*step_dev);
@@ -498,7 +576,9 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const laff_opt_tensor* __
   }
   const long long s = blk_start[blockIdx.x];
   float coef = 1.0f;
-  if (max_norm > 0.f) {
+  if (ctl) {
+    coef = ctl[0];
+  } else if (max_norm > 0.f) {
     const float c = static_cast<float>(static_cast<double>(max_norm) / (*total_norm + 1e-6));
     coef = c < 1.0f ? c : 1.0f;
   }
@@ -745,7 +825,7 @@ extern "C" int laff_optimizer_step(const laff_opt_tensor* tensors_dev, const int
   if (rc) return rc;
   if (n_blocks == 0) return LAFF_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  grad_sqnorm_kernel<<<n_blocks, 256, 0, st>>>(tensors_dev, blk_tensor_dev, blk_start_dev, partial_dev);
+  grad_sqnorm_kernel<<<n_blocks, 256, 0, st>>>(tensors_dev, blk_tensor_dev, blk_start_dev, partial_dev, nullptr);
   sqnorm_final_kernel<<<1, 256, 0, st>>>(partial_dev, n_blocks, total_norm_dev);
   float c1 = 1.f, c2 = 1.f;
   if (kind == 1) {
@@ -753,7 +833,32 @@ extern "C" int laff_optimizer_step(const laff_opt_tensor* tensors_dev, const int
     c2 = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step))));
   }
   opt_step_kernel<<<n_blocks, 256, 0, st>>>(tensors_dev, blk_tensor_dev, blk_start_dev, total_norm_dev, max_grad_norm, kind, lr,
-                                            alpha_or_beta1, beta2, eps, c1, c2, step_dev, lr_dev);
+                                            alpha_or_beta1, beta2, eps, c1, c2, step_dev, lr_dev, nullptr);
+  count_launch(3);
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}
+
+extern "C" int laff_optimizer_step_scaled(const laff_opt_tensor* tensors_dev, const int* blk_tensor_dev,
+                                          const long long* blk_start_dev, int n_blocks, int kind, float alpha_or_beta1, float beta2,
+                                          float eps, float max_grad_norm, double* partial_dev, float* partial_max_dev,
+                                          double* total_norm_dev, long long* step_dev, const float* lr_dev,
+                                          laff_scaler_state* scaler_dev, float growth_factor, float backoff_factor,
+                                          int growth_interval, float overflow_limit, float* ctl_dev, void* stream) {
+  LAFF_REQUIRE(tensors_dev && blk_tensor_dev && blk_start_dev && partial_dev && partial_max_dev && total_norm_dev && step_dev &&
+                   lr_dev && scaler_dev && ctl_dev && n_blocks >= 0 && (kind == 0 || kind == 1) && growth_factor >= 1.f &&
+                   backoff_factor > 0.f && backoff_factor <= 1.f && growth_interval >= 1,
+               LAFF_EINVAL, "laff_optimizer_step_scaled: bad arguments");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  if (n_blocks == 0) return LAFF_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  grad_sqnorm_kernel<<<n_blocks, 256, 0, st>>>(tensors_dev, blk_tensor_dev, blk_start_dev, partial_dev, partial_max_dev);
+  scaler_final_kernel<<<1, 256, 0, st>>>(partial_dev, partial_max_dev, n_blocks, max_grad_norm, scaler_dev, growth_factor,
+                                         backoff_factor, growth_interval, overflow_limit, total_norm_dev, ctl_dev, step_dev);
+  opt_step_kernel<<<n_blocks, 256, 0, st>>>(tensors_dev, blk_tensor_dev, blk_start_dev, total_norm_dev, max_grad_norm, kind, 0.f,
+                                            alpha_or_beta1, beta2, eps, 1.f, 1.f, step_dev, lr_dev, ctl_dev);
   count_launch(3);
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;

@@ -225,8 +225,11 @@ class Multi_head_MyApply_Attention(nn.Module):
         return self.attention_layer[head].get_attention_weight().detach()
 
 
-def get_attention_layer(attention_type: str, common_space_dim, encoder_num, opt):
-    """model/model.py:95-208, restricted to the variants the LAFF / LAFF-ml scripts select."""
+def get_attention_layer(attention_type: str, common_space_dim, encoder_num, opt, single_head_ok: bool = False):
+    """model/model.py:95-208, restricted to the variants the LAFF / LAFF-ml scripts select.  The fusion
+    nets pool over H heads and need the multi-head block; the single-head `Attention_1` names are only handed out
+    where the caller says it can take them (the frame-level attention of LAFF-ml), so an unsupported configuration
+    fails at construction rather than at the first encode."""
     if attention_type == "Multi_head_MyApply_Attention":
         return Multi_head_MyApply_Attention(
             common_space_dim, opt.multi_head_attention["heads"], common_space_dim // opt.multi_head_attention["heads"],
@@ -235,6 +238,9 @@ def get_attention_layer(attention_type: str, common_space_dim, encoder_num, opt)
     table = {"attention_noAverageMul_Ave": (True, False), "attention_noAveNoAverageMul": (False, False),
              "attention_averageMul": (True, True), "average_AverageMul_noAve": (False, True)}
     if attention_type in table:
+        if not single_head_ok:
+            raise NotImplementedError("attention type %r (single-head Attention_1) as the fusion block: the shipped "
+                                      "LAFF configs use 'Multi_head_MyApply_Attention' (configs/laff.py:41)" % attention_type)
         a, m = table[attention_type]
         return Attention_1(common_space_dim, with_ave=a, mul=m)
     raise NotImplementedError("attention type %r is an ablation variant outside the LAFF hot path" % attention_type)
@@ -581,7 +587,7 @@ class VisMutiTransformNetPlusFrameFeat(nn.Module):
             if opt.vis_frame_addFC:
                 raise NotImplementedError("vis_frame_addFC=True is not used by the LAFF-ml script (FrameLaff...:58)")
             self.frame_attention[each] = nn.Sequential(
-                get_attention_layer(opt.vis_frame_attention, opt.vis_fc_layers[0][each], 1, opt))
+                get_attention_layer(opt.vis_frame_attention, opt.vis_fc_layers[0][each], 1, opt, single_head_ok=True))
 
     def frame_pool(self, feat_name, frames: torch.Tensor) -> torch.Tensor:
         att: Attention_1 = self.frame_attention[feat_name][0]
@@ -787,12 +793,15 @@ class W2VVPP(nn.Module):
         return loss
 
     def _make_optimizer(self):
-        from .train import DeviceOptimizer
+        from .train import DeviceGradScaler, DeviceOptimizer
         opt = self.opt
         kind = getattr(opt, "optimizer", "rmsprop")
         eps = self._adam_eps if kind == "adam" else None
+        # config.float16: the reference trains under autocast + GradScaler and clips the *scaled* gradients
+        # (model/model.py:970-989); `self.scaler` mirrors its attribute of the same name (model/model.py:793)
+        self.scaler = DeviceGradScaler() if getattr(opt, "float16", False) else None
         return DeviceOptimizer(list(self.parameters()), kind=kind, lr=getattr(opt, "lr", 1e-4), eps=eps,
-                               max_grad_norm=self.grad_clip if self.grad_clip and self.grad_clip > 0 else 0.0)
+                               max_grad_norm=self.grad_clip if self.grad_clip and self.grad_clip > 0 else 0.0, scaler=self.scaler)
 
     _adam_eps = 1e-8  # torch default (model/model.py:824); the LAFF class overrides it with 1e-4 (model/model.py:2022)
     use_cuda_graph = True   # replay the whole step as one CUDA graph from the 4th step on (launch-bound at B = 128)
@@ -814,8 +823,9 @@ class W2VVPP(nn.Module):
         self.iters += 1
         dev = _cuda_device(next(self.parameters()).device)
         # config.float16 (AMP in the reference, model/model.py:970-989): fp16 tensor-core operands with fp32 accumulation,
-        # master weights and gradients — no GradScaler is needed (nothing is stored in fp16), and the reference's
-        # clip-before-unscale ordering has no counterpart.
+        # master weights and gradients.  Nothing is stored in fp16 here, but the reference's ordering -- clip_grad_norm_ on
+        # the scaled gradients, skipped steps, the moving loss scale -- is observable in the trained weights, so the
+        # optimizer reproduces it on the device (train.DeviceGradScaler / laff_optimizer_step_scaled).
         precision = "fp16" if getattr(opt, "float16", False) else self.train_precision
         if getattr(self, "optimizer", None) is None:
             self.optimizer = self._make_optimizer()

@@ -568,7 +568,9 @@ def dsl_forward_backward(txt: torch.Tensor, vis: torch.Tensor, temp: float = 100
 def mrl_score_forward_backward(score: torch.Tensor, margin: float, max_violation: bool, direction: str,
                                cost_style: str, need_grad: bool = True):
     _need_cuda(score)
-    score = _rowmajor(score.detach().float())
+    # the C entry point uses one pitch for the scores and their gradient: a strided view of a wider matrix would make
+    # it write past the contiguous [B, B] gradient, so the scores are made contiguous first
+    score = score.detach().float().contiguous()
     B = score.shape[0]
     loss = torch.empty((), dtype=torch.float32, device=score.device)
     d_score = torch.empty((B, B), dtype=torch.float32, device=score.device) if need_grad else None

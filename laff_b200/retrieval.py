@@ -112,16 +112,22 @@ class SearchResult:
         `.cpu()` calls cost four round trips -- visible once a step is a few milliseconds, as at 8 GPUs)."""
         if not self.rank0.is_cuda:
             return self
-        parts = [self.rank0.to(torch.int32).reshape(-1), self.topk_val.float().reshape(-1).view(torch.int32),
-                 self.topk_idx.to(torch.int32).reshape(-1), self.metrics.double().reshape(-1).view(torch.int32)]
+        # the float64 metrics go first so that their view starts at an 8-byte aligned offset whatever Q is
+        parts = [self.metrics.double().reshape(-1).view(torch.int32), self.rank0.to(torch.int32).reshape(-1),
+                 self.topk_val.float().reshape(-1).view(torch.int32), self.topk_idx.to(torch.int32).reshape(-1)]
         flat = torch.cat(parts)
         host = torch.empty(flat.shape, dtype=torch.int32, pin_memory=True)
         host.copy_(flat, non_blocking=True)
         torch.cuda.current_stream(flat.device).synchronize()
-        n0, n1, n2 = parts[0].numel(), parts[1].numel(), parts[2].numel()
-        return SearchResult(host[:n0], host[n0:n0 + n1].view(torch.float32).reshape(self.topk_val.shape),
-                            host[n0 + n1:n0 + n1 + n2].reshape(self.topk_idx.shape),
-                            host[n0 + n1 + n2:].view(torch.float64))
+        return self._unpack(host, self.rank0.numel(), tuple(self.topk_val.shape), self.metrics.numel())
+
+    @staticmethod
+    def _unpack(host: torch.Tensor, Q: int, klist_shape, n_metrics: int) -> "SearchResult":
+        """Inverse of the packing in to_host(): int32 words [metrics (2 words each) | rank0 | score bits | indices]."""
+        n_m, n_k = 2 * n_metrics, klist_shape[0] * klist_shape[1]
+        o1 = n_m + Q
+        return SearchResult(host[n_m:o1], host[o1:o1 + n_k].view(torch.float32).reshape(klist_shape),
+                            host[o1 + n_k:o1 + 2 * n_k].reshape(klist_shape), host[:n_m].view(torch.float64))
 
 
 class GalleryIndex:

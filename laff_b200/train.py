@@ -159,13 +159,63 @@ class FusionTrainStep:
         return dxs
 
 
+class DeviceGradScaler:
+    """torch.cuda.amp.GradScaler as the reference's float16 training branch drives it (model/model.py:793, :970-989),
+    with its state -- scale S, growth tracker, found-inf flag, skipped-step count -- in four device words updated by
+    `laff_optimizer_step_scaled`, so the step stays free of host synchronisation and graph-capturable.  The gradients
+    of this implementation are fp32 and never scaled; S enters where the reference's ordering makes it observable:
+    `clip_grad_norm_` runs on the scaled gradients (the effective clip threshold on the true gradients is
+    grad_clip / S), and a step whose scaled parameter gradients would overflow fp16 is skipped and halves S."""
+
+    def __init__(self, init_scale: float = 65536.0, growth_factor: float = 2.0, backoff_factor: float = 0.5,
+                 growth_interval: int = 2000, overflow_limit: float = 65520.0):
+        self.init_scale, self.growth_factor, self.backoff_factor = float(init_scale), float(growth_factor), float(backoff_factor)
+        self.growth_interval, self.overflow_limit = int(growth_interval), float(overflow_limit)
+        self._state = None
+
+    def state(self, device) -> torch.Tensor:
+        if self._state is None or self._state.device != device:
+            st = torch.zeros(4, dtype=torch.int32, device=device)
+            st[:1].view(torch.float32).fill_(self.init_scale)
+            self._state = st
+        return self._state
+
+    def _host(self):
+        if self._state is None:
+            return self.init_scale, 0, 0, 0
+        h = self._state.cpu()
+        return float(h[:1].view(torch.float32)[0]), int(h[1]), int(h[2]), int(h[3])
+
+    def get_scale(self) -> float:
+        return self._host()[0]
+
+    def skipped_steps(self) -> int:
+        return self._host()[3]
+
+    def last_step_skipped(self) -> bool:
+        return bool(self._host()[2])
+
+    def state_dict(self):
+        s, tracker, _, _ = self._host()
+        return {"scale": s, "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
+                "growth_interval": self.growth_interval, "_growth_tracker": tracker}
+
+    def load_state_dict(self, sd):
+        self.growth_factor, self.backoff_factor = float(sd["growth_factor"]), float(sd["backoff_factor"])
+        self.growth_interval = int(sd["growth_interval"])
+        self.init_scale = float(sd["scale"])
+        if self._state is not None:
+            self._state[:1].view(torch.float32).fill_(self.init_scale)
+            self._state[1] = int(sd.get("_growth_tracker", 0))
+
+
 class DeviceOptimizer:
     """clip_grad_norm_ + torch.optim.RMSprop / Adam semantics for a fixed list of parameters, one fused device pass per
     step (`laff_optimizer_step`).  State tensors are allocated on first use; parameters whose `.grad` is None at the
     first step are skipped for good (like parameters that never receive a gradient in the reference's model)."""
 
     def __init__(self, params: Sequence[nn.Parameter], kind: str = "rmsprop", lr: float = 1e-4, alpha: float = 0.99,
-                 betas=(0.9, 0.999), eps: Optional[float] = None, max_grad_norm: float = 0.0):
+                 betas=(0.9, 0.999), eps: Optional[float] = None, max_grad_norm: float = 0.0, scaler: Optional["DeviceGradScaler"] = None):
         if kind not in ("rmsprop", "adam"):
             raise LaffError("optimizer %r: the reference trains with 'rmsprop' or 'adam'" % kind)
         self.params = [p for p in params]
@@ -174,6 +224,8 @@ class DeviceOptimizer:
         self.max_grad_norm = float(max_grad_norm)
         self.step_count = 0
         self._built = None
+        self._state = {}
+        self.scaler = scaler   # the reference's float16 branch (model/model.py:970-989): see DeviceGradScaler
         self.param_groups = [{"lr": self.lr}]  # lr schedulers of the caller read / write this like torch's
 
     def _build(self):
@@ -181,8 +233,19 @@ class DeviceOptimizer:
         if not live:
             raise LaffError("DeviceOptimizer.step: no parameter has a gradient")
         dev = live[0].device
-        self.state1 = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in live]
-        self.state2 = [torch.zeros_like(p, memory_format=torch.contiguous_format) if self.kind == "adam" else None for p in live]
+        # a rebuild (a parameter or gradient was re-allocated) keeps the running averages of the parameters it already
+        # tracked, keyed by parameter object, and the device-side step count; only new parameters start from zero
+        old = self._state if getattr(self, "_state", None) else {}
+        self._state = {}
+        for p in live:
+            s1, s2 = old.get(id(p), (None, None))
+            if s1 is None or s1.shape != p.shape or s1.device != p.device:
+                s1 = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                s2 = torch.zeros_like(p, memory_format=torch.contiguous_format) if self.kind == "adam" else None
+            self._state[id(p)] = (s1, s2)
+        self.state1 = [self._state[id(p)][0] for p in live]
+        self.state2 = [self._state[id(p)][1] for p in live]
+        prev_step = self._built["step_dev"] if self._built is not None else None
         arr = (OptTensor * len(live))()
         for i, p in enumerate(live):
             if not p.is_contiguous() or not p.grad.is_contiguous() or p.dtype != torch.float32:
@@ -204,8 +267,11 @@ class DeviceOptimizer:
             "live": live, "ptrs": [(p.data_ptr(), p.grad.data_ptr()) for p in live], "desc": raw,
             "bt": torch.tensor(list(bt), dtype=torch.int32, device=dev), "bs": torch.tensor(list(bs), dtype=torch.int64, device=dev),
             "partial": torch.empty(n_blocks, dtype=torch.float64, device=dev),
+            "partial_max": torch.empty(n_blocks, dtype=torch.float32, device=dev),
+            "ctl": torch.zeros(2, dtype=torch.float32, device=dev),
             "norm": torch.zeros(1, dtype=torch.float64, device=dev), "n_blocks": n_blocks,
-            "step_dev": torch.full((1,), self.step_count, dtype=torch.int64, device=dev),
+            # the device word is the authoritative step count (graph replays advance it, not the Python counter)
+            "step_dev": prev_step if prev_step is not None else torch.full((1,), self.step_count, dtype=torch.int64, device=dev),
             "lr_dev": torch.zeros(1, dtype=torch.float32, device=dev), "lr_host": None}
 
     def step(self) -> torch.Tensor:
@@ -220,8 +286,16 @@ class DeviceOptimizer:
             b = self._built
         self.sync_lr()
         self.step_count += 1
-        b["step_dev"].add_(1)
         first = self.alpha if self.kind == "rmsprop" else self.betas[0]
+        if self.scaler is not None:
+            sc = self.scaler
+            _capi.call("laff_optimizer_step_scaled", ops._ptr(b["desc"]), ops._ptr(b["bt"]), ops._ptr(b["bs"]), b["n_blocks"],
+                       0 if self.kind == "rmsprop" else 1, float(first), float(self.betas[1]), self.eps, self.max_grad_norm,
+                       ops._ptr(b["partial"]), ops._ptr(b["partial_max"]), ops._ptr(b["norm"]), ops._ptr(b["step_dev"]),
+                       ops._ptr(b["lr_dev"]), ops._ptr(sc.state(b["desc"].device)), sc.growth_factor, sc.backoff_factor,
+                       sc.growth_interval, sc.overflow_limit, ops._ptr(b["ctl"]), ops._stream(b["desc"]))
+            return b["norm"]
+        b["step_dev"].add_(1)
         _capi.call("laff_optimizer_step", ops._ptr(b["desc"]), ops._ptr(b["bt"]), ops._ptr(b["bs"]), b["n_blocks"],
                    0 if self.kind == "rmsprop" else 1, float(b["lr_host"]), float(first), float(self.betas[1]), self.eps,
                    max(1, self.step_count), self.max_grad_norm, ops._ptr(b["partial"]), ops._ptr(b["norm"]),

@@ -403,12 +403,37 @@ def frame_attention_train(frames: np.ndarray, w: np.ndarray, dout: Optional[np.n
     return np.einsum("bf,bfd->d", de, x), de.sum()
 
 
+FP16_OVERFLOW = 65520.0   # smallest magnitude that rounds to inf in IEEE half precision
+
+
 def clip_and_step(sd: dict, grads: Mapping[str, np.ndarray], state: dict, optimizer="rmsprop", lr=1e-4, max_norm=2.0,
-                  alpha=0.99, betas=(0.9, 0.999), eps=None):
+                  alpha=0.99, betas=(0.9, 0.999), eps=None, scaler: Optional[dict] = None):
     """clip_grad_norm_(params, max_norm) then torch.optim.RMSprop / Adam (model/model.py:824-827, :2021-2024, :996-998).
-    `state` carries the optimizer state between steps.  Returns the total gradient norm before clipping."""
+    `state` carries the optimizer state between steps.  Returns the total gradient norm before clipping.
+
+    scaler (dict with 'scale', 'tracker'; torch GradScaler defaults growth 2 / backoff 0.5 / interval 2000) selects the
+    float16 branch (model/model.py:970-989): the loss is scaled by S before backward, clip_grad_norm_ then sees S*g,
+    scaler.step() unscales and skips the optimizer when a gradient is non-finite, scaler.update() moves S.  The
+    gradients given here are exact (unscaled); the reference's fp16 overflow is restated on the parameter gradients,
+    all of which pass through fp16 under autocast: overflow <=> S * max|g| >= 65520 (or a non-finite gradient).
+    Returns S * ||g|| in that case, like clip_grad_norm_ there; scaler['skipped'] says whether the step was dropped."""
     total = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values())))
-    coef = min(1.0, max_norm / (total + 1e-6)) if max_norm and max_norm > 0 else 1.0
+    if scaler is not None:
+        S = float(scaler["scale"])
+        gmax = max(float(np.abs(g).max()) for g in grads.values())
+        bad = (not np.isfinite(total)) or (not np.isfinite(gmax)) or S * gmax >= FP16_OVERFLOW
+        scaler["skipped"] = bool(bad)
+        if bad:
+            scaler["scale"], scaler["tracker"] = S * scaler.get("backoff", 0.5), 0
+            return S * total
+        scaler["tracker"] = scaler.get("tracker", 0) + 1
+        if scaler["tracker"] >= scaler.get("interval", 2000):
+            scaler["scale"], scaler["tracker"] = S * scaler.get("growth", 2.0), 0
+        total *= S
+        grads = {k: g.astype(np.float64) for k, g in grads.items()}
+        coef = min(1.0, max_norm / (total + 1e-6)) if max_norm and max_norm > 0 else 1.0
+    else:
+        coef = min(1.0, max_norm / (total + 1e-6)) if max_norm and max_norm > 0 else 1.0
     state["t"] = state.get("t", 0) + 1
     t = state["t"]
     for k, g in grads.items():
@@ -509,7 +534,7 @@ def gru_train(idx_vecs: Sequence[np.ndarray], sd: Mapping[str, np.ndarray], pref
 
 def laff_ml_train_step(sd: dict, vis_in: Mapping[str, np.ndarray], frames: np.ndarray, frame_feat: str,
                        txt_in: Mapping[str, np.ndarray], state: dict, heads: int, optimizer="rmsprop", lr=1e-4, grad_clip=2.0,
-                       margin=0.2, adam_eps=1e-8):
+                       margin=0.2, adam_eps=1e-8, scaler: Optional[dict] = None):
     """W2VVPP_MutiVisFrameFeat ('FrameLAFF' / LAFF-ml) training step: as laff_train_step with the frame-level block in
     front of the video net (model/model.py:2147-2190) and BatchNorm on every projected feature."""
     wkey = "vis_net.frame_attention.%s.0.embedding_common.0." % frame_feat
@@ -528,9 +553,11 @@ def laff_ml_train_step(sd: dict, vis_in: Mapping[str, np.ndarray], frames: np.nd
     grads[wkey + "weight"] = dw.reshape(1, -1)
     grads[wkey + "bias"] = np.array([dc])
     total = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values())))
+    if scaler is not None:
+        total *= float(scaler["scale"])
     coef = min(1.0, grad_clip / (total + 1e-6)) if grad_clip and grad_clip > 0 else 1.0
     clipped = {k: (g * coef) for k, g in grads.items()}
-    clip_and_step(sd, grads, state, optimizer, lr, grad_clip, eps=(adam_eps if optimizer == "adam" else None))
+    clip_and_step(sd, grads, state, optimizer, lr, grad_clip, eps=(adam_eps if optimizer == "adam" else None), scaler=scaler)
     return float(loss), clipped, total
 
 

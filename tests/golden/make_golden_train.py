@@ -125,15 +125,26 @@ def run_gru_case(mm, tag, optimizer, lr, steps=3, B=12, D=256, H=8, seed=95):
     return out
 
 
-def run_frame_case(mm, tag, optimizer, lr, steps=3, B=16, D=256, H=8, F=6, seed=91):
-    """'FrameLAFF' (LAFF-ml, W2VVPP_MutiVisFrameFeat): frame-level attention + BatchNorm on every projected feature."""
+def run_frame_case(mm, tag, optimizer, lr, steps=3, B=16, D=256, H=8, F=6, seed=91, amp=False):
+    """'FrameLAFF' (LAFF-ml, W2VVPP_MutiVisFrameFeat): frame-level attention + BatchNorm on every projected feature.
+
+    amp=True runs the reference's float16 branch (model/model.py:970-989: autocast, scaler.scale(loss).backward(),
+    clip_grad_norm_ on the scaled gradients, scaler.step / update) -- the branch configs/FrameLaff_...:33 selects.  The
+    reference imports torch.cuda.amp's autocast / GradScaler, which switch themselves off without a CUDA device; here
+    the two names are bound to torch's CPU flavours of the same classes (fp16 autocast, GradScaler('cpu')), so the
+    reference's own step code runs with a live loss scale.  Per step the loss, the scale after scaler.update() and
+    whether the step was skipped are recorded; state dicts only after the first executed step and at the end."""
     import torch
+    if amp:
+        mm.autocast = lambda: torch.autocast("cpu", dtype=torch.float16)
+        mm.GradScaler = lambda: torch.amp.GradScaler("cpu")
+        mm.float16 = True
     dims = SMALL
     vis_dims = {synth.VIS_C3D: dims["c3d"], synth.VIS_TF: dims["tf"], synth.VIS_X3D: dims["x3d"], synth.VIS_IRCSN: dims["ircsn"],
                 synth.VIS_FRAME: dims["clip"]}
     cfg = mg.make_config("frame", D, H, vis_dims, dims)
     cfg.dropout = 0.0
-    cfg.float16 = False            # AMP needs CUDA autocast; the fp32 path is the numerical reference
+    cfg.float16 = bool(amp)        # False: the fp32 path is the numerical reference
     cfg.optimizer, cfg.lr = optimizer, lr
     torch.manual_seed(0)
     model = mm.W2VVPP_MutiVisFrameFeat(cfg)
@@ -144,7 +155,7 @@ def run_frame_case(mm, tag, optimizer, lr, steps=3, B=16, D=256, H=8, F=6, seed=
            "frame_feat": np.array(synth.VIS_FRAME)}
     for k, v in sd0.items():
         out["sd0/" + k] = v
-    losses = []
+    losses, scales, skipped, first_done = [], [], [], None
     for s in range(steps):
         vis_in = {n: synth.feature(seed + s, "vis/" + n, B, d, "relu") for n, d in vis_dims.items() if n != synth.VIS_FRAME}
         fr = synth.feature(seed + s, "frames", B * F, dims["clip"]).reshape(B, F, dims["clip"])
@@ -165,8 +176,23 @@ def run_frame_case(mm, tag, optimizer, lr, steps=3, B=16, D=256, H=8, F=6, seed=
                       "captions": {k: torch.from_numpy(v) for k, v in txt_in.items()}, "captions_task2": None,
                       "vis_frame_feat_dict": {"mask_tensor": torch.from_numpy(mask), synth.VIS_FRAME: torch.from_numpy(fr.copy())},
                       "vis_origin_frame_tuple": None}
+        if amp:
+            before = model.scaler.get_scale()
         items = model(train_data, epoch=0)
-        losses.append(float(items["triplet_loss"]))
+        losses.append(float(items["triplet_loss"].detach()))
+        if amp:
+            scales.append(model.scaler.get_scale())
+            skipped.append(int(scales[-1] < before))
+            if not skipped[-1] and first_done is None:
+                first_done = s
+                out["first_executed_step"] = np.int64(s)
+                for k, p in model.named_parameters():   # unscaled + clipped, as scaler.step() leaves them in .grad
+                    if p.grad is not None:
+                        out["grad_first/" + k] = p.grad.detach().float().numpy().copy()
+            if s == first_done or s == steps - 1:
+                for k, v in model.state_dict().items():
+                    out["sd%d/%s" % (s + 1, k)] = v.detach().float().numpy().copy()
+            continue
         if s == 0:
             for k, p in model.named_parameters():
                 if p.grad is not None:
@@ -174,6 +200,10 @@ def run_frame_case(mm, tag, optimizer, lr, steps=3, B=16, D=256, H=8, F=6, seed=
         for k, v in model.state_dict().items():
             out["sd%d/%s" % (s + 1, k)] = v.detach().numpy().copy()
     out["losses"] = np.array(losses)
+    if amp:
+        out["scales"], out["skipped"] = np.array(scales), np.array(skipped)
+        mm.float16 = False
+        print(tag, "scales", scales, "skipped", skipped)
     print(tag, "losses", losses)
     return out
 
@@ -195,6 +225,10 @@ def main():
         np.savez_compressed(os.path.join(HERE, "train_gru_rmsprop.npz"), **run_gru_case(mm, "gru_rmsprop", "rmsprop", 1e-3))
     if not only or "frame_rmsprop" in only:
         np.savez_compressed(os.path.join(HERE, "train_frame_rmsprop.npz"), **run_frame_case(mm, "frame_rmsprop", "rmsprop", 1e-3))
+    for tag, optimizer in (("frame_amp_rmsprop", "rmsprop"), ("frame_amp_adam", "adam")):
+        if not only or tag in only:
+            np.savez_compressed(os.path.join(HERE, "train_%s.npz" % tag),
+                                **run_frame_case(mm, tag, optimizer, 1e-3, steps=12, amp=True))
 
 
 if __name__ == "__main__":

@@ -224,6 +224,9 @@ def test_ranked_lists_at_gallery_scale_match_stable_argsort():
     h = res.to_host()                                    # one packed device->host copy
     assert not h.rank0.is_cuda and torch.equal(h.rank0, res.rank0.cpu()) and torch.equal(h.topk_idx, res.topk_idx.cpu())
     assert torch.equal(h.topk_val, res.topk_val.cpu()) and torch.equal(h.metrics, res.metrics.cpu())
+    odd = idx.search(q16[:33], torch.from_numpy(gt[:33]).cuda().to(torch.int32), 5)   # odd Q, odd k: alignment of the packed copy
+    ho = odd.to_host()
+    assert torch.equal(ho.rank0, odd.rank0.cpu()) and torch.equal(ho.metrics, odd.metrics.cpu()) and torch.equal(ho.topk_idx, odd.topk_idx.cpu())
 
 
 def test_ranked_lists_threshold_path_equals_dense_path(monkeypatch):

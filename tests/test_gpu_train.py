@@ -209,6 +209,73 @@ def test_laff_ml_train_steps_match_reference():
     assert model._graph is not None
 
 
+@pytest.mark.parametrize("tag", ["frame_amp_rmsprop", "frame_amp_adam"])
+def test_laff_ml_float16_branch_follows_reference_scaler(tag):
+    """config.float16 = True (the shipped FrameLAFF setting, configs/FrameLaff_...:33): the reference's AMP branch
+    (model/model.py:970-989) over 12 steps of the unmodified reference.  Loss-scale trajectory and skipped steps
+    identical, losses within fp16 forward rounding, the clipped gradient has norm grad_clip / S and the direction of
+    the reference's, parameters follow the reference's trajectory; the last steps run as a replayed CUDA graph."""
+    g, sd, H, steps = load_case(tag)
+    D = int(g["meta"][1])
+    ff = str(g["frame_feat"])
+    c = cfg.frame_laff_config(D, H, SMALL)
+    c.dropout, c.float16 = 0.0, True
+    c.optimizer, c.lr, c.grad_clip = str(g["optimizer"]), float(g["lr"]), float(g["grad_clip"])
+    model = M.get_model("FrameLAFF", torch.device("cuda"), c)
+    load_numpy_state(model, sd)
+    model.train()
+    first = int(g["first_executed_step"])
+    lr, clip = float(g["lr"]), float(g["grad_clip"])
+    S = 65536.0
+    for s in range(steps):
+        vis_in, txt_in = step_inputs(g, s)
+        td = train_data(vis_in, txt_in)
+        td["vis_frame_feat_dict"] = {"mask_tensor": torch.from_numpy(g["step%d/mask" % s]), ff: torch.from_numpy(g["step%d/frames" % s])}
+        loss = float(model(td, epoch=0)["triplet_loss"])
+        assert abs(loss - g["losses"][s]) <= 1e-2 * abs(g["losses"][s]), (s, loss, g["losses"][s])
+        assert model.scaler.get_scale() == float(g["scales"][s]), (s, model.scaler.get_scale(), g["scales"][s])
+        assert model.scaler.last_step_skipped() == bool(g["skipped"][s]), s
+        if s == first:
+            grads = {k: p.grad.double().cpu().numpy() for k, p in model.named_parameters() if p.grad is not None}
+            n = np.sqrt(sum(float((v ** 2).sum()) for v in grads.values()))
+            assert abs(n - clip / S) <= 1e-3 * clip / S, (n, clip / S)
+            nref = np.sqrt(sum(float((g[k].astype(np.float64) ** 2).sum()) for k in g.files if k.startswith("grad_first/")))
+            for k, got in grads.items():
+                ref = g["grad_first/" + k].astype(np.float64).ravel()
+                if np.linalg.norm(ref) > 1e-3 * nref:
+                    cos = float(ref @ got.ravel() / (np.linalg.norm(ref) * np.linalg.norm(got)))
+                    assert cos >= 0.99, (k, cos)
+        S = model.scaler.get_scale()
+    assert model._graph is not None and model.scaler.skipped_steps() == int(g["skipped"].sum())
+    executed = int(steps - g["skipped"].sum())
+    for k, v in model.state_dict().items():
+        if "running_" in k or "num_batches" in k:
+            continue
+        ref = g["sd%d/%s" % (steps, k)]
+        err = np.abs(v.detach().cpu().numpy().reshape(ref.shape).astype(np.float64) - ref)
+        assert err.max() <= 11 * lr * executed, (k, err.max())
+        moved = np.abs(ref - g["sd0/" + k].reshape(ref.shape))
+        if moved.max() > 0 and err.size >= 1024:
+            assert np.median(err) <= 0.25 * max(np.median(moved), 1e-7), (k, np.median(err), np.median(moved))
+
+
+def test_optimizer_rebuild_keeps_state_and_step_count():
+    """A re-allocated gradient makes DeviceOptimizer rebuild its descriptor table: the running averages and the
+    device-side step count must survive (Adam's bias correction depends on it)."""
+    torch.manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(3000, device="cuda"))
+    q = torch.nn.Parameter(p.detach().clone())
+    a = DeviceOptimizer([p], kind="adam", lr=1e-2, eps=1e-8)
+    b = torch.optim.Adam([q], lr=1e-2, eps=1e-8)
+    for it in range(4):
+        gr = torch.randn(3000, device="cuda")
+        p.grad = gr.clone()          # a fresh tensor every step: the pointers change, the optimizer rebuilds
+        q.grad = gr.clone()
+        a.step()
+        b.step()
+        assert torch.allclose(p, q, atol=2e-6), (it, float((p - q).abs().max()))
+
+
 def test_dual_softmax_loss_kernel_vs_reference_autograd():
     """laff_dsl_forward_backward (loss.py:291-310) against the reference's value and autograd gradients."""
     from laff_b200 import loss as L

@@ -173,3 +173,17 @@ def test_collect_plan_keeps_its_statistical_margins():
             assert n_s == B.collect_sample and 1 <= r <= 2048
             assert mean * (1 - rel) >= k and mean * (1 + rel) <= B.collect_cap
     assert seen >= 10 and B.collect_plan(1000000, 2000) is not None and B.collect_plan(1000000, 500) is not None
+
+
+@pytest.mark.parametrize("Q,k", [(3, 1), (7, 5), (1, 10), (8, 4)])
+def test_search_result_unpack_any_parity_of_q(Q, k):
+    """SearchResult.to_host() packs [metrics (float64) | rank0 | score bits | indices] into one int32 buffer; the float64
+    view must stay 8-byte aligned for odd Q (a packed buffer with the metrics last failed there)."""
+    from laff_b200.retrieval import SearchResult
+    m = torch.arange(8, dtype=torch.float64) * 1.5
+    r = torch.arange(Q, dtype=torch.int32)
+    v = torch.rand(Q, k)
+    i = torch.randint(0, 100, (Q, k), dtype=torch.int32)
+    flat = torch.cat([m.view(torch.int32), r, v.reshape(-1).view(torch.int32), i.reshape(-1)])
+    h = SearchResult._unpack(flat, Q, (Q, k), 8)
+    assert torch.equal(h.metrics, m) and torch.equal(h.rank0, r) and torch.equal(h.topk_val, v) and torch.equal(h.topk_idx, i)

@@ -85,6 +85,49 @@ def test_oracle_laff_ml_train_steps_match_reference():
         check_params(sd, g, s, lr)
 
 
+@pytest.mark.parametrize("tag", ["frame_amp_rmsprop", "frame_amp_adam"])
+def test_oracle_float16_branch_follows_reference_scaler(tag):
+    """The reference's float16 branch (model/model.py:970-989: autocast + GradScaler, clip_grad_norm_ on the scaled
+    gradients) over 12 steps of the unmodified reference (torch's CPU autocast / GradScaler bound to the names the
+    reference imports, tests/golden/make_golden_train.py).  The restatement works on exact fp32 gradients and emulates
+    the fp16 overflow on the parameter gradients: the loss-scale trajectory and the skipped steps must be IDENTICAL;
+    losses agree to fp16 forward rounding; the clipped gradient of the first executed step has norm grad_clip / S."""
+    g, sd, H, steps = load_case(tag)
+    ff = str(g["frame_feat"])
+    state, scaler = {}, {"scale": 65536.0, "tracker": 0}
+    lr, clip, opt = float(g["lr"]), float(g["grad_clip"]), str(g["optimizer"])
+    first = int(g["first_executed_step"])
+    for s in range(steps):
+        vis_in, txt_in = step_inputs(g, s)
+        S = scaler["scale"]
+        loss, grads, total = O.laff_ml_train_step(sd, vis_in, g["step%d/frames" % s], ff, txt_in, state, H, opt, lr, clip, scaler=scaler)
+        assert scaler["scale"] == float(g["scales"][s]) and scaler["skipped"] == bool(g["skipped"][s]), (s, scaler, g["scales"][s])
+        assert abs(loss - g["losses"][s]) <= 1e-2 * abs(g["losses"][s]), (s, loss, g["losses"][s])
+        if s == first:
+            n = np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for v in grads.values()))
+            nref = np.sqrt(sum(float((g[k].astype(np.float64) ** 2).sum()) for k in g.files if k.startswith("grad_first/")))
+            assert abs(n - clip / S) <= 1e-3 * clip / S and abs(nref - clip / S) <= 2e-2 * clip / S, (n, nref, clip / S)
+            for k in grads:   # direction of the clipped gradient: fp16 autocast noise on the reference side
+                ref = g["grad_first/" + k].astype(np.float64).ravel()
+                got = grads[k].astype(np.float64).ravel()
+                if np.linalg.norm(ref) > 1e-3 * nref:
+                    cos = float(ref @ got / (np.linalg.norm(ref) * np.linalg.norm(got)))
+                    assert cos >= 0.99, (k, cos)
+    # parameters after 12 steps (9 executed): each executed step moves an element by at most ~lr / sqrt(1 - alpha)
+    executed = int(steps - g["skipped"].sum())
+    for k in sd:
+        ref = g["sd%d/%s" % (steps, k)]
+        err = np.abs(np.asarray(sd[k]).reshape(ref.shape).astype(np.float64) - ref)
+        if "running_" in k or "num_batches" in k:
+            continue
+        assert err.max() <= 11 * lr * executed, (k, err.max())
+        moved = np.abs(ref - g["sd0/" + k].reshape(ref.shape))
+        # the big tensors (FC weights) must follow the reference's trajectory; the 1 x d_h logit weights and biases see
+        # gradients at the level of the reference's fp16 rounding noise and only get the hard bound above
+        if moved.max() > 0 and err.size >= 1024:
+            assert np.median(err) <= 0.25 * max(np.median(moved), 1e-7), (k, np.median(err), np.median(moved))
+
+
 def gru_tokens_of(g, s):
     """Token ids of step s's captions under the test vocabulary (IndexVec: <start> words <end>, unknown -> <unk>)."""
     from laff_b200 import text as T
