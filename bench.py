@@ -174,19 +174,27 @@ def raw_gallery_features(lo, hi, dims, device):
 
 
 def query_features(Q, pinned: bool):
-    """Synthetic per-encoder text features of Q queries on the host (optionally pinned)."""
+    """Synthetic per-encoder text features of Q queries on the host (optionally pinned).  The bag-of-words feature is
+    what a tokenised caption is -- 8 vocabulary ids per query, CSR ('bow_csr': ops.SparseRows) -- not the dense
+    [Q, 3981] count matrix the reference expands it to (txt2vec.py:56-63): 32 bytes instead of 15.9 KB per query."""
     g = torch.Generator().manual_seed(1234 + 5)
-    from laff_b200 import synth
+    from laff_b200 import ops, synth
     feats = {"gru": torch.randn(Q, synth.DIMS["gru"], generator=g),
              "w2v": torch.randn(Q, synth.DIMS["w2v"], generator=g),
              "clip": torch.randn(Q, synth.DIMS["clip"], generator=g)}
-    bow = torch.zeros(Q, synth.DIMS["bow"])
     ids = torch.randint(0, synth.DIMS["bow"], (Q, 8), generator=g)
-    bow.scatter_add_(1, ids, torch.ones(Q, 8))
-    feats["bow"] = bow
+    feats["bow_csr"] = ops.SparseRows(torch.arange(Q + 1, dtype=torch.int64) * 8, ids.reshape(-1).to(torch.int32), synth.DIMS["bow"])
     if pinned:
         feats = {k: v.pin_memory() for k, v in feats.items()}
     return feats
+
+
+def feature_bytes(feats):
+    return sum(v.nbytes() if hasattr(v, "nbytes") and callable(v.nbytes) else v.numel() * v.element_size() for v in feats.values())
+
+
+def op_dtype(precision):
+    return torch.float16 if precision == "fp16" else torch.bfloat16
 
 
 def unit_rows(n, gen, device, dtype=torch.float32):
@@ -194,17 +202,17 @@ def unit_rows(n, gen, device, dtype=torch.float32):
     return (x / x.norm(dim=2, keepdim=True)).reshape(n, D).to(dtype)
 
 
-def build_gallery_shard(lo, hi, q_emb, gt, sigma, device):
+def build_gallery_shard(lo, hi, q_emb, gt, sigma, device, dtype=torch.float16):
     """Rows [lo, hi) of the synthetic gallery: unit-norm noise per head; row gt(i) = normalise(q_i + sigma * noise) so
     that R@1 is ~30 %.  Deterministic in the global row index, independent of the sharding."""
     n = hi - lo
-    g16 = torch.empty(n, D, dtype=torch.bfloat16, device=device)
+    g16 = torch.empty(n, D, dtype=dtype, device=device)
     block = 65536
     for s in range(lo - lo % block, hi, block):
         gen = torch.Generator(device=device).manual_seed(9000 + s // block)
         rows = unit_rows(block, gen, device)
         a, b = max(s, lo), min(s + block, hi)
-        g16[a - lo:b - lo] = rows[a - s:b - s].to(torch.bfloat16)
+        g16[a - lo:b - lo] = rows[a - s:b - s].to(dtype)
     own = ((gt >= lo) & (gt < hi)).nonzero().flatten()
     if own.numel():
         gen = torch.Generator(device=device).manual_seed(777)
@@ -212,7 +220,7 @@ def build_gallery_shard(lo, hi, q_emb, gt, sigma, device):
         planted = q_emb[own].float() + sigma * noise
         planted = planted.view(-1, HEADS, HEAD_DIM)
         planted = (planted / planted.norm(dim=2, keepdim=True)).reshape(-1, D)
-        g16[gt[own] - lo] = planted.to(torch.bfloat16)
+        g16[gt[own] - lo] = planted.to(dtype)
     return g16
 
 
@@ -270,6 +278,61 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+@torch.no_grad()
+def parity_block(txt_net, index, feats_dev, gt_dev, res, n, world, precision):
+    """T2 parity of the benchmarked precision on the benchmark's own inputs: the first n queries are fused and ranked
+    again with fp32-grade arithmetic -- 3-term bf16-split operands ('bf16x3') in the projections AND in the similarity
+    sweep, the path whose ranks are identical to the fp32 reference on the reference-trained fixture
+    (tests/test_gpu_trained.py) -- against the same 16-bit gallery (its values are exactly representable in the
+    split).  Reports how many ground-truth ranks / top-10 lists the 16-bit step moved and the recall deltas."""
+    import torch.distributed as dist
+    from laff_b200 import ops
+    n = min(n, gt_dev.numel())
+    part = {k: v[:n] for k, v in feats_dev.items()}
+    t32, _ = txt_net.encode(part, precision="bf16x3")
+    q3 = ops.split3_16(t32.reshape(n, -1), 0)
+    gt = gt_dev[:n].to(torch.int32)
+    lo, hi, H = index.lo, index.hi, index.heads
+    owned = (gt >= lo) & (gt < hi)
+    rows = index.g16[torch.where(owned, gt - lo, torch.zeros_like(gt)).long()].float() if hi > lo else torch.zeros(n, D, device=gt.device)
+    sgt = ops.sim_gt_scores(q3, ops.split3_16(rows, 1), torch.arange(n, device=gt.device, dtype=torch.int32))
+    sgt = torch.where(owned, sgt, torch.zeros_like(sgt))
+    if world > 1:
+        dist.all_reduce(sgt)
+    count = torch.zeros(n, dtype=torch.int32, device=gt.device)
+    vals, idxs = [], []
+    for s in range(0, hi - lo, 131072):
+        e = min(hi - lo, s + 131072)
+        c, tv, ti = ops.sim_rank_topk(q3, ops.split3_16(index.g16[s:e].float(), 1), sgt, gt, TOPK, scale=1.0 / H, col_offset=lo + s)
+        count += c
+        vals.append(tv)
+        idxs.append(ti)
+    if vals:
+        tv, ti = ops.topk_merge(torch.stack(vals), torch.stack(idxs), TOPK)
+    else:
+        tv = torch.full((n, TOPK), float("-inf"), device=gt.device)
+        ti = torch.full((n, TOPK), -1, dtype=torch.int32, device=gt.device)
+    if world > 1:
+        dist.all_reduce(count)
+        av = [torch.empty_like(tv) for _ in range(world)]
+        ai = [torch.empty_like(ti) for _ in range(world)]
+        dist.all_gather(av, tv.contiguous())
+        dist.all_gather(ai, ti.contiguous())
+        tv, ti = ops.topk_merge(torch.stack(av), torch.stack(ai), TOPK)
+    ref_rank, got_rank = count.cpu(), res.rank0[:n].cpu()
+    m_ref, m_got = ops.rank_metrics(count).cpu().tolist(), ops.rank_metrics(res.rank0[:n].contiguous()).cpu().tolist()
+    moved = int((ref_rank != got_rank).sum())
+    lists = int((ti.cpu() != res.topk_idx[:n].cpu()).any(1).sum())
+    return {"what": "first %d queries re-fused and re-ranked with fp32-grade arithmetic (bf16x3: 3-term split operands in the "
+                    "projections and the sweep) against the same gallery; counts of queries the %s step answers differently"
+                    % (n, precision),
+            "queries": n, "ranks_moved": moved, "ranks_moved_frac": moved / max(1, n),
+            "max_rank_shift": int((ref_rank - got_rank).abs().max()) if n else 0, "top10_lists_differ": lists,
+            "max_abs_score_diff": float((tv - res.topk_val[:n]).abs().max()),
+            "d_r1": m_got[0] - m_ref[0], "d_r5": m_got[1] - m_ref[1], "d_r10": m_got[2] - m_ref[2], "d_medr": m_got[3] - m_ref[3],
+            "recall_ref": {"r1": m_ref[0], "r5": m_ref[1], "r10": m_ref[2], "medr": m_ref[3]}}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from laff_b200 import _capi, ops, synth
@@ -287,11 +350,12 @@ def run_ours(args, rank, world, local_rank):
     gt = ((torch.arange(Q, dtype=torch.int64) * 97) % V)
     gt_host = gt.to(torch.int32).pin_memory()
     gt_dev = gt.to(dev)
+    dt16 = op_dtype(args.precision)
     with torch.no_grad():
-        _, q16 = txt_net.encode(feats_dev, out16_dtype=torch.bfloat16)
+        _, q16 = txt_net.encode(feats_dev, out16_dtype=dt16, precision=args.precision)
     sigma = synth.sigma_for_recall(V, D)
     lo, hi = shard_bounds(V, world, rank)
-    g16 = build_gallery_shard(lo, hi, q16.reshape(Q, D), gt_dev, sigma, dev)
+    g16 = build_gallery_shard(lo, hi, q16.reshape(Q, D), gt_dev, sigma, dev, dt16)
     index = GalleryIndex(g16, V, HEADS, rank, world)
     retr = Retriever(txt_net, index)
     torch.cuda.synchronize()
@@ -342,6 +406,7 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
 
     metrics = res.metrics.cpu().tolist()
+    parity = parity_block(txt_net, index, feats_dev, gt_dev, res, args.parity_queries, world, args.precision) if args.parity_queries > 0 else None
 
     # ---- mode B: the gallery shard is re-fused from raw fp32 features inside the timed region -------
     modeb_ms = modeb_fuse_ms = 0.0
@@ -354,7 +419,7 @@ def run_ours(args, rank, world, local_rank):
             if timers is not None:
                 a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
                 a.record()
-            idx_b = GalleryIndex.from_features(vis_net, raw, V, rank, world)
+            idx_b = GalleryIndex.from_features(vis_net, raw, V, rank, world, out16_dtype=dt16)
             if timers is not None:
                 b.record()
                 timers.append((a, b))
@@ -389,13 +454,13 @@ def run_ours(args, rank, world, local_rank):
     n_local = hi - lo
     achieved = Q * n_local * FLOP_PER_PAIR / (sweep_avg_ms * 1e-3) / 1e12
     # summed over the ranks: every rank copies its 1/W slice of the query features and the whole ground-truth vector
-    h2d = sum(v.numel() * v.element_size() for v in feats_host.values()) + world * gt_host.numel() * 4
+    h2d = feature_bytes(feats_host) + world * gt_host.numel() * 4
     d2h = world * (Q * 4 + Q * TOPK * 8 + 8 * 8)   # every rank reads the (replicated) ranks, top-k lists and metrics back
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "C5: %d queries (gru1024+bow3981+w2v500 FC -> 4096, CLIP512 tiled, LAFF pooling, 8x512) "
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "C5: %d queries (gru1024+w2v500 FC -> 4096, bow3981 as CSR token ids -> gather-sum FC, CLIP512 tiled, LAFF pooling, 8x512) "
                                "ranked against a %d-video gallery of fused embeddings resident in HBM: similarity "
                                "sweep + exact rank + top-%d + R@K/MedR" % (Q, V, TOPK),
                    "queries": Q, "gallery": V, "gallery_per_gpu": n_local, "topk": TOPK, "sharding": "gallery rows / %d" % world,
@@ -409,14 +474,17 @@ def run_ours(args, rank, world, local_rank):
                        "gallery_fusion_tflops": n_local * 2.0 * D * (768 + 2048 + 2048) / (modeb_fuse_ms * 1e-3) / 1e12}},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
+        "parity": parity,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel<2, EpiRank<16>> (similarity sweep + rank + top-k; one sweep = one "
                                                   "laff_sim_rank_topk call = %d back-to-back launches of this kernel, timed as a whole)"
                                                   % sweep_launches(Q, n_local),
                      "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tensor_tflops"],
-                     "peak_source": pk["source"] + " (bf16 dense sustained)",
+                     "peak_source": pk["source"] + " (bf16 dense sustained; fp16 and bf16 operands share the kind::f16 MMA rate)",
                      "flop_per_launch": Q * n_local * FLOP_PER_PAIR, "avg_launch_ms": sweep_avg_ms,
-                     "traffic": recorded_traffic() if world == 1 and V == V_FULL and Q == Q_FULL else None},
+                     "traffic": recorded_traffic() if world == 1 and V == V_FULL and Q == Q_FULL else None,
+                     "traffic_source": "recorded: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
+                                       "sweep (profiles/roofline_traffic.json), not measured in this run"},
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -443,6 +511,11 @@ def main():
     ap.add_argument("--videos", type=int, default=V_FULL)
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
+                    help="16-bit operand type of the projections and the similarity sweep (same MMA rate; fp16 moves ~7x fewer "
+                         "ranks against the fp32 reference, tests/test_gpu_trained.py)")
+    ap.add_argument("--parity-queries", type=int, default=256,
+                    help="queries of the parity block: re-ranked with fp32-grade (bf16x3) fusion + sweep and compared (0 = skip)")
     ap.add_argument("--mode-b-steps", type=int, default=2, help="timed steps of the mode-B leg (0 = skip it)")
     ap.add_argument("--e2e-chunks", type=int, default=0,
                     help="query pieces whose H2D copies overlap the sweep in the e2e leg (0 = by world size: 4 / 2 / 1 / 1 "

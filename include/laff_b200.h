@@ -192,6 +192,12 @@ int laff_label_metrics(const uint8_t* label, int Q, int V, long long ld, int32_t
  * N2  Text front-end after tokenisation (model/model.py:322-434, txt2vec.py:49-109).  Token lists are CSR:
  *     ids[offsets[i] .. offsets[i+1]) belong to caption i; ids outside the table are skipped.
  *   laff_bow_counts   BowVec._encoding: out[i, id] += 1 (rows are zeroed first).  out fp32 [rows, ndims].
+ *   laff_bow_project  BoWTxtEncoder + its TransformNet without the dense count vector (model/model.py:399-417 then
+ *       :257-276; txt2vec.py:56-63): y[i, :] = BN(act(row_scale[i] * sum_t wt[id_t, :] + bias)), wt = the FC weight
+ *       transposed, fp32 [vocab, D]; a repeated token adds its row twice (its count).  Token t of caption i is
+ *       tok_ids[tok_offsets[i] - id_base + ...] (id_base lets a caller pass a slice of the id array with the
+ *       offsets of the whole batch).  row_scale (optional): 1 / norm of the count vector (Txt2Vec.do_norm).
+ *       The result enters laff_fuse_forward as a tiled feature with in_dim = D and no BatchNorm.
  *   laff_gather_mean  W2Vec._encoding: mean of table rows, summed in float64 in list order, rounded to fp32 once
  *                     (numpy's np.array(vectors).mean(axis=0) on float64); no valid id -> zeros.  The caller passes the
  *                     ids de-duplicated and sorted, as BigFile.read returns them (bigfile.py:204-211).
@@ -216,6 +222,9 @@ long long laff_tokenize_lookup(const char* text_blob, const long long* cap_offse
                                const laff_vocab* stopwords, int mode, int unk_id, int start_id, int end_id,
                                long long* out_offsets, int32_t* out_ids, long long capacity);
 
+int laff_bow_project(const long long* tok_offsets, const int32_t* tok_ids, long long id_base, int rows, int vocab,
+                     const float* wt, long long ld_wt, int D, const float* bias, int activation, const float* bn_scale,
+                     const float* bn_shift, const float* row_scale, float* y, long long ld_y, void* stream);
 int laff_bow_counts(const long long* tok_offsets, const int32_t* tok_ids, int rows, int ndims, float* out, long long ld,
                     void* stream);
 int laff_gather_mean(const float* table, long long ld_table, long long n_table, const long long* offsets,

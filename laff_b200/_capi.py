@@ -117,6 +117,7 @@ SIGNATURES = {
     "laff_vocab_create": (_vp, [_vp, _vp, _vp, _i]),
     "laff_vocab_destroy": (None, [_vp]),
     "laff_tokenize_lookup": (_ll, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _ll]),
+    "laff_bow_project": (_i, [_vp, _vp, _ll, _i, _i, _vp, _ll, _i, _vp, _i, _vp, _vp, _vp, _vp, _ll, _vp]),
     "laff_bow_counts": (_i, [_vp, _vp, _i, _i, _vp, _ll, _vp]),
     "laff_gather_mean": (_i, [_vp, _ll, _ll, _vp, _vp, _i, _i, _vp, _ll, _vp]),
     "laff_gather_rows": (_i, [_vp, _ll, _ll, _vp, _ll, _i, _vp, _ll, _vp]),

@@ -23,9 +23,11 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// fp16 operands (the default: 8x finer rounding than bf16 at the same MMA rate) have a narrow range: a raw
+// feature beyond +-65504 saturates instead of turning into an inf that would poison a whole output row (NaN stays NaN).
 __device__ __forceinline__ uint16_t to16(float v, int dtype) {
   if (dtype == LAFF_BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
-  return __half_as_ushort(__float2half_rn(v));
+  return __half_as_ushort(__float2half_rn(v != v ? v : fminf(fmaxf(v, -65504.f), 65504.f)));
 }
 __device__ __forceinline__ float from16(uint16_t b, int dtype) {
   if (dtype == LAFF_BF16) return __bfloat162float(__ushort_as_bfloat16(b));

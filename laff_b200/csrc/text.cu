@@ -26,6 +26,65 @@ __global__ void bow_counts_kernel(const long long* __restrict__ offsets, const i
   }
 }
 
+// Sparse BoW projection (BoWTxtEncoder + its TransformNet, model/model.py:399-417 then :257-276): the reference builds the
+// dense count vector c (txt2vec.py:56-63: vec[idx] += 1 per in-vocabulary token, ~8 non-zeros of 3981) and multiplies it
+// by W [D, vocab]; here y[r, :] = BN(act(row_scale[r] * sum_t Wt[id_t, :] + b)) is a gather-sum over the rows of the
+// transposed weight Wt [vocab, D] fp32 -- a repeated token is simply added twice, which IS its count.  One block per
+// caption, 4 consecutive columns per thread per pass (16-byte loads of 16 KB rows: coalesced); tokens in caption order,
+// fp32 accumulation (the dense tensor-core path rounds W to 16 bits; this one does not).  HBM/L2-bound:
+// n_tokens * D * 4 bytes read + D * 4 written per caption; Wt (65 MB at D = 4096, vocab = 3981) stays L2-resident.
+__device__ __forceinline__ float bow_act(float z, int act) {
+  switch (act) {
+    case LAFF_ACT_TANH: {   // same formulation as EpiProject (fuse.cu): 1 - 2 / (exp(2z) + 1), |err| < 3e-7
+      const float e = __expf(2.0f * z);
+      return 1.0f - __fdividef(2.0f, e + 1.0f);
+    }
+    case LAFF_ACT_RELU: return fmaxf(z, 0.f);
+    case LAFF_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-z));
+    default: return z;
+  }
+}
+
+__global__ void __launch_bounds__(256) bow_project_kernel(const long long* __restrict__ offsets, const int32_t* __restrict__ ids,
+                                                          long long id_base, int vocab, const float* __restrict__ wt, long long ld_wt,
+                                                          int D, const float* __restrict__ bias, int act,
+                                                          const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                                                          const float* __restrict__ row_scale, float* __restrict__ y, long long ld_y) {
+  const long long row = blockIdx.x;
+  const long long a = offsets[row] - id_base, b = offsets[row + 1] - id_base;
+  __shared__ int s_ids[256];
+  const float rs = row_scale ? row_scale[row] : 1.0f;
+  for (int c0 = 0; c0 < D; c0 += 256 * 4) {
+    const int c = c0 + threadIdx.x * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long t0 = a; t0 < b; t0 += 256) {
+      __syncthreads();
+      if (t0 + threadIdx.x < b) s_ids[threadIdx.x] = ids[t0 + threadIdx.x];
+      __syncthreads();
+      const int n = b - t0 < 256 ? static_cast<int>(b - t0) : 256;
+      if (c < D) {
+        for (int t = 0; t < n; ++t) {
+          const int id = s_ids[t];
+          if (id < 0 || id >= vocab) continue;   // out-of-vocabulary marker: contributes nothing (vocab.find() < 0)
+          const float4 w = __ldg(reinterpret_cast<const float4*>(wt + static_cast<long long>(id) * ld_wt + c));
+          acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+        }
+      }
+    }
+    if (c < D) {
+      float v[4] = {acc.x * rs, acc.y * rs, acc.z * rs, acc.w * rs};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float z = v[j] + (bias ? __ldg(bias + c + j) : 0.f);
+        z = bow_act(z, act);
+        if (bn_scale) z = fmaf(z, __ldg(bn_scale + c + j), __ldg(bn_shift + c + j));
+        v[j] = z;
+      }
+      *reinterpret_cast<float4*>(y + row * ld_y + c) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
 __global__ void gather_mean_kernel(const float* __restrict__ table, long long ld_t, long long n_table,
                                    const long long* __restrict__ offsets, const int32_t* __restrict__ ids, int dim,
                                    float* __restrict__ out, long long ld) {
@@ -175,6 +234,26 @@ extern "C" int laff_bow_counts(const long long* tok_offsets, const int32_t* tok_
   if (rc) return rc;
   if (rows == 0) return LAFF_OK;
   bow_counts_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(tok_offsets, tok_ids, ndims, out, ld);
+  count_launch();
+  LAFF_CUDA(cudaGetLastError());
+  return LAFF_OK;
+}
+
+extern "C" int laff_bow_project(const long long* tok_offsets, const int32_t* tok_ids, long long id_base, int rows, int vocab,
+                                const float* wt, long long ld_wt, int D, const float* bias, int activation,
+                                const float* bn_scale, const float* bn_shift, const float* row_scale, float* y, long long ld_y,
+                                void* stream) {
+  if (rows == 0) return LAFF_OK;
+  LAFF_REQUIRE(tok_offsets && wt && y && rows > 0 && vocab > 0 && D > 0 && D % 4 == 0 && ld_wt >= D && ld_wt % 4 == 0 &&
+                   ld_y >= D && ld_y % 4 == 0 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+               LAFF_EINVAL, "laff_bow_project: bad arguments (D and the row pitches must be multiples of 4, 16-byte aligned)");
+  LAFF_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), LAFF_EINVAL, "laff_bow_project: bn_scale / bn_shift mismatch");
+  LAFF_REQUIRE(activation >= LAFF_ACT_NONE && activation <= LAFF_ACT_SIGMOID, LAFF_EINVAL, "laff_bow_project: activation %d", activation);
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  bow_project_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(tok_offsets, tok_ids, id_base, vocab, wt, ld_wt, D, bias,
+                                                                          activation, bn_scale, bn_shift, row_scale, y, ld_y);
   count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;

@@ -97,11 +97,33 @@ class TransformNet(nn.Module):
             if self.bn1 is not None:
                 c["bn_scale"], c["bn_shift"] = ops.bn_fold(self.bn1.weight, self.bn1.bias, self.bn1.running_mean,
                                                            self.bn1.running_var, self.bn1.eps)
+            if "sparse" in self._cache:
+                c["sparse"] = self._cache["sparse"]
             self._cache = c
         return self._cache
 
+    def prepared_sparse(self):
+        """W^T as fp32 [d_in, D] for the gather-sum projection of a sparse BoW feature (rebuilt when W changes)."""
+        key = ("sparse", self._version())
+        c = self._cache.get("sparse")
+        if c is None or c["key"] != key:
+            c = {"key": key, "wt": self.fc1.weight.detach().float().t().contiguous(),
+                 "bias": self.fc1.bias.detach().float().contiguous()}
+            if self.bn1 is not None:
+                c["bn_scale"], c["bn_shift"] = ops.bn_fold(self.bn1.weight, self.bn1.bias, self.bn1.running_mean,
+                                                           self.bn1.running_var, self.bn1.eps)
+            self._cache["sparse"] = c
+        return c
+
+    def project_sparse(self, x: "ops.SparseRows", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """y = BN(act(counts W^T + b)) of a CSR BoW batch without the dense count matrix (ops.bow_project)."""
+        c = self.prepared_sparse()
+        return ops.bow_project(x, c["wt"], c["bias"], self.activation_name, c.get("bn_scale"), c.get("bn_shift"), out=out)
+
     def project(self, x: torch.Tensor, precision: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """y = BN(act(x W^T + b)) for an fc feature; x fp32 [rows, d_in] on the device."""
+        if isinstance(x, ops.SparseRows):
+            return self.project_sparse(x, out=out)
         c = self.prepared(precision)
         if precision == "bf16x3":
             x16 = ops.split3_16(x, 0, torch.bfloat16)
@@ -261,7 +283,7 @@ def _fuse_single_kernel(features, attention, precision, out16_dtype, want_f32=Tr
     dev = features[0][0].device
     D = attention.multi_heads * attention.dim_per_head
     w, b = attention.head_params()
-    prepared = [tn.prepared(precision) for _, tn in features]
+    prepared = [None if isinstance(x, ops.SparseRows) else tn.prepared(precision) for x, tn in features]
     out = torch.empty((B, D), dtype=torch.float32, device=dev) if want_f32 else None
     out16 = torch.empty((B, D), dtype=ops.torch_dtype(out16_dtype), device=dev) if out16_dtype is not None else None
     chunk = min(max(B, 1), _FUSED_ROW_CHUNK)
@@ -271,7 +293,10 @@ def _fuse_single_kernel(features, attention, precision, out16_dtype, want_f32=Tr
         fc, tiled = [], []
         for i, ((x, tn), c) in enumerate(zip(features, prepared)):
             xs = x[s:e]
-            if tn.fc1 is not None:
+            if isinstance(xs, ops.SparseRows):
+                # sparse BoW: gather-sum projection (bias, activation, BN applied), then a "tiled" feature of full width
+                tiled.append({"x": tn.project_sparse(xs), "bn_scale": None, "bn_shift": None})
+            elif tn.fc1 is not None:
                 if precision == "bf16x3":
                     x16 = ops.split3_16(xs, 0, torch.bfloat16)
                 else:
@@ -291,7 +316,7 @@ def _fuse_single_kernel(features, attention, precision, out16_dtype, want_f32=Tr
 def _single_kernel_ok(features, attention, want_att) -> bool:
     if not _SINGLE_KERNEL or want_att or attention.with_ave or attention.mul or attention.dim_per_head != 512:
         return False
-    n_fc = sum(1 for _, tn in features if tn.fc1 is not None)
+    n_fc = sum(1 for x, tn in features if tn.fc1 is not None and not isinstance(x, ops.SparseRows))
     n_tiled = len(features) - n_fc
     if not (1 <= n_fc <= 4 and n_tiled <= 2):
         return False
@@ -461,7 +486,11 @@ class BoWTxtEncoder(TxtEncoder):
         super().__init__(opt)
         self.t2v_bow = opt.t2v_bow
 
-    def forward(self, caption_feat_dict, task3=False):
+    def forward(self, caption_feat_dict, task3=False, sparse=False):
+        """Dense count vectors like the reference; sparse=True (the eval-mode fusion path asks for it) keeps the CSR
+        token ids, which the projection consumes directly (ops.bow_project) -- no [B, |vocab|] matrix is built."""
+        if sparse:
+            return {"text_features": self.t2v_bow.encode_sparse(caption_feat_dict["caption"])}
         return {"text_features": self.t2v_bow.encode_batch(caption_feat_dict["caption"])}
 
 
@@ -539,12 +568,24 @@ class MultiScaleTxtEncoderAttention(nn.Module):
             self.transform_layer.add_module(name + "_transform", tn)
         self.attention_layer = get_attention_layer(opt.txt_attention, D, self.txt_encoder_num, opt)
 
-    def _feature(self, caption_feat_dict, enc):
+    def _feature(self, caption_feat_dict, enc, sparse_ok=False):
+        """The feature of one encoder: precomputed under one of its keys, or from the caption strings.  The BoW feature
+        may arrive sparse ('bow_csr': ops.SparseRows or an (offsets, ids) pair); sparse_ok says the caller can consume
+        it that way, otherwise it is expanded to the dense count matrix the reference builds (txt2vec.py:56-63)."""
+        if enc == "bow_encoder" and "bow_csr" in caption_feat_dict:
+            x = caption_feat_dict["bow_csr"]
+            if not isinstance(x, ops.SparseRows):
+                x = ops.SparseRows(torch.as_tensor(x[0]), torch.as_tensor(x[1]), self.space_dict["bow_encoder"])
+            if x.ndims != self.space_dict["bow_encoder"]:
+                raise ops.LaffError("bow_csr: vocabulary size %d, the model expects %d" % (x.ndims, self.space_dict["bow_encoder"]))
+            return x if sparse_ok else x.to(_cuda_device(self.attention_layer.layer_norm.weight.device)).dense()
         for key in dict(_TXT_ENCODERS)[enc]:
             if key in caption_feat_dict:
                 return caption_feat_dict[key]
         front = dict(self.encoder.named_children()).get(enc)
         if front is not None and "caption" in caption_feat_dict:
+            if enc == "bow_encoder" and sparse_ok:
+                return front(caption_feat_dict, sparse=True)["text_features"]
             return front(caption_feat_dict)["text_features"]
         raise KeyError("caption_feat_dict has no feature for %s (expected one of %s)" % (enc, dict(_TXT_ENCODERS)[enc]))
 
@@ -554,7 +595,7 @@ class MultiScaleTxtEncoderAttention(nn.Module):
         if self.training:
             raise NotImplementedError("train-mode forward of the fusion net is SURVEY §8f N4; call .eval()")
         mods = dict(self.transform_layer.named_children())
-        feats = [(self._feature(caption_feat_dict, n).to(dev, non_blocking=True).float(), mods[n + "_transform"])
+        feats = [(self._feature(caption_feat_dict, n, sparse_ok=True).to(dev, non_blocking=True).float(), mods[n + "_transform"])
                  for n in self.encoder_name_list]
         return _fuse(feats, self.attention_layer, dev, precision, out16_dtype, want_att, want_f32)
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import _capi
@@ -471,6 +472,110 @@ def frame_pool(frames: torch.Tensor, att_weight: torch.Tensor, att_bias: float, 
 def _csr(offsets: torch.Tensor, ids: torch.Tensor):
     _need_cuda(offsets, ids)
     return offsets.to(torch.int64).contiguous(), ids.to(torch.int32).contiguous()
+
+
+class SparseRows:
+    """A batch of bag-of-words rows kept sparse: CSR token ids (a token that occurs twice is listed twice -- its count)
+    instead of the dense [rows, ndims] count matrix of BowVec._encoding (txt2vec.py:56-63; ~8 non-zeros of 3981).
+
+    offsets int64 [rows + 1], ids int32 [n_tokens] (host or device tensors), ndims = vocabulary size; token t of row i
+    is ids[offsets[i] - base + ...].  Quacks like the dense tensor where the query path needs it: `.shape`, `.is_cuda`,
+    row slicing, `.to(device)`, `.pin_memory()`, `.record_stream()`; `.dense()` expands on the device (the training
+    step and the bf16x3 / attention-weight paths still take the dense matrix).  Host-side slices carry only their own
+    ids, so a rank (or an H2D chunk) copies 4 bytes per token instead of 4 * ndims bytes per caption."""
+
+    def __init__(self, offsets: torch.Tensor, ids: torch.Tensor, ndims: int, base: int = 0, row_scale: Optional[torch.Tensor] = None):
+        self.offsets, self.ids, self.ndims, self.base, self.row_scale = offsets, ids, int(ndims), int(base), row_scale
+
+    @classmethod
+    def from_lists(cls, lists, ndims: int) -> "SparseRows":
+        off = np.zeros(len(lists) + 1, dtype=np.int64)
+        np.cumsum([len(l) for l in lists], out=off[1:])
+        ids = np.fromiter((i for l in lists for i in l), dtype=np.int32, count=int(off[-1]))
+        return cls(torch.from_numpy(off), torch.from_numpy(ids), ndims)
+
+    @classmethod
+    def from_dense(cls, counts: torch.Tensor) -> "SparseRows":
+        """Exact CSR form of a dense count matrix with non-negative integer entries (host tensor)."""
+        c = counts.detach().cpu()
+        if not bool(((c >= 0) & (c == c.round())).all()):
+            raise LaffError("SparseRows.from_dense: a BoW count matrix has non-negative integer entries")
+        r, col = torch.nonzero(c, as_tuple=True)
+        rep = c[r, col].to(torch.int64)
+        ids = torch.repeat_interleave(col, rep).to(torch.int32)
+        per_row = torch.zeros(c.shape[0], dtype=torch.int64).index_add_(0, r, rep)
+        off = torch.zeros(c.shape[0] + 1, dtype=torch.int64)
+        off[1:] = torch.cumsum(per_row, 0)
+        return cls(off, ids, c.shape[1])
+
+    @property
+    def shape(self):
+        return (self.offsets.numel() - 1, self.ndims)
+
+    @property
+    def is_cuda(self):
+        return self.offsets.is_cuda
+
+    @property
+    def device(self):
+        return self.offsets.device
+
+    def nbytes(self) -> int:
+        return self.offsets.numel() * 8 + self.ids.numel() * 4 + (0 if self.row_scale is None else self.row_scale.numel() * 4)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, key) -> "SparseRows":
+        if not isinstance(key, slice) or key.step not in (None, 1):
+            raise LaffError("SparseRows supports contiguous row slices only")
+        lo, hi, _ = key.indices(self.shape[0])
+        hi = max(hi, lo)
+        off = self.offsets[lo:hi + 1]
+        rs = None if self.row_scale is None else self.row_scale[lo:hi]
+        if self.offsets.is_cuda:                       # no host read: keep the id array whole
+            return SparseRows(off, self.ids, self.ndims, self.base, rs)
+        a, b = int(off[0]) - self.base, int(off[-1]) - self.base
+        return SparseRows(off, self.ids[a:b], self.ndims, self.base + a, rs)
+
+    def to(self, device, non_blocking: bool = False) -> "SparseRows":
+        return SparseRows(self.offsets.to(device, non_blocking=non_blocking), self.ids.to(device, non_blocking=non_blocking),
+                          self.ndims, self.base, None if self.row_scale is None else self.row_scale.to(device, non_blocking=non_blocking))
+
+    def pin_memory(self) -> "SparseRows":
+        return SparseRows(self.offsets.contiguous().pin_memory(), self.ids.contiguous().pin_memory(), self.ndims, self.base,
+                          None if self.row_scale is None else self.row_scale.pin_memory())
+
+    def float(self) -> "SparseRows":
+        return self
+
+    def record_stream(self, stream) -> None:
+        for t in (self.offsets, self.ids, self.row_scale):
+            if t is not None and t.is_cuda:
+                t.record_stream(stream)
+
+    def dense(self) -> torch.Tensor:
+        _need_cuda(self.offsets)
+        off = (self.offsets - self.base) if self.base else self.offsets
+        out = bow_counts(off, self.ids, self.ndims)
+        return out if self.row_scale is None else out * self.row_scale[:, None]
+
+
+def bow_project(x: "SparseRows", wt: torch.Tensor, bias: Optional[torch.Tensor], activation, bn_scale=None, bn_shift=None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = BN(act(counts @ W^T + b)) of a sparse BoW batch as a gather-sum over the rows of wt = W^T (fp32 [ndims, D])
+    (laff_bow_project; the reference's BoWTxtEncoder + TransformNet, model/model.py:399-417, :257-276)."""
+    _need_cuda(x.offsets, x.ids, wt)
+    if wt.dtype != torch.float32 or wt.dim() != 2 or wt.stride(1) != 1 or wt.shape[0] != x.ndims:
+        raise LaffError("bow_project: wt must be fp32 [ndims = %d, D] row-major, got %s" % (x.ndims, tuple(wt.shape)))
+    rows, D = x.shape[0], wt.shape[1]
+    offsets, ids = _csr(x.offsets, x.ids)
+    if out is None:
+        out = torch.empty((rows, D), dtype=torch.float32, device=wt.device)
+    act = activation if isinstance(activation, int) else _capi.ACT[activation]
+    _capi.call("laff_bow_project", _ptr(offsets), _ptr(ids), x.base, rows, x.ndims, _ptr(wt), wt.stride(0), D, _ptr(bias), act,
+               _ptr(bn_scale), _ptr(bn_shift), _ptr(x.row_scale), _ptr(out), out.stride(0), _stream(wt))
+    return out
 
 
 def bow_counts(offsets: torch.Tensor, ids: torch.Tensor, ndims: int) -> torch.Tensor:

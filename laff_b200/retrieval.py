@@ -151,15 +151,19 @@ class GalleryIndex:
     @classmethod
     @torch.no_grad()
     def from_features(cls, vis_net, vis_input, total: int, rank: int = 0, world_size: int = 1, group=None,
-                      backend=None, frame_input=None, out16_dtype=torch.bfloat16):
+                      backend=None, frame_input=None, out16_dtype=None):
         """Fuse this rank's shard of raw video features into the resident 16-bit gallery (the reference's
         `vis_net(vis_input)` loop over the gallery loader, model/model.py:1036-1049, data-parallel over the shard; no
         communication).  vis_input: dict name -> [rows of this shard, d_l] tensors (host or device); frame_input: the
-        LAFF-ml frame-feature dict."""
+        LAFF-ml frame-feature dict; out16_dtype: torch.float16 / torch.bfloat16 (default: the type of the current
+        precision, loss.get_precision()) -- the projection operands follow the same type."""
+        from . import loss as _loss
+        out16_dtype = out16_dtype or _loss.operand_dtype()
+        precision = "fp16" if out16_dtype == torch.float16 else "bf16"
         if frame_input is not None:
-            _, g16 = vis_net.encode(vis_input, frame_input, out16_dtype=out16_dtype, want_f32=False)
+            _, g16 = vis_net.encode(vis_input, frame_input, out16_dtype=out16_dtype, precision=precision, want_f32=False)
         else:
-            _, g16 = vis_net.encode(vis_input, out16_dtype=out16_dtype, want_f32=False)
+            _, g16 = vis_net.encode(vis_input, out16_dtype=out16_dtype, precision=precision, want_f32=False)
         heads = g16.shape[1]
         g16 = g16.reshape(g16.shape[0], -1)
         return cls(g16, total, heads, rank, world_size, group, backend)
@@ -241,10 +245,12 @@ class Retriever:
     """The whole query path behind one call: fuse the text features of a batch of queries (txt_net, F1-F6), then rank
     them against the resident gallery shard(s) (S2 + E2 + E3).  This is the public API bench.py's e2e leg times."""
 
-    def __init__(self, txt_net, index: GalleryIndex, out16_dtype=torch.bfloat16):
+    def __init__(self, txt_net, index: GalleryIndex, out16_dtype=None):
+        """Queries are fused in the gallery's operand type (fp16 or bf16), projection operands included."""
         self.txt_net = txt_net
         self.index = index
-        self.out16_dtype = out16_dtype
+        self.out16_dtype = out16_dtype or index.g16.dtype
+        self.precision = "fp16" if self.out16_dtype == torch.float16 else "bf16"
 
     def query_slice(self, Q: int):
         """Rows [lo, hi) of a Q-query batch that this rank fuses, and the per-rank slot size of the all-gather."""
@@ -261,7 +267,7 @@ class Retriever:
         idx = self.index
         W = idx.world_size
         if W == 1:
-            _, q16 = self.txt_net.encode(caption_feat_dict, out16_dtype=self.out16_dtype)
+            _, q16 = self.txt_net.encode(caption_feat_dict, out16_dtype=self.out16_dtype, precision=self.precision)
             return q16.reshape(q16.shape[0], -1)
         if total is None:
             Q = next(iter(caption_feat_dict.values())).shape[0]
@@ -274,9 +280,9 @@ class Retriever:
             if next(iter(part.values())).shape[0] != hi - lo:
                 raise ValueError("encode_queries(total=%d): expected this rank's %d rows" % (Q, hi - lo))
         D = idx.g16.shape[1]
-        buf = torch.zeros((per, D), dtype=idx.g16.dtype if self.out16_dtype is None else self.out16_dtype, device=idx.g16.device)
+        buf = torch.zeros((per, D), dtype=self.out16_dtype, device=idx.g16.device)
         if hi > lo:
-            _, q16 = self.txt_net.encode(part, out16_dtype=self.out16_dtype)
+            _, q16 = self.txt_net.encode(part, out16_dtype=self.out16_dtype, precision=self.precision)
             buf[: hi - lo] = q16.reshape(hi - lo, -1)
         out = torch.empty((W * per, D), dtype=buf.dtype, device=buf.device)
         dist.all_gather_into_tensor(out, buf, group=idx.group)

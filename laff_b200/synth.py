@@ -123,3 +123,39 @@ def retrieval_embeddings(seed: int, Q: int, V: int, heads: int = 8, head_dim: in
     noise = unit_heads(rng_for(seed, "emb/query").standard_normal((Q, D)).astype(np.float32), heads)
     q = unit_heads(g[gt] + sigma * noise, heads)
     return q, g, gt
+
+
+# Dimensions of the trained-checkpoint fixture (tests/golden/make_golden_trained.py): the shipped head size d_h = 512 (so
+# the single-kernel fusion path and the 16-bit similarity sweep are the ones exercised) with H = 4 heads and narrow input
+# features, which keeps the reference-trained checkpoint at ~4 MB.
+TRAINED_DIMS = {"clip": 512, "gru": 96, "bow": 128, "w2v": 60, "x3d": 96, "ircsn": 96, "tf": 64, "c3d": 96}
+TRAINED_HEADS, TRAINED_D, TRAINED_LATENT = 4, 2048, 64
+
+
+def latent_collection(seed: int, n: int, dims: Mapping[str, int] = None, map_seed: int = 4242, latent: int = TRAINED_LATENT,
+                      vis_noise: float = 0.6, cap_noise: float = 0.5, txt_noise: float = 0.6):
+    """n (video, caption) pairs that share a latent factor (SURVEY §8d "trained fixture"): z_i ~ N(0, I_64); every video
+    feature is a fixed random linear map of z_i plus noise (pooled-CNN-like features pass through a ReLU); the caption's
+    latent is z_i plus noise and every text feature a fixed random map of it plus noise; the BoW vector marks the 8
+    vocabulary entries with the largest (map + Gumbel noise) score.  The maps depend on `map_seed` only, so collections
+    of different `seed` (train / test) are draws from the same distribution.  Ground truth: caption i <-> video i.
+    Returns (vis_feats {reference feature name: [n, d]}, txt_feats {'gru','bow','w2v','clip': [n, d]})."""
+    d = dict(TRAINED_DIMS if dims is None else dims)
+    z = rng_for(seed, "latent/z").standard_normal((n, latent)).astype(np.float32)
+    zc = z + np.float32(cap_noise) * rng_for(seed, "latent/cap").standard_normal((n, latent)).astype(np.float32)
+
+    def mapped(zz, name, dim, noise, relu):
+        m = rng_for(map_seed, "map/" + name).standard_normal((latent, dim)).astype(np.float32) / np.float32(np.sqrt(latent))
+        x = zz @ m + np.float32(noise) * rng_for(seed, "noise/" + name).standard_normal((n, dim)).astype(np.float32)
+        return np.maximum(x, 0.0).astype(np.float32) if relu else x.astype(np.float32)
+
+    vis = {VIS_CLIP_FT: mapped(z, "v/clip", d["clip"], vis_noise, False), VIS_TF: mapped(z, "v/tf", d["tf"], vis_noise, True),
+           VIS_X3D: mapped(z, "v/x3d", d["x3d"], vis_noise, True), VIS_IRCSN: mapped(z, "v/ircsn", d["ircsn"], vis_noise, True)}
+    txt = {"gru": mapped(zc, "t/gru", d["gru"], txt_noise, False), "w2v": mapped(zc, "t/w2v", d["w2v"], txt_noise, False),
+           "clip": mapped(zc, "t/clip", d["clip"], txt_noise, False)}
+    score = mapped(zc, "t/bow", d["bow"], 0.0, False) + 0.5 * rng_for(seed, "noise/bow").gumbel(size=(n, d["bow"])).astype(np.float32)
+    ids = np.argsort(-score, axis=1, kind="stable")[:, :8]
+    bow = np.zeros((n, d["bow"]), dtype=np.float32)
+    np.put_along_axis(bow, ids, 1.0, axis=1)
+    txt["bow"] = bow
+    return vis, txt

@@ -245,6 +245,12 @@ class BowVec(Txt2Vec):
         off, ids = self.token_csr(captions)
         return ops.bow_counts(torch.from_numpy(off).to(dev), torch.from_numpy(ids).to(dev), self.ndims)
 
+    def encode_sparse(self, captions, device=None):
+        """The same batch kept sparse: CSR token ids on the device (ops.SparseRows) for the gather-sum projection."""
+        dev = _device(device)
+        off, ids = self.token_csr(captions)
+        return ops.SparseRows(torch.from_numpy(off).to(dev), torch.from_numpy(ids).to(dev), self.ndims)
+
     def __len__(self):
         return self.ndims
 

@@ -110,3 +110,23 @@ def test_native_batch_tokeniser_equals_the_python_path():
     bow_plain = T.BowVec(None, vocab=T.load_vocab(os.path.join(D, "vocab_bow_nsw.pkl")))   # a non-'gru' vocabulary has no <unk>
     with pytest.raises(Exception, match="word out of vocab"):
         T.IndexVec(None, vocab=bow_plain.vocab).encoding_batch(["zebra"])
+
+
+def test_sparse_rows_host_logic():
+    """ops.SparseRows (CSR BoW batch): shape, exact CSR form of a count matrix, host slices carry only their ids."""
+    import torch
+    from laff_b200 import ops
+    counts = torch.tensor([[0., 2., 0., 1.], [0., 0., 0., 0.], [3., 0., 0., 0.], [0., 1., 1., 1.]])
+    x = ops.SparseRows.from_dense(counts)
+    assert x.shape == (4, 4) and x.offsets.tolist() == [0, 3, 3, 6, 9] and x.ids.tolist() == [1, 1, 3, 0, 0, 0, 1, 2, 3]
+    s = x[2:4]
+    assert s.shape == (2, 4) and s.base == 3 and s.ids.tolist() == [0, 0, 0, 1, 2, 3] and s.offsets.tolist() == [3, 6, 9]
+    assert x[1:2].ids.numel() == 0 and x[4:4].shape == (0, 4)
+    assert s[1:2].base == 6 and s[1:2].ids.tolist() == [1, 2, 3]
+    y = ops.SparseRows.from_lists([[1, 1, 3], [], [0, 0, 0], [1, 2, 3]], 4)
+    assert y.offsets.tolist() == x.offsets.tolist() and y.ids.tolist() == x.ids.tolist()
+    assert x.nbytes() == 5 * 8 + 9 * 4
+    with pytest.raises(ops.LaffError):
+        ops.SparseRows.from_dense(torch.tensor([[0.5]]))
+    with pytest.raises(ops.LaffError):
+        x[::2]
