@@ -76,10 +76,17 @@ def test_predict_collection_end_to_end(tmp_path):
         # --- the same scores computed piecewise through the public model API
         ids2, caps = read_captions(str(tmp_path / "toyset" / "TextData" / "toyset.caption.txt"))
         assert ids2 == cap_ids
+        from laff_b200 import loss as L
+        from laff_b200 import ops
         with torch.no_grad():
-            v = model.vis_net({k: torch.from_numpy(x) for k, x in feats.items()})
-            t = model.txt_net({"caption": [caps[i] for i in cap_ids], "CLIP_encoding": torch.from_numpy(np.stack([clip[i] for i in cap_ids]))})
-            s = model.get_txt2vis_matrix(t, v).cpu().numpy()
+            dt = L.operand_dtype()
+            v, v16 = model.vis_net.encode({k: torch.from_numpy(x) for k, x in feats.items()}, out16_dtype=dt)
+            t, t16 = model.txt_net.encode({"caption": [caps[i] for i in cap_ids],
+                                           "CLIP_encoding": torch.from_numpy(np.stack([clip[i] for i in cap_ids]))}, out16_dtype=dt)
+            # the collection path ranks the 16-bit embeddings the fused kernel writes; get_txt2vis_matrix re-normalises the
+            # fp32 copies before rounding, which can move a component by one 16-bit ulp: same scores within that rounding
+            s = ops.sim_dense(t16.reshape(len(cap_ids), -1), v16.reshape(V, -1), 1.0 / 8).cpu().numpy()
+            assert np.abs(model.get_txt2vis_matrix(t, v).cpu().numpy() - s).max() <= 2e-5
         t2v, _ = O.predictor_t2v_eval(s, cap_ids, vis_ids)
         v2t, _ = O.predictor_v2t_eval(s, cap_ids, vis_ids)
         np.testing.assert_allclose(res["toyset.caption.txt"]["t2v"], t2v, atol=1e-9)
