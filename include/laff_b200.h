@@ -61,6 +61,11 @@ long long laff_launch_count(int reset);
  *   chunk_tiles number of consecutive 256-column gallery tiles one work unit sweeps with per-row top-k state.
  *   m_group     number of query row-tiles that sweep the gallery together (L2 residency of the query block). */
 int laff_set_tuning(int cta_group, int chunk_tiles, int m_group);
+/* SM budget of the persistent kernels launched after the call (GEMM engine, fused fusion kernel, grid-stride kernels):
+ * at most `sms` SMs are filled; 0 = the whole device.  Returns the previous value.  The retrieval pipeline gives the
+ * sweep all but a couple of SMs and runs the next batch's query fusion (and the NCCL kernels of its collectives) on
+ * those, so the two overlap instead of queueing behind each other.  Process-wide; set by the launching host thread. */
+int laff_set_sm_limit(int sms);
 int laff_get_tuning(int* cta_group, int* chunk_tiles, int* m_group);
 /* laff_sim_rank_topk (and laff_sim_collect) cut a sweep into back-to-back launches: one per group of m_group row tiles and
  * per ~480 gallery column tiles, which keeps the CTA pairs that share a gallery tile aligned (10 % faster than one launch,

@@ -81,6 +81,7 @@ SIGNATURES = {
     "laff_abi_version": (_i, []),
     "laff_launch_count": (C.c_longlong, [_i]),
     "laff_set_tuning": (_i, [_i, _i, _i]),
+    "laff_set_sm_limit": (_i, [_i]),
     "laff_get_tuning": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "laff_debug_fuse_profile": (_i, [_vp, _i]),
     "laff_set_fuse_variant": (_i, [_i]),

@@ -799,13 +799,21 @@ extern "C" int laff_fuse_forward(const laff_fuse_desc* d, long long rows, float*
   // Variant: wall time ~ waves x unit time; a cta_group::2 unit covers twice the rows in ~4/3 of the time, but only
   // the clusters that fit the GPCs run at once.
   int max1 = 0, max2 = 0;
-  rc = fuse_max_clusters<1>(di.sms, &max1);
+  rc = fuse_max_clusters<1>(di.sms_total, &max1);
   if (rc) return rc;
-  rc = fuse_max_clusters<2>(di.sms, &max2);
+  rc = fuse_max_clusters<2>(di.sms_total, &max2);
   if (rc) return rc;
+  // an SM budget (laff_set_sm_limit) caps the number of co-resident clusters; below four SMs only pairs fit
+  const bool budget = di.sms < di.sms_total;
+  if (budget) {
+    max1 = max1 < di.sms / 2 ? max1 : di.sms / 2;
+    max2 = max2 < di.sms / 4 ? max2 : di.sms / 4;
+    LAFF_REQUIRE(max1 >= 1, LAFF_EINVAL, "laff_fuse_forward: an SM budget of %d leaves no room for a 2-CTA cluster", di.sms);
+  }
   const long long units1 = (rows + kBlockM - 1) / kBlockM * d->heads;
   const long long units2 = (rows + 2 * kBlockM - 1) / (2 * kBlockM) * d->heads;
   int cg = g_fuse_variant.load();
+  if (max2 < 1) cg = 1;
   if (cg == 0) {
     // Measured (profiles/README.md): the pair variant only wins when a wide feature (K >= 3072, the 3981-word BoW)
     // makes the kernel operand-feed bound; otherwise running on all 148 SMs is worth more than the cheaper feed.

@@ -21,6 +21,11 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return static_cast<int>(e);
 }
 
+// SM budget of the persistent kernels launched from now on (0 = the whole device): the retrieval pipeline runs the
+// similarity sweep on all but a couple of SMs and the next step's query fusion / collectives' neighbours on those, so
+// that the two overlap instead of queueing behind each other (laff_b200/retrieval.py::Retriever.submit).
+static std::atomic<int> g_sm_limit{0};
+
 int get_device_info(DeviceInfo* info) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -39,10 +44,14 @@ int get_device_info(DeviceInfo* info) {
     return LAFF_ENODEV;
   }
   info->device = dev;
-  info->sms = sms;
+  info->sms_total = sms;
+  const int limit = g_sm_limit.load();
+  info->sms = (limit > 0 && limit < sms) ? limit : sms;
   info->cc_major = major;
   return LAFF_OK;
 }
+
+int sm_limit() { return g_sm_limit.load(); }
 
 // Measured on B200 (profiles/): single-tile units in n-major order with ~10 query row-tiles per group keep the query
 // block L2-resident and let the CTA pairs that share a gallery tile run within a fraction of a tile of each other.
@@ -130,3 +139,8 @@ int laff_get_tuning(int* cta_group, int* chunk_tiles, int* m_group) {
 }
 
 }  // extern "C"
+
+extern "C" int laff_set_sm_limit(int sms) {
+  if (sms < 0) sms = 0;
+  return laff::g_sm_limit.exchange(sms);
+}

@@ -12,9 +12,11 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 struct DeviceInfo {
   int device;
-  int sms;
+  int sms;        // SMs the caller may fill: the device's count, or the budget set with laff_set_sm_limit
+  int sms_total;  // the device's SM count
   int cc_major;
 };
+int sm_limit();
 // Fails (LAFF_ENODEV) unless the current device is sm_100-class: there is no fallback path.
 int get_device_info(DeviceInfo* info);
 

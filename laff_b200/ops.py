@@ -474,6 +474,22 @@ def _csr(offsets: torch.Tensor, ids: torch.Tensor):
     return offsets.to(torch.int64).contiguous(), ids.to(torch.int32).contiguous()
 
 
+class sm_limit:
+    """`with ops.sm_limit(n):` -- the persistent kernels launched inside fill at most n SMs (laff_set_sm_limit); n = 0
+    or None leaves the whole device.  Host-side state read at launch time: use from the launching thread only."""
+
+    def __init__(self, sms: Optional[int]):
+        self.sms = int(sms or 0)
+
+    def __enter__(self):
+        self.prev = _capi.lib().laff_set_sm_limit(self.sms)
+        return self
+
+    def __exit__(self, *exc):
+        _capi.lib().laff_set_sm_limit(self.prev)
+        return False
+
+
 class SparseRows:
     """A batch of bag-of-words rows kept sparse: CSR token ids (a token that occurs twice is listed twice -- its count)
     instead of the dense [rows, ndims] count matrix of BowVec._encoding (txt2vec.py:56-63; ~8 non-zeros of 3981).

@@ -17,6 +17,8 @@ kernels).  Tests inject a numpy backend to exercise the sharding / collective lo
 """
 from __future__ import annotations
 
+import contextlib
+import types
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -112,14 +114,21 @@ class SearchResult:
         `.cpu()` calls cost four round trips -- visible once a step is a few milliseconds, as at 8 GPUs)."""
         if not self.rank0.is_cuda:
             return self
+        host, ev = self._pack_to_pinned()
+        ev.synchronize()
+        return self._unpack(host, self.rank0.numel(), tuple(self.topk_val.shape), self.metrics.numel())
+
+    def _pack_to_pinned(self):
+        """Enqueues the packed device->host copy on the current stream; returns (pinned int32 buffer, completion event)."""
         # the float64 metrics go first so that their view starts at an 8-byte aligned offset whatever Q is
         parts = [self.metrics.double().reshape(-1).view(torch.int32), self.rank0.to(torch.int32).reshape(-1),
                  self.topk_val.float().reshape(-1).view(torch.int32), self.topk_idx.to(torch.int32).reshape(-1)]
         flat = torch.cat(parts)
         host = torch.empty(flat.shape, dtype=torch.int32, pin_memory=True)
         host.copy_(flat, non_blocking=True)
-        torch.cuda.current_stream(flat.device).synchronize()
-        return self._unpack(host, self.rank0.numel(), tuple(self.topk_val.shape), self.metrics.numel())
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(flat.device))
+        return host, ev
 
     @staticmethod
     def _unpack(host: torch.Tensor, Q: int, klist_shape, n_metrics: int) -> "SearchResult":
@@ -128,6 +137,34 @@ class SearchResult:
         o1 = n_m + Q
         return SearchResult(host[n_m:o1], host[o1:o1 + n_k].view(torch.float32).reshape(klist_shape),
                             host[o1 + n_k:o1 + 2 * n_k].reshape(klist_shape), host[:n_m].view(torch.float64))
+
+
+class PendingSearch:
+    """Handle of a search submitted to the pipelined path (Retriever.submit): the result tensors are being produced on the
+    pipeline's streams.  `result()` makes the caller's current stream wait for them; `to_host()` returns host copies
+    (one packed device->host transfer, enqueued at submit time when fetch=True so that only its completion is awaited)."""
+
+    def __init__(self, res: SearchResult, done, stream, packed=None):
+        self._res, self._done, self._stream, self._packed = res, done, stream, packed
+
+    def result(self) -> SearchResult:
+        if self._done is not None:
+            cur = torch.cuda.current_stream(self._res.rank0.device)
+            cur.wait_event(self._done)
+            for t in (self._res.rank0, self._res.topk_val, self._res.topk_idx, self._res.metrics):
+                t.record_stream(cur)
+        return self._res
+
+    def to_host(self) -> SearchResult:
+        if self._done is None:
+            return self._res.to_host()
+        if self._packed is None:
+            with torch.cuda.stream(self._stream):
+                self._packed = self._res._pack_to_pinned()
+        host, ev = self._packed
+        ev.synchronize()
+        r = self._res
+        return SearchResult._unpack(host, r.rank0.numel(), tuple(r.topk_val.shape), r.metrics.numel())
 
 
 class GalleryIndex:
@@ -168,46 +205,61 @@ class GalleryIndex:
         g16 = g16.reshape(g16.shape[0], -1)
         return cls(g16, total, heads, rank, world_size, group, backend)
 
-    def _all_reduce(self, t):
+    def _all_reduce(self, t, group=None):
         if self.world_size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group if group is not None else self.group)
         return t
 
-    def search(self, q16: torch.Tensor, gt_global: torch.Tensor, k: int = 10) -> SearchResult:
-        """q16 [Q, H*d_h] 16-bit unit-norm query embeddings (replicated on every rank), gt_global int [Q]."""
-        be = self.backend
-        scale = 1.0 / self.heads
-        gt_global = gt_global.to(torch.int32)
+    # The three stages of a search.  `group` lets the pipelined path (Retriever.submit) run the collectives of the stages
+    # before and after the sweep on two extra communicators, each on its own stream.
+    def _gt_scores(self, q16, gt_global, group=None):
+        """Raw (unscaled) score of every query's ground truth, replicated: computed by the shard that owns the ground
+        truth (others contribute 0) and summed over the shards."""
         n_local = self.hi - self.lo
         owned = (gt_global >= self.lo) & (gt_global < self.hi)
         gt_local = torch.where(owned, gt_global - self.lo, torch.full_like(gt_global, -1))
         if n_local > 0:
-            sgt = be.gt_scores(q16, self.g16, gt_local)
+            sgt = self.backend.gt_scores(q16, self.g16, gt_local)
         else:
             sgt = torch.zeros(q16.shape[0], dtype=torch.float32, device=q16.device)
-        sgt = self._all_reduce(sgt)
-        if n_local > 0:
+        return self._all_reduce(sgt, group)
+
+    def _sweep(self, q16, sgt, gt_global, k):
+        """Local shard: (count of videos ranked above the ground truth, ordered top-k values, global indices)."""
+        if self.hi - self.lo > 0:
             if self.timers is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            count, tv, ti = be.rank_topk(q16, self.g16, sgt, gt_global, k, scale, self.lo, self._ws)
+            count, tv, ti = self.backend.rank_topk(q16, self.g16, sgt, gt_global, k, 1.0 / self.heads, self.lo, self._ws)
             if self.timers is not None:
                 e1.record()
                 self.timers.append((e0, e1))
-        else:
-            Q = q16.shape[0]
-            count = torch.zeros(Q, dtype=torch.int32, device=q16.device)
-            tv = torch.full((Q, k), float("-inf"), dtype=torch.float32, device=q16.device)
-            ti = torch.full((Q, k), -1, dtype=torch.int32, device=q16.device)
-        count = self._all_reduce(count)
-        if self.world_size > 1 and k > 0:
-            # one collective for both halves of the lists: [score bits | index] per query, gathered into [W, Q, 2k]
-            mine = torch.cat([tv.contiguous().view(torch.int32), ti.to(torch.int32)], 1).contiguous()
-            flat = torch.empty((self.world_size * mine.shape[0], mine.shape[1]), dtype=torch.int32, device=mine.device)
-            dist.all_gather_into_tensor(flat, mine, group=self.group)
-            both = flat.view(self.world_size, mine.shape[0], mine.shape[1])
-            tv, ti = be.merge(both[:, :, :k].contiguous().view(torch.float32), both[:, :, k:].contiguous(), k)
-        return SearchResult(count, tv, ti, be.metrics(count))
+            return count, tv, ti
+        Q = q16.shape[0]
+        return (torch.zeros(Q, dtype=torch.int32, device=q16.device),
+                torch.full((Q, k), float("-inf"), dtype=torch.float32, device=q16.device),
+                torch.full((Q, k), -1, dtype=torch.int32, device=q16.device))
+
+    def _merge(self, count, tv, ti, k, group=None):
+        """Global rank0 and top-k from the per-shard partial results: ONE collective -- [count | score bits | index] per
+        query, gathered into [W, Q, 1 + 2k] -- then the counts are summed and the lists merged under the tie rule."""
+        if self.world_size == 1:
+            return count, tv, ti
+        mine = torch.cat([count.to(torch.int32).reshape(-1, 1), tv.contiguous().view(torch.int32), ti.to(torch.int32)], 1).contiguous()
+        flat = torch.empty((self.world_size * mine.shape[0], mine.shape[1]), dtype=torch.int32, device=mine.device)
+        dist.all_gather_into_tensor(flat, mine, group=group if group is not None else self.group)
+        both = flat.view(self.world_size, mine.shape[0], mine.shape[1])
+        count = both[:, :, 0].sum(0, dtype=torch.int32)
+        if k > 0:
+            tv, ti = self.backend.merge(both[:, :, 1:1 + k].contiguous().view(torch.float32), both[:, :, 1 + k:].contiguous(), k)
+        return count, tv, ti
+
+    def search(self, q16: torch.Tensor, gt_global: torch.Tensor, k: int = 10) -> SearchResult:
+        """q16 [Q, H*d_h] 16-bit unit-norm query embeddings (replicated on every rank), gt_global int [Q]."""
+        gt_global = gt_global.to(torch.int32)
+        sgt = self._gt_scores(q16, gt_global)
+        count, tv, ti = self._merge(*self._sweep(q16, sgt, gt_global, k), k)
+        return SearchResult(count, tv, ti, self.backend.metrics(count))
 
     def ranked_lists(self, q16: torch.Tensor, k: int, query_chunk: int = 2048):
         """The k best videos of every query over the whole (sharded) gallery, k up to 2048: the lists the reference
@@ -259,7 +311,7 @@ class Retriever:
         return min(Q, r * per), min(Q, (r + 1) * per), per
 
     @torch.no_grad()
-    def encode_queries(self, caption_feat_dict, total: Optional[int] = None) -> torch.Tensor:
+    def encode_queries(self, caption_feat_dict, total: Optional[int] = None, group=None) -> torch.Tensor:
         """Fused 16-bit query embeddings [Q, H*d_h], replicated on every rank.  With W > 1 ranks each rank fuses only
         its 1/W slice of the queries (the fusion is data-parallel per item) and the slices are all-gathered over
         NVLink, so the replicated part of a step shrinks with W.  `total` = Q says that caption_feat_dict already holds
@@ -285,7 +337,7 @@ class Retriever:
             _, q16 = self.txt_net.encode(part, out16_dtype=self.out16_dtype, precision=self.precision)
             buf[: hi - lo] = q16.reshape(hi - lo, -1)
         out = torch.empty((W * per, D), dtype=buf.dtype, device=buf.device)
-        dist.all_gather_into_tensor(out, buf, group=idx.group)
+        dist.all_gather_into_tensor(out, buf, group=group if group is not None else idx.group)
         return out[:Q]
 
     @torch.no_grad()
@@ -333,3 +385,139 @@ class Retriever:
         rank0 = torch.cat([r.rank0 for r in outs])
         return SearchResult(rank0, torch.cat([r.topk_val for r in outs]), torch.cat([r.topk_idx for r in outs]),
                             self.index.backend.metrics(rank0))
+
+    # ------------------------------------------------------------------------------------------------------------
+    # pipelined path
+    # ------------------------------------------------------------------------------------------------------------
+    reserve_sms = 2      # SMs left to the side streams while a sweep runs (the sweep takes the rest)
+    side_max_ctas = 1    # CTAs of an NCCL kernel on the side communicators (one per reserved SM and side stream)
+
+    def _side_group(self):
+        """A communicator over the index's ranks for one side stream; NCCL kernels limited to `side_max_ctas` CTAs so that
+        the collective of the stage before a sweep and the one after it fit the reserved SMs together (a kernel waiting
+        for its peers then never blocks the other stage's)."""
+        idx = self.index
+        ranks = dist.get_process_group_ranks(idx.group) if idx.group is not None else list(range(dist.get_world_size()))
+        if dist.get_backend(idx.group) == "nccl":
+            opts = dist.ProcessGroupNCCL.Options()
+            try:
+                opts.config.max_ctas = int(self.side_max_ctas)
+                opts.config.min_ctas = 1
+            except Exception:
+                pass
+            return dist.new_group(ranks, pg_options=opts)
+        return dist.new_group(ranks)
+
+    def _pipe(self):
+        P = getattr(self, "_pipe_state", None)
+        if P is not None:
+            return P
+        idx = self.index
+        dev = idx.g16.device
+        P = types.SimpleNamespace(pre=None, sweep=None, post=None, copy=None, g_pre=idx.group, g_post=idx.group,
+                                  sweep_sms=0, side_sms=0)
+        if idx.world_size > 1:                                   # collective calls: every rank creates them in this order
+            P.g_pre, P.g_post = self._side_group(), self._side_group()
+        if dev.type == "cuda":
+            P.pre, P.post, P.copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            P.sweep = torch.cuda.Stream(dev, priority=-1)        # a sweep launch gets freed SMs before queued side work
+            total = torch.cuda.get_device_properties(dev).multi_processor_count
+            r = max(0, min(int(self.reserve_sms), total - 2))
+            r += r % 2                                           # CTA pairs
+            P.side_sms, P.sweep_sms = (r, total - r) if r > 0 else (0, 0)
+        self._pipe_state = P
+        return P
+
+    @torch.no_grad()
+    def submit(self, caption_feat_dict, gt_global, k: int = 10, pieces: Optional[int] = None, inputs_ready=None,
+               fetch: bool = False) -> PendingSearch:
+        """rank() as a three-stage pipeline over pieces of the query batch, each stage on its own stream:
+
+            pre   fuse this rank's slice of the piece, all-gather the embeddings, ground-truth scores (+ all-reduce)
+            sweep similarity + rank + top-k over the local gallery shard (high-priority stream, all but `reserve_sms` SMs)
+            post  one all-gather of [count | lists], merge; after the last piece: metrics (and the packed D2H if fetch)
+
+        The stages of consecutive pieces -- and of consecutive submits, which need not wait for each other -- overlap:
+        the pre / post kernels and the NCCL kernels of their collectives (separate communicators, `side_max_ctas` CTAs)
+        run on the reserved SMs while the sweep of another piece owns the rest, so neither their run time nor the
+        rank-to-rank skew of a collective stalls the tensor cores.  Results are identical to rank(): queries are
+        independent and every stage is the same kernel sequence.
+
+        inputs_ready: None -- the inputs are complete once the work already queued on the caller's current stream has run
+        (an event is recorded there); a torch.cuda.Event to wait for; or False: they are complete now (resident inputs).
+        Host (pinned) inputs are copied piece by piece on a copy stream."""
+        idx = self.index
+        P = self._pipe()
+        dev = idx.g16.device
+        first = next(iter(caption_feat_dict.values()))
+        Q = first.shape[0]
+        cuda = dev.type == "cuda"
+        if pieces is None:
+            pieces = max(1, min(4, (Q + 2559) // 2560))          # the sweep's own row groups (10 row tiles of 256)
+        pieces = max(1, min(int(pieces), max(1, Q)))
+        per = (Q + pieces - 1) // pieces
+        per = (per + 255) // 256 * 256 if per > 256 else per     # whole row tiles per piece
+        host_in = cuda and not first.is_cuda
+        stream = (lambda s: torch.cuda.stream(s)) if cuda else (lambda s: contextlib.nullcontext())
+        dep = None
+        if cuda and not host_in and inputs_ready is not False:
+            dep = inputs_ready
+            if dep is None:
+                dep = torch.cuda.Event()
+                dep.record(torch.cuda.current_stream(dev))
+        # ---- stage the pieces (host inputs: H2D copies of this rank's slice of every piece, issued up front)
+        staged = []
+        for lo in range(0, Q, per):
+            hi = min(Q, lo + per)
+            a, b, _ = self.query_slice(hi - lo)                  # this rank fuses rows [lo + a, lo + b) of the piece
+            if host_in:
+                with stream(P.copy):
+                    part = {n: v[lo + a:lo + b].to(dev, non_blocking=True) for n, v in caption_feat_dict.items()}
+                    g = gt_global[lo:hi].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(P.copy)
+            else:
+                part = {n: v[lo + a:lo + b] for n, v in caption_feat_dict.items()}
+                g = gt_global[lo:hi].to(dev) if not gt_global.is_cuda and cuda else gt_global[lo:hi]
+                ev = dep
+            staged.append((part, g, ev, hi - lo))
+        outs = []
+        for part, g, ev, n in staged:
+            with stream(P.pre), ops.sm_limit(P.side_sms) if cuda else contextlib.nullcontext():
+                if cuda and ev is not None:
+                    P.pre.wait_event(ev)
+                if host_in:
+                    for t in list(part.values()) + [g]:
+                        t.record_stream(P.pre)
+                q16 = self.encode_queries(part, total=n, group=P.g_pre) if idx.world_size > 1 else self.encode_queries(part)
+                g32 = g.to(torch.int32)
+                sgt = idx._gt_scores(q16, g32, group=P.g_pre)
+                if cuda:
+                    ready = torch.cuda.Event()
+                    ready.record(P.pre)
+            with stream(P.sweep), ops.sm_limit(P.sweep_sms) if cuda else contextlib.nullcontext():
+                if cuda:
+                    P.sweep.wait_event(ready)
+                    for t in (q16, g32, sgt):
+                        t.record_stream(P.sweep)
+                count, tv, ti = idx._sweep(q16, sgt, g32, k)
+                if cuda:
+                    swept = torch.cuda.Event()
+                    swept.record(P.sweep)
+            with stream(P.post), ops.sm_limit(P.side_sms) if cuda else contextlib.nullcontext():
+                if cuda:
+                    P.post.wait_event(swept)
+                    for t in (count, tv, ti):
+                        t.record_stream(P.post)
+                outs.append(idx._merge(count, tv, ti, k, group=P.g_post))
+        with stream(P.post), ops.sm_limit(P.side_sms) if cuda else contextlib.nullcontext():
+            rank0 = outs[0][0] if len(outs) == 1 else torch.cat([o[0] for o in outs])
+            tv = outs[0][1] if len(outs) == 1 else torch.cat([o[1] for o in outs])
+            ti = outs[0][2] if len(outs) == 1 else torch.cat([o[2] for o in outs])
+            res = SearchResult(rank0, tv, ti, idx.backend.metrics(rank0))
+            packed = res._pack_to_pinned() if (fetch and cuda) else None
+            done = None
+            if cuda:
+                done = torch.cuda.Event()
+                done.record(P.post)
+        return PendingSearch(res, done, P.post, packed)

@@ -340,3 +340,36 @@ def test_full_size_properties(V):
     assert bool((sl[:, 1:] != sl[:, :-1]).all())
     dv, di = CudaBackend()._dense_topk(q16[:64], g16, 2000, 1.0 / H, 0)
     assert torch.equal(di, li[:64]) and torch.equal(dv, lv[:64])
+
+
+def test_pipelined_submit_equals_serial_rank():
+    """Retriever.submit (pieces through pre / sweep / post stages on three streams, the sweep on all but two SMs, side
+    kernels under an SM budget) returns exactly what Retriever.rank returns -- for device-resident inputs, for pinned host
+    inputs with the packed device->host copy enqueued at submit time, and with several submits in flight."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from laff_b200 import _capi
+    from laff_b200.retrieval import Retriever
+    dev = torch.device("cuda")
+    Q, V, H, k = 3001, 20011, 8, 10
+    txt_net = bench.build_txt_net(dev)
+    feats = bench.query_features(Q, pinned=True)
+    feats_dev = {n: v.to(dev) for n, v in feats.items()}
+    gt = ((torch.arange(Q) * 97) % V).to(torch.int32)
+    gen = torch.Generator(device=dev).manual_seed(3)
+    g16 = bench.unit_rows(V, gen, dev, torch.float16)
+    retr = Retriever(txt_net, GalleryIndex(g16, V, H))
+    ref = retr.rank(feats_dev, gt.to(dev), k)
+    pend = [retr.submit(feats_dev, gt.to(dev), k, pieces=p, inputs_ready=r) for p, r in ((1, None), (3, False), (4, None), (None, None))]
+    pend.append(retr.submit(feats, gt.pin_memory(), k, pieces=3, fetch=True))
+    assert _capi.lib().laff_set_sm_limit(0) == 0                 # the SM budget is restored after every stage
+    for p in pend[:-1]:
+        got = p.result()
+        assert torch.equal(got.rank0, ref.rank0) and torch.equal(got.topk_idx, ref.topk_idx)
+        assert torch.equal(got.topk_val, ref.topk_val) and torch.equal(got.metrics, ref.metrics)
+    h = pend[-1].to_host()
+    assert torch.equal(h.rank0, ref.rank0.cpu()) and torch.equal(h.topk_idx, ref.topk_idx.cpu()) and torch.equal(h.metrics, ref.metrics.cpu())
+    h2 = pend[0].to_host()                                       # a handle submitted without fetch can still be read back
+    assert torch.equal(h2.topk_val, ref.topk_val.cpu())

@@ -106,6 +106,16 @@ def _worker(rank, world, port, out):
             full = retr.encode_queries(feats)
             pre = retr.encode_queries({"x": feats["x"][a:b]}, total=Qs)
             enc_ok = enc_ok and torch.equal(full, want) and torch.equal(pre, want)
+        # the pipelined path (pieces of the batch through pre / sweep / post stages with their own communicators) must
+        # give the serial path's answer, for piece counts that divide the batch unevenly and for one piece
+        feats = {"x": torch.from_numpy(q).clone()}
+        serial = retr.rank(feats, torch.from_numpy(gt), 7)
+        for pieces in (1, 3, 5):
+            pend = retr.submit(feats, torch.from_numpy(gt), 7, pieces=pieces)
+            got, host = pend.result(), pend.to_host()
+            enc_ok = enc_ok and all(torch.equal(a, b) for a, b in ((got.rank0, serial.rank0), (got.topk_idx, serial.topk_idx),
+                                                                   (got.topk_val, serial.topk_val), (got.metrics, serial.metrics),
+                                                                   (host.rank0, serial.rank0)))
         oks = [None] * world
         dist.all_gather_object(oks, bool(enc_ok))
         if rank == 0:

@@ -43,12 +43,24 @@ def main():
     feats = bench.query_features(1001, pinned=True)
     gt2 = ((torch.arange(1001) * 97) % V).to(torch.int32)
     rr = Retriever(txt_net, GalleryIndex(g16[lo:hi].contiguous(), V, H, rank, world)).rank(feats, gt2.pin_memory(), k, chunks=3)
+    # the pipelined path: pieces through pre / sweep / post stages on their own streams and communicators, two submits in
+    # flight (device-resident inputs, then pinned host inputs with the packed D2H enqueued at submit time)
+    retr_p = Retriever(txt_net, GalleryIndex(g16[lo:hi].contiguous(), V, H, rank, world))
+    feats_dev = {n: v.to(dev) for n, v in feats.items()}
+    p1 = retr_p.submit(feats_dev, gt2.to(dev), k, pieces=3, inputs_ready=None)
+    p2 = retr_p.submit(feats, gt2.pin_memory(), k, pieces=2, fetch=True)
+    pr1, pr2 = p1.result(), p2.to_host()
     torch.cuda.synchronize()
     ok = True
     if rank == 0:
         r1 = Retriever(txt_net, GalleryIndex(g16, V, H)).rank({n: v.to(dev) for n, v in feats.items()}, gt2.to(dev), k)
         ok = torch.equal(rr.rank0, r1.rank0) and torch.equal(rr.topk_idx, r1.topk_idx) and torch.equal(rr.topk_val, r1.topk_val)
         print("sharded query fusion + chunked host copies vs single process: %s" % ("OK" if ok else "MISMATCH"), flush=True)
+        okp = (torch.equal(pr1.rank0, r1.rank0) and torch.equal(pr1.topk_idx, r1.topk_idx) and torch.equal(pr1.topk_val, r1.topk_val)
+               and torch.equal(pr1.metrics, r1.metrics) and torch.equal(pr2.rank0, r1.rank0.cpu()) and torch.equal(pr2.topk_idx, r1.topk_idx.cpu())
+               and torch.equal(pr2.topk_val, r1.topk_val.cpu()) and torch.equal(pr2.metrics, r1.metrics.cpu()))
+        print("pipelined submit (3 + 2 pieces, two in flight) vs single process: %s" % ("OK" if okp else "MISMATCH"), flush=True)
+        ok = ok and okp
     if rank == 0:
         single = GalleryIndex(g16, V, H)
         ref = single.search(q16, gt.to(torch.int32), k)
