@@ -915,9 +915,53 @@ class W2VVPP(nn.Module):
     def predict(self, txt_loader, vis_loader, measure, record_emb=False):
         """Dense score matrix for small galleries; same return contract as the reference:
         (scores ndarray [Q, V] float32, txt_ids, vis_ids).  Video embeddings stay on the device (the reference parks
-        them on the host and re-uploads them per text batch, model/model.py:1047, :1066)."""
+        them on the host and re-uploads them per text batch, model/model.py:1047, :1066).  Galleries above 5e4 videos
+        take the predict_batch branch like the reference's (model/model.py:1020-1021)."""
+        if _loader_length(vis_loader) > self.LARGE_GALLERY:
+            return self.predict_batch(txt_loader, vis_loader, measure, record_emb)
         scores, txt_ids, vis_ids = self.predict_device(txt_loader, vis_loader, measure, record_emb)
         return scores.cpu().numpy(), txt_ids, vis_ids
+
+    LARGE_GALLERY = 5e4   # model/model.py:1020
+
+    def predict_batch(self, txt_loader, vis_loader, measure, record_emb=False):
+        """The large-gallery branch (model/model.py:1081-1128).  The reference re-encodes the whole gallery for every text
+        batch and fills a dense host matrix -- 40 GB for 10 k x 1 M.  Here the gallery is fused once into a resident
+        16-bit index (column j = dataset index j, model/model.py:1118), the queries are fused batch by batch, and the
+        first element of the returned triple is a retrieval.RankedScores: the object laff_b200.predictor ranks,
+        evaluates and writes the result files from with the fused similarity sweep (no Q x V matrix); np.asarray() of
+        it still yields the dense matrix when that is small enough to exist.  record_emb keeps the index for the next
+        call, like the reference's video_all_embs cache of predict()."""
+        from .retrieval import GalleryIndex, RankedScores
+        self.eval()
+        if measure != "cosine":
+            self.compute_sim(None, None, measure)
+        dt = _loss.operand_dtype()
+        H = self.opt.multi_head_attention["heads"]
+        with torch.no_grad():
+            index = getattr(self, "_gallery_index", None) if record_emb else None
+            if index is None:
+                V = _loader_length(vis_loader)
+                g16, self.vis_ids, seen = None, [None] * V, 0
+                for output_dict in vis_loader:
+                    e16 = self._encode_vis(output_dict, dt)[1]
+                    if g16 is None:
+                        g16 = torch.empty((V, e16.shape[1] * e16.shape[2]), dtype=e16.dtype, device=e16.device)
+                    idxs = torch.as_tensor(np.asarray(output_dict["idxs"]), device=e16.device).long()
+                    g16[idxs] = e16.reshape(e16.shape[0], -1)
+                    for j, v in zip(np.asarray(output_dict["idxs"]).tolist(), output_dict["vis_ids"]):
+                        self.vis_ids[j] = v
+                    seen += e16.shape[0]
+                if seen != V:
+                    raise ops.LaffError("predict_batch: the video loader yielded %d of %d videos" % (seen, V))
+                index = GalleryIndex(g16, V, H)
+                self._gallery_index = index if record_emb else None
+            txt_ids, q = [], []
+            for caption_feat_dict, txt_idxs, batch_txt_ids in txt_loader:
+                q.append(self.txt_net.encode(caption_feat_dict, out16_dtype=index.g16.dtype)[1])
+                txt_ids.extend(batch_txt_ids)
+            q16 = torch.cat(q, 0).reshape(len(txt_ids), -1)
+        return RankedScores(index, q16), txt_ids, list(self.vis_ids)
 
     def predict_device(self, txt_loader, vis_loader, measure, record_emb=False):
         """predict() with the score matrix left on the device (CUDA fp32 [Q, V]) for laff_b200.predictor, which ranks,
@@ -986,6 +1030,13 @@ class W2VVPP_MutiVisFrameFeat(W2VVPP):
 
 
 NAME_TO_MODELS = {"LAFF": W2VVPP_MultiHeadAttention, "FrameLAFF": W2VVPP_MutiVisFrameFeat}
+
+
+def _loader_length(loader) -> int:
+    """`vis_loader.dataset.length` as the reference reads it (model/model.py:1020), else len(dataset)."""
+    ds = getattr(loader, "dataset", loader)
+    n = getattr(ds, "length", None)
+    return int(n) if n is not None else len(ds)
 
 
 def get_model(name, device_, config):

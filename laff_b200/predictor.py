@@ -201,6 +201,11 @@ def evaluate_and_write(t2i_matrix, txt_ids, vis_ids, output_dir, predict_result_
     with_ground_truth (collections with labelled captions): metrics in both directions appended to
     <dir>/TextToVideo/<file> and <dir>/VideoToText/<file>, plus <output_dir>/t2v.pkl (top 500).  Otherwise (ad-hoc
     queries): t2v.pkl and the id.sent.score.txt list (top 2000).  Returns a dict of what was computed."""
+    from .retrieval import RankedScores
+    if isinstance(t2i_matrix, RankedScores):     # large gallery (W2VVPP.predict_batch): no Q x V matrix anywhere
+        return evaluate_and_write_ranked(t2i_matrix, txt_ids, vis_ids, output_dir, predict_result_file, model_path, checkpoint,
+                                         captions=captions, txt_loader=txt_loader, pred_result_file=pred_result_file,
+                                         with_ground_truth=with_ground_truth)
     s = _as_scores(t2i_matrix)
     os.makedirs(output_dir, exist_ok=True)
     out = {}
@@ -221,6 +226,41 @@ def evaluate_and_write(t2i_matrix, txt_ids, vis_ids, output_dir, predict_result_
         pred_result_file = os.path.join(output_dir, "id.sent.score.txt")
     txt2video_write_to_file(pred_result_file, None, vis_ids, txt_ids, s)
     out.update(pred_result_file=pred_result_file)
+    return out
+
+
+def evaluate_and_write_ranked(pred, txt_ids, vis_ids, output_dir, predict_result_file, model_path, checkpoint,
+                              captions: Optional[Mapping[str, str]] = None, txt_loader=None, pred_result_file=None,
+                              with_ground_truth: bool = True):
+    """evaluate_and_write for a retrieval.RankedScores (gallery too large for a dense score matrix): text->video ranks,
+    top-10 and metrics from ONE fused similarity sweep (laff_sim_rank_topk), the written lists (t2v.pkl top 500,
+    id.sent.score.txt top 2000) from the threshold sweep (laff_sim_collect) -- the files and numbers are those of the
+    dense path (tests/test_gpu_collection.py, test_gpu_predictor.py).  The video->text direction needs every column of
+    the matrix and is only evaluated on the dense path."""
+    os.makedirs(output_dir, exist_ok=True)
+    out = {}
+    dev = pred.q16.device
+    if with_ground_truth:
+        gt = torch.from_numpy(gt_index(txt_ids, vis_ids)).to(dev)
+        res = pred.search(gt, 10)
+        out["t2v"] = _metrics_tuple(res.metrics)
+        out["rank0"] = res.rank0
+        names = ("r1", "r5", "r10", "medr", "meanr", "mir", "mAP")
+        vals = dict(zip(names, out["t2v"]))
+        print(" * Text to video:")
+        print(" * r_1_5_10: {}".format([round(vals["r1"], 3), round(vals["r5"], 3), round(vals["r10"], 3)]))
+        print(" * medr, meanr, mir: {}".format([round(vals["medr"], 3), round(vals["meanr"], 3), round(vals["mir"], 3)]))
+        write_to_predict_result_file(os.path.join(os.path.dirname(predict_result_file), "TextToVideo", os.path.basename(predict_result_file)),
+                                     model_path, checkpoint, out["t2v"])
+    k500 = writer_topk(len(vis_ids), 500)
+    vals, idx = pred.ranked_lists(max(k500, 1 if with_ground_truth else writer_topk(len(vis_ids), 2000)))
+    vals, idx = vals.cpu().numpy(), idx.cpu().numpy()
+    txt2video_write_to_file(None, (vals, idx), vis_ids, txt_ids, None, pkl_saved_file=os.path.join(output_dir, "t2v.pkl"),
+                            txt_loader=txt_loader, Threshold=500, captions=captions)
+    if not with_ground_truth:
+        f = pred_result_file or os.path.join(output_dir, "id.sent.score.txt")
+        txt2video_write_to_file(f, (vals, idx), vis_ids, txt_ids, None)
+        out["pred_result_file"] = f
     return out
 
 

@@ -293,6 +293,44 @@ class GalleryIndex:
         return torch.cat(out_v), torch.cat(out_i)
 
 
+class RankedScores:
+    """What W2VVPP.predict returns in place of the dense [Q, V] score matrix when the gallery is large (the reference's
+    `predict_batch` branch, model/model.py:1020-1021, :1081-1128, would build a 40 GB host matrix for 10 k x 1 M and
+    re-encode the gallery for every text batch): the resident gallery index plus the fused 16-bit query embeddings,
+    from which everything predictor.py:232-284 derives from the matrix is produced without materialising it --
+    `search` (rank of the ground truth, top-k, R@K / MedR ... in one sweep), `ranked_lists` (the writers' top-500 /
+    top-2000 lists), `rows` (a dense block of rows on the device).  `numpy()` / np.asarray() still give the dense
+    matrix when it is small enough to exist."""
+
+    dense_limit_bytes = 1 << 31
+
+    def __init__(self, index: GalleryIndex, q16: torch.Tensor):
+        self.index, self.q16 = index, q16
+        self.shape = (q16.shape[0], index.total)
+
+    def search(self, gt_global, k: int = 10) -> SearchResult:
+        return self.index.search(self.q16, torch.as_tensor(gt_global).to(self.q16.device), k)
+
+    def ranked_lists(self, k: int, query_chunk: int = 2048):
+        return self.index.ranked_lists(self.q16, k, query_chunk)
+
+    def rows(self, lo: int, hi: int) -> torch.Tensor:
+        """Dense fp32 scores of queries [lo, hi) against this rank's shard, on the device."""
+        return ops.sim_dense(self.q16[lo:hi], self.index.g16, 1.0 / self.index.heads)
+
+    def numpy(self):
+        if self.index.world_size > 1:
+            raise ops.LaffError("RankedScores.numpy(): the gallery is sharded over %d ranks" % self.index.world_size)
+        if self.shape[0] * self.shape[1] * 4 > self.dense_limit_bytes:
+            raise MemoryError("the dense %d x %d score matrix is %.1f GB: use search() / ranked_lists() / rows()"
+                              % (self.shape[0], self.shape[1], self.shape[0] * self.shape[1] * 4 / 1e9))
+        return self.rows(0, self.shape[0]).cpu().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
+
 class Retriever:
     """The whole query path behind one call: fuse the text features of a batch of queries (txt_net, F1-F6), then rank
     them against the resident gallery shard(s) (S2 + E2 + E3).  This is the public API bench.py's e2e leg times."""

@@ -176,3 +176,55 @@ def test_frame_laff_model_predict(golden):
     for out in FakeVisLoader(vis_in, 2, frames=d["frames"]):
         embs.append(model._encode_vis(out)[0])
     assert max_abs(torch.cat(embs, 0), d["emb"]) <= 2e-5
+
+
+def test_predict_large_gallery_branch_returns_ranked_scores(golden, tmp_path):
+    """predict() above LARGE_GALLERY videos takes the predict_batch branch like the reference (model/model.py:1020-1021)
+    but hands back a retrieval.RankedScores instead of a dense host matrix: the predictor's evaluation and writers run
+    on it with the fused sweep and give the dense path's ranks, metrics and files; np.asarray() still yields the
+    matrix when it is small; vis loaders that deliver the videos in shuffled batches land in dataset order."""
+    import pickle
+    from laff_b200 import predictor as P
+    from laff_b200.retrieval import RankedScores
+    d = golden("fusion_small.npz")
+    D, H = int(d["meta"][0]), int(d["meta"][1])
+    dims = small_dims(d)
+    c = cfg.laff_config(D, H, dims)
+    model = M.get_model("LAFF", "cuda", c)
+    sd = {"vis_net." + k: v for k, v in sd_from_npz(d, "vsd/").items()}
+    sd.update({"txt_net." + k: v for k, v in sd_from_npz(d, "tsd/").items()})
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
+    n = 61
+    names = [str(x) for x in d["vis_names"]]
+    vis_in = {nm: synth.feature(3, "v/" + nm, n, dm, "dense" if nm == synth.VIS_CLIP_FT else "relu")
+              for nm, dm in zip(names, [int(x) for x in d["vis_dims"]])}
+    txt_in = {"gru": synth.feature(3, "t/gru", n, dims["gru"]), "bow": synth.feature(3, "t/bow", n, dims["bow"], "bow"),
+              "w2v": synth.feature(3, "t/w2v", n, dims["w2v"]), "clip": synth.feature(3, "t/clip", n, dims["clip"])}
+    dense, txt_ids, vis_ids = model.predict(FakeTxtLoader(txt_in, 9), FakeVisLoader(vis_in, 7), "cosine")
+    assert isinstance(dense, np.ndarray)
+    model.LARGE_GALLERY = 50
+    try:
+        pred, txt_ids2, vis_ids2 = model.predict(FakeTxtLoader(txt_in, 9), FakeVisLoader(vis_in, 7), "cosine")
+    finally:
+        del model.LARGE_GALLERY
+    assert isinstance(pred, RankedScores) and pred.shape == (n, n) and txt_ids2 == txt_ids and vis_ids2 == vis_ids
+    # the 16-bit embeddings of the fused kernel vs predict()'s renormalise-then-round: one 16-bit ulp on a few components
+    assert np.abs(np.asarray(pred) - dense).max() <= 2e-5
+    own = np.asarray(pred)
+    gt = P.gt_index(txt_ids, vis_ids)
+    res = pred.search(torch.from_numpy(gt), 10)
+    np.testing.assert_array_equal(res.rank0.cpu().numpy(), O.tie_rule_rank(own, gt))
+    np.testing.assert_array_equal(res.topk_idx.cpu().numpy(), O.tie_rule_topk(own, 10)[1])
+    caps = {t: "caption of %s" % t for t in txt_ids}
+    a = P.evaluate_and_write(pred, txt_ids, vis_ids, str(tmp_path / "ranked"), str(tmp_path / "res" / "r.txt"), "m", None, captions=caps)
+    b = P.evaluate_and_write(own, txt_ids, vis_ids, str(tmp_path / "dense"), str(tmp_path / "res2" / "r.txt"), "m", None, captions=caps)
+    np.testing.assert_allclose(a["t2v"], b["t2v"], atol=1e-9)
+    da, db = pickle.load(open(tmp_path / "ranked" / "t2v.pkl", "rb")), pickle.load(open(tmp_path / "dense" / "t2v.pkl", "rb"))
+    assert list(da) == list(db) and all(da[k]["rank_list"] == db[k]["rank_list"] for k in da)
+    a2 = P.evaluate_and_write(pred, txt_ids, vis_ids, str(tmp_path / "adhoc"), None, "m", None, captions=caps, with_ground_truth=False)
+    lines = open(a2["pred_result_file"]).read().splitlines()
+    assert len(lines) == n and all(len(l.split()) == 1 + 2 * (n - 1) for l in lines)
+    big = RankedScores(pred.index, pred.q16)
+    big.dense_limit_bytes = 100
+    with pytest.raises(MemoryError):
+        big.numpy()
