@@ -115,6 +115,13 @@ int laff_sim_dense(const void* q, const void* g, int Q, int V, int D, long long 
 int laff_sim_collect(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
                      float scale, const float* thr, int col_offset, int cap, int32_t* count, float* cand_val,
                      int32_t* cand_idx, void* stream);
+/* laff_sim_collect that ALSO counts the rank of every query's ground truth in the same sweep (sgt_raw / gt_global as in
+ * laff_sim_rank_topk; rank_count[i] = number of local videos ranked above the ground truth, zeroed by the call), for a
+ * caller that writes the long lists and the metrics of one query set (predictor.py:232-259): one pass, not two. */
+int laff_sim_collect_rank(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                          float scale, const float* thr, int col_offset, int cap, int32_t* count, float* cand_val,
+                          int32_t* cand_idx, const float* sgt_raw, const int32_t* gt_global, int32_t* rank_count,
+                          void* stream);
 
 /* Diagnostics: run the GEMM mainloop of laff_sim_* with a null epilogue (mode 1 drains TMEM, mode < 0 only sets the
  * TMA L2 eviction hints used by later laff_sim_* calls; hint codes 0 default, 1 normal, 2 evict-first, 3 evict-last). */

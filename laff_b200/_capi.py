@@ -91,6 +91,7 @@ SIGNATURES = {
     "laff_cast_pad_16": (_i, [_vp, _ll, _i, _ll, _i, _vp, _i, _ll, _vp]),
     "laff_sim_dense": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _f, _vp, _ll, _vp]),
     "laff_sim_collect": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _f, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "laff_sim_collect_rank": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _f, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "laff_debug_gemm": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),
     "laff_sim_gt_workspace_bytes": (_sz, [_i, _i]),
     "laff_sim_gt_scores": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -226,6 +226,9 @@ struct EpiRank {
 // to the query's candidate list.  With a threshold a little below the k-th best (estimated from a sample of the
 // gallery) ~2k of the V scores survive, so the Q x V matrix is never written and the exact top-k is a sort of the
 // survivors.  count may end above cap (list truncated) or below k: the caller checks both and falls back.
+// Optionally (sgt != nullptr) the same pass also counts the ground truth's rank exactly as EpiRank does (compare-and-count
+// against the raw score of the ground truth + the tie rule), so a caller that wants the long lists AND the ranks
+// (predictor.py:232-259: metrics and t2v.pkl of one query set) sweeps the gallery once instead of twice.
 struct EpiCollect {
   struct Params {
     const float* thr;     // [M] threshold on the scaled score
@@ -236,18 +239,51 @@ struct EpiCollect {
     int M, N;
     int col_offset;
     float scale;
+    const float* sgt;     // optional [M]: raw accumulator of (i, gt_i)
+    const int32_t* gt;    // optional [M]: global gallery index of the ground truth
+    int32_t* rank_count;  // optional [M] += number of local videos ranked above the ground truth
   };
   static constexpr int kSmemBytes = 0;
   Params p;
   float t;
+  float sg;
+  int g, cnt;
   __device__ EpiCollect(const Params& p_, uint8_t*, int) : p(p_) {}
-  __device__ __forceinline__ void unit_begin(int row, const Unit&) { t = row < p.M ? __ldg(p.thr + row) : INFINITY; }
-  __device__ __forceinline__ void unit_end(int, const Unit&) {}
+  __device__ __forceinline__ void unit_begin(int row, const Unit&) {
+    t = row < p.M ? __ldg(p.thr + row) : INFINITY;
+    cnt = 0;
+    sg = INFINITY;
+    g = -1;
+    if (p.sgt != nullptr && row < p.M) {
+      sg = __ldg(p.sgt + row);
+      g = __ldg(p.gt + row);
+    }
+  }
+  __device__ __forceinline__ void unit_end(int row, const Unit&) {
+    if (p.sgt != nullptr && row < p.M && cnt) atomicAdd(p.rank_count + row, cnt);
+  }
   __device__ __forceinline__ void chunk(const uint32_t (&r)[32], int row, int col0) {
     uint32_t hit = 0;
+    const uint32_t valid = (col0 + 32 > p.N) ? ((col0 >= p.N) ? 0u : (0xffffffffu >> (32 - (p.N - col0)))) : 0xffffffffu;
+    if (p.sgt != nullptr) {   // rank of the ground truth: #{v > s_gt} + #{v == s_gt, index > gt} (columns past the gallery excluded)
+      uint32_t above = 0, tie = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float v = __uint_as_float(r[j]);
+        above |= (v > sg) ? (1u << j) : 0u;
+        tie |= (v == sg) ? (1u << j) : 0u;
+      }
+      cnt += __popc(above & valid);
+      tie &= valid;
+      while (tie) {
+        const int j = __ffs(tie) - 1;
+        tie &= tie - 1;
+        if (col0 + j + p.col_offset > g) ++cnt;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[j]) * p.scale >= t) ? (1u << j) : 0u;
-    if (col0 + 32 > p.N) hit &= (col0 >= p.N) ? 0u : (0xffffffffu >> (32 - (p.N - col0)));  // columns past the gallery read as zero
+    hit &= valid;  // columns past the gallery read as zero
     if (hit == 0) return;
     const int n = __popc(hit);
     const int base = atomicAdd(p.count + row, n);
@@ -702,9 +738,19 @@ int laff_debug_gemm(const void* q, const void* g, int Q, int V, int D, long long
 int laff_sim_collect(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
                      float scale, const float* thr, int col_offset, int cap, int32_t* count, float* cand_val,
                      int32_t* cand_idx, void* stream) {
+  return laff_sim_collect_rank(q, g, Q, V, D, ldq, ldg, dtype, scale, thr, col_offset, cap, count, cand_val, cand_idx, nullptr,
+                               nullptr, nullptr, stream);
+}
+
+int laff_sim_collect_rank(const void* q, const void* g, int Q, int V, int D, long long ldq, long long ldg, int dtype,
+                          float scale, const float* thr, int col_offset, int cap, int32_t* count, float* cand_val,
+                          int32_t* cand_idx, const float* sgt_raw, const int32_t* gt_global, int32_t* rank_count, void* stream) {
   LAFF_REQUIRE(q && g && thr && count && cand_val && cand_idx, LAFF_EINVAL, "laff_sim_collect: null pointer");
   LAFF_REQUIRE(cap > 0, LAFF_EINVAL, "laff_sim_collect: cap must be positive (got %d)", cap);
+  LAFF_REQUIRE((sgt_raw != nullptr) == (gt_global != nullptr) && (sgt_raw != nullptr) == (rank_count != nullptr), LAFF_EINVAL,
+               "laff_sim_collect_rank: sgt_raw, gt_global and rank_count go together");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rank_count) LAFF_CUDA(cudaMemsetAsync(rank_count, 0, sizeof(int32_t) * static_cast<size_t>(Q), st));
   const Tuning t = get_tuning();
   GemmOperands op;
   int rc = prepare_operands(&op, q, g, Q, V, D, ldq, ldg, dtype, t.cta_group);
@@ -724,7 +770,7 @@ int laff_sim_collect(const void* q, const void* g, int Q, int V, int D, long lon
       if (rc) return rc;
     }
     const Sched s = make_sched(Q, cols, oc.cg, t.chunk_tiles, t.m_group, 0);
-    EpiCollect::Params ep{thr, count, cand_val, cand_idx, cap, Q, cols, col_offset + c0, scale};
+    EpiCollect::Params ep{thr, count, cand_val, cand_idx, cap, Q, cols, col_offset + c0, scale, sgt_raw, gt_global, rank_count};
     rc = launch_gemm<EpiCollect>(oc, s, ep, st);
     if (rc) return rc;
   }

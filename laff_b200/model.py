@@ -875,7 +875,8 @@ class W2VVPP(nn.Module):
             self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
             self._frame_grads = {}
             self._graph, self._graphs = None, {}
-        txt, vis = self._stage_train_inputs(train_data, dev)
+        with ops.nvtx_range("train_stage_inputs"):
+            txt, vis = self._stage_train_inputs(train_data, dev)
         sig = (precision,) + tuple((k, tuple(v.shape)) for k, v in list(txt.items()) + list(vis.items()))
         g = self._graphs.get(sig) if self._graphs else None
         self._graph = g
@@ -885,10 +886,12 @@ class W2VVPP(nn.Module):
                 g["txt"][k].copy_(v, non_blocking=True)
             for k, v in vis.items():
                 g["vis"][k].copy_(v, non_blocking=True)
-            g["graph"].replay()
+            with ops.nvtx_range("train_step_graph_replay"):
+                g["graph"].replay()
             loss = g["loss"].clone()
         else:
-            loss = self._train_step_device(txt, vis, precision)
+            with ops.nvtx_range("train_step_eager"):
+                loss = self._train_step_device(txt, vis, precision)
             if self.use_cuda_graph and self.iters >= 3 and all(st.capturable for st in self._steps.values()):
                 if len(self._graphs) >= 16:  # caption lengths vary: keep the graphs of the most recent shapes
                     self._graphs.pop(next(iter(self._graphs)))

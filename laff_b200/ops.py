@@ -8,6 +8,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Sequence
 
+import os
+
 import numpy as np
 import torch
 
@@ -146,10 +148,12 @@ def sim_dense(q: torch.Tensor, g: torch.Tensor, scale: float = 1.0, out: Optiona
     return out
 
 
-def sim_collect(q: torch.Tensor, g: torch.Tensor, thr: torch.Tensor, cap: int, scale: float = 1.0, col_offset: int = 0):
+def sim_collect(q: torch.Tensor, g: torch.Tensor, thr: torch.Tensor, cap: int, scale: float = 1.0, col_offset: int = 0,
+                sgt_raw: Optional[torch.Tensor] = None, gt_global: Optional[torch.Tensor] = None):
     """Candidates of long ranked lists without the dense matrix (laff_sim_collect): every score scale * <q_i, g_j> >=
     thr[i], unordered.  -> (count int32 [Q], cand_val fp32 [Q, cap], cand_idx int32 [Q, cap] global indices, -inf / -1
-    in unused slots).  count[i] > cap means query i's list was truncated."""
+    in unused slots).  count[i] > cap means query i's list was truncated.  With sgt_raw / gt_global (as for
+    sim_rank_topk) the same sweep also counts the ground truth's local rank: a fourth result, int32 [Q]."""
     q, g = _check_operands(q, g)
     Q, D = q.shape
     _need_cuda(thr)
@@ -159,6 +163,14 @@ def sim_collect(q: torch.Tensor, g: torch.Tensor, thr: torch.Tensor, cap: int, s
     count = torch.empty(Q, dtype=torch.int32, device=q.device)
     cv = torch.empty((Q, cap), dtype=torch.float32, device=q.device)
     ci = torch.empty((Q, cap), dtype=torch.int32, device=q.device)
+    if sgt_raw is not None:
+        _need_cuda(sgt_raw, gt_global)
+        sgt_raw, gt_global = sgt_raw.float().contiguous(), gt_global.to(torch.int32).contiguous()
+        rank = torch.empty(Q, dtype=torch.int32, device=q.device)
+        _capi.call("laff_sim_collect_rank", _ptr(q), _ptr(g), Q, g.shape[0], D, q.stride(0), g.stride(0), _DT[q.dtype], float(scale),
+                   _ptr(thr), int(col_offset), int(cap), _ptr(count), _ptr(cv), _ptr(ci), _ptr(sgt_raw), _ptr(gt_global), _ptr(rank),
+                   _stream(q))
+        return count, cv, ci, rank
     _capi.call("laff_sim_collect", _ptr(q), _ptr(g), Q, g.shape[0], D, q.stride(0), g.stride(0), _DT[q.dtype], float(scale),
                _ptr(thr), int(col_offset), int(cap), _ptr(count), _ptr(cv), _ptr(ci), _stream(q))
     return count, cv, ci
@@ -472,6 +484,25 @@ def frame_pool(frames: torch.Tensor, att_weight: torch.Tensor, att_bias: float, 
 def _csr(offsets: torch.Tensor, ids: torch.Tensor):
     _need_cuda(offsets, ids)
     return offsets.to(torch.int64).contiguous(), ids.to(torch.int32).contiguous()
+
+
+class nvtx_range:
+    """NVTX range around a stage of the hot path (SURVEY §5 tracing row): shows up in nsys / ncu timelines as
+    laff/<name>; a no-op costing well under a microsecond when no profiler is attached.  LAFF_NVTX=0 disables it."""
+    enabled = os.environ.get("LAFF_NVTX", "1") != "0"
+
+    def __init__(self, name: str):
+        self.name = "laff/" + name
+
+    def __enter__(self):
+        if self.enabled and torch.cuda.is_available():
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled and torch.cuda.is_available():
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 class sm_limit:

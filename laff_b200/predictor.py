@@ -240,11 +240,13 @@ def evaluate_and_write_ranked(pred, txt_ids, vis_ids, output_dir, predict_result
     os.makedirs(output_dir, exist_ok=True)
     out = {}
     dev = pred.q16.device
+    k500 = writer_topk(len(vis_ids), 500)
     if with_ground_truth:
         gt = torch.from_numpy(gt_index(txt_ids, vis_ids)).to(dev)
-        res = pred.search(gt, 10)
-        out["t2v"] = _metrics_tuple(res.metrics)
-        out["rank0"] = res.rank0
+        # ONE sweep: the candidates of the top-500 lists and the exact rank of every ground truth (laff_sim_collect_rank)
+        vals, idx, rank0 = pred.ranked_lists(max(k500, 1), gt_global=gt)
+        out["t2v"] = _metrics_tuple(ops.rank_metrics(rank0))
+        out["rank0"] = rank0
         names = ("r1", "r5", "r10", "medr", "meanr", "mir", "mAP")
         vals = dict(zip(names, out["t2v"]))
         print(" * Text to video:")
@@ -252,8 +254,8 @@ def evaluate_and_write_ranked(pred, txt_ids, vis_ids, output_dir, predict_result
         print(" * medr, meanr, mir: {}".format([round(vals["medr"], 3), round(vals["meanr"], 3), round(vals["mir"], 3)]))
         write_to_predict_result_file(os.path.join(os.path.dirname(predict_result_file), "TextToVideo", os.path.basename(predict_result_file)),
                                      model_path, checkpoint, out["t2v"])
-    k500 = writer_topk(len(vis_ids), 500)
-    vals, idx = pred.ranked_lists(max(k500, 1 if with_ground_truth else writer_topk(len(vis_ids), 2000)))
+    else:
+        vals, idx = pred.ranked_lists(max(k500, writer_topk(len(vis_ids), 2000)))
     vals, idx = vals.cpu().numpy(), idx.cpu().numpy()
     txt2video_write_to_file(None, (vals, idx), vis_ids, txt_ids, None, pkl_saved_file=os.path.join(output_dir, "t2v.pkl"),
                             txt_loader=txt_loader, Threshold=500, captions=captions)

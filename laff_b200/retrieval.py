@@ -79,23 +79,33 @@ class CudaBackend:
             return None
         return n_s, r
 
-    def dense_topk(self, q16, g16, k, scale, col_offset):
+    lists_with_rank = True   # dense_topk(..., sgt, gt) can count the ground truth's rank in the same sweep
+
+    def dense_topk(self, q16, g16, k, scale, col_offset, sgt=None, gt=None):
         """Ranked list of the k best local videos per query (k <= 2048).  Large shards: a threshold just below the k-th
         best is read off a sample of the shard, one sweep keeps the scores above it (laff_sim_collect, ~2k of V per
         query; no Q x V matrix) and the survivors are sorted; if a query ends with fewer than k or more than the slot
         count (a gallery whose first rows are not representative) the chunk is redone densely.  Small shards: dense
-        scores of 256-query chunks + laff_topk_dense.  Both give the tie-rule order of the full row."""
+        scores of 256-query chunks + laff_topk_dense.  Both give the tie-rule order of the full row.
+        With sgt (raw ground-truth scores) and gt (global ground-truth indices) a third result is returned: the local
+        count of videos ranked above the ground truth, taken in the same sweep on the threshold path (None on the dense
+        path: the caller then counts with a rank-only sweep)."""
         V = g16.shape[0]
+        want_rank = sgt is not None
         plan = self.collect_plan(V, k)
         if plan is None:
-            return self._dense_topk(q16, g16, k, scale, col_offset)
+            out = self._dense_topk(q16, g16, k, scale, col_offset)
+            return out + (None,) if want_rank else out
         n_s, r = plan
         sv, _ = ops.topk_dense(ops.sim_dense(q16, g16[:n_s], scale), r)
         thr = sv[:, r - 1].contiguous()
-        count, cv, ci = ops.sim_collect(q16, g16, thr, self.collect_cap, scale, col_offset)
+        got = ops.sim_collect(q16, g16, thr, self.collect_cap, scale, col_offset, sgt_raw=sgt, gt_global=gt)
+        count, cv, ci = got[:3]
         if bool(((count < k) | (count > self.collect_cap)).any()):       # one host read per chunk
-            return self._dense_topk(q16, g16, k, scale, col_offset)
-        return ops.topk_dense(cv, k, idx_in=ci)
+            out = self._dense_topk(q16, g16, k, scale, col_offset)
+            return out + (got[3],) if want_rank else out                 # the rank count does not depend on the lists
+        out = ops.topk_dense(cv, k, idx_in=ci)
+        return out + (got[3],) if want_rank else out
 
     def merge_lists(self, vals, idx, k):
         """vals/idx [Q, n] candidates carrying global indices (-1 = empty) -> the k best by the tie rule."""
@@ -257,24 +267,48 @@ class GalleryIndex:
     def search(self, q16: torch.Tensor, gt_global: torch.Tensor, k: int = 10) -> SearchResult:
         """q16 [Q, H*d_h] 16-bit unit-norm query embeddings (replicated on every rank), gt_global int [Q]."""
         gt_global = gt_global.to(torch.int32)
-        sgt = self._gt_scores(q16, gt_global)
-        count, tv, ti = self._merge(*self._sweep(q16, sgt, gt_global, k), k)
-        return SearchResult(count, tv, ti, self.backend.metrics(count))
+        with ops.nvtx_range("gt_scores"):
+            sgt = self._gt_scores(q16, gt_global)
+        with ops.nvtx_range("sweep_rank_topk"):
+            part = self._sweep(q16, sgt, gt_global, k)
+        with ops.nvtx_range("merge_metrics"):
+            count, tv, ti = self._merge(*part, k)
+            return SearchResult(count, tv, ti, self.backend.metrics(count))
 
-    def ranked_lists(self, q16: torch.Tensor, k: int, query_chunk: int = 2048):
+    def ranked_lists(self, q16: torch.Tensor, k: int, query_chunk: int = 2048, gt_global: Optional[torch.Tensor] = None):
         """The k best videos of every query over the whole (sharded) gallery, k up to 2048: the lists the reference
         writes to id.sent.score.txt (top 2000) and t2v.pkl (top 500), predictor.py:53-88.  Queries are processed
         `query_chunk` at a time (the backend bounds its own scratch: candidate lists, or dense 256-query pieces); with W > 1 shards
         every rank extracts its local lists and one all_gather + merge per chunk yields the global ones.
-        Returns (values fp32 [Q, k], global indices int32 [Q, k]) on the device, -inf / -1 beyond the gallery size."""
+        Returns (values fp32 [Q, k], global indices int32 [Q, k]) on the device, -inf / -1 beyond the gallery size.
+        With gt_global (int [Q]) a third result: rank0 int32 [Q], the exact rank of every query's ground truth -- counted
+        in the SAME sweep that collects the list candidates, so metrics + lists of a query set cost one pass."""
         be = self.backend
         scale = 1.0 / self.heads
         Q = q16.shape[0]
         n_local = self.hi - self.lo
-        out_v, out_i = [], []
+        out_v, out_i, out_r = [], [], []
+        want_rank = gt_global is not None
+        if want_rank:
+            gt_global = gt_global.to(torch.int32)
+            sgt_all = self._gt_scores(q16, gt_global)
         for lo in range(0, Q, query_chunk):
             qc = q16[lo:lo + query_chunk]
-            if n_local > 0:
+            if want_rank:
+                gc, sc = gt_global[lo:lo + query_chunk], sgt_all[lo:lo + query_chunk]
+                if n_local > 0 and getattr(be, "lists_with_rank", False):
+                    tv, ti, cnt = be.dense_topk(qc, self.g16, k, scale, self.lo, sgt=sc, gt=gc)
+                    if cnt is None:
+                        cnt = be.rank_topk(qc, self.g16, sc, gc, 0, scale, self.lo)[0]
+                elif n_local > 0:
+                    tv, ti = be.dense_topk(qc, self.g16, k, scale, self.lo)
+                    cnt = be.rank_topk(qc, self.g16, sc, gc, 0, scale, self.lo)[0]
+                else:
+                    cnt = torch.zeros(qc.shape[0], dtype=torch.int32, device=q16.device)
+                out_r.append(self._all_reduce(cnt.to(torch.int32)))
+            if n_local > 0 and want_rank:
+                pass
+            elif n_local > 0:
                 tv, ti = be.dense_topk(qc, self.g16, k, scale, self.lo)
             else:
                 tv = torch.full((qc.shape[0], k), float("-inf"), dtype=torch.float32, device=q16.device)
@@ -288,8 +322,10 @@ class GalleryIndex:
             out_v.append(tv)
             out_i.append(ti)
         if not out_v:
-            return (torch.empty((0, k), dtype=torch.float32, device=q16.device),
-                    torch.empty((0, k), dtype=torch.int32, device=q16.device))
+            empty = (torch.empty((0, k), dtype=torch.float32, device=q16.device), torch.empty((0, k), dtype=torch.int32, device=q16.device))
+            return empty + (torch.empty(0, dtype=torch.int32, device=q16.device),) if want_rank else empty
+        if want_rank:
+            return torch.cat(out_v), torch.cat(out_i), torch.cat(out_r)
         return torch.cat(out_v), torch.cat(out_i)
 
 
@@ -311,8 +347,9 @@ class RankedScores:
     def search(self, gt_global, k: int = 10) -> SearchResult:
         return self.index.search(self.q16, torch.as_tensor(gt_global).to(self.q16.device), k)
 
-    def ranked_lists(self, k: int, query_chunk: int = 2048):
-        return self.index.ranked_lists(self.q16, k, query_chunk)
+    def ranked_lists(self, k: int, query_chunk: int = 2048, gt_global=None):
+        gt = None if gt_global is None else torch.as_tensor(gt_global).to(self.q16.device)
+        return self.index.ranked_lists(self.q16, k, query_chunk, gt_global=gt)
 
     def rows(self, lo: int, hi: int) -> torch.Tensor:
         """Dense fp32 scores of queries [lo, hi) against this rank's shard, on the device."""
@@ -357,7 +394,8 @@ class Retriever:
         idx = self.index
         W = idx.world_size
         if W == 1:
-            _, q16 = self.txt_net.encode(caption_feat_dict, out16_dtype=self.out16_dtype, precision=self.precision)
+            with ops.nvtx_range("fuse_queries"):
+                _, q16 = self.txt_net.encode(caption_feat_dict, out16_dtype=self.out16_dtype, precision=self.precision)
             return q16.reshape(q16.shape[0], -1)
         if total is None:
             Q = next(iter(caption_feat_dict.values())).shape[0]
@@ -372,10 +410,12 @@ class Retriever:
         D = idx.g16.shape[1]
         buf = torch.zeros((per, D), dtype=self.out16_dtype, device=idx.g16.device)
         if hi > lo:
-            _, q16 = self.txt_net.encode(part, out16_dtype=self.out16_dtype, precision=self.precision)
+            with ops.nvtx_range("fuse_queries"):
+                _, q16 = self.txt_net.encode(part, out16_dtype=self.out16_dtype, precision=self.precision)
             buf[: hi - lo] = q16.reshape(hi - lo, -1)
         out = torch.empty((W * per, D), dtype=buf.dtype, device=buf.device)
-        dist.all_gather_into_tensor(out, buf, group=group if group is not None else idx.group)
+        with ops.nvtx_range("all_gather_queries"):
+            dist.all_gather_into_tensor(out, buf, group=group if group is not None else idx.group)
         return out[:Q]
 
     @torch.no_grad()
@@ -427,8 +467,11 @@ class Retriever:
     # ------------------------------------------------------------------------------------------------------------
     # pipelined path
     # ------------------------------------------------------------------------------------------------------------
-    reserve_sms = 2      # SMs left to the side streams while a sweep runs (the sweep takes the rest)
-    side_max_ctas = 1    # CTAs of an NCCL kernel on the side communicators (one per reserved SM and side stream)
+    # Measured at 8 GPUs (profiles/r02_scale_experiments.md): the pre-stage collective, the post-stage collective and one
+    # 2-CTA compute cluster must fit the reserved SMs TOGETHER -- a post-stage all-gather spins until the slowest rank's
+    # sweep is done, and if it leaves no SM for the pre stage, every rank's next sweep waits.  2 + 2 + 2 = 6.
+    reserve_sms = 6      # SMs left to the side streams while a sweep runs with W > 1 ranks (W = 1: none, see _pipe)
+    side_max_ctas = 2    # CTAs of an NCCL kernel on the side communicators
 
     def _side_group(self):
         """A communicator over the index's ranks for one side stream; NCCL kernels limited to `side_max_ctas` CTAs so that
@@ -460,7 +503,8 @@ class Retriever:
             P.pre, P.post, P.copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             P.sweep = torch.cuda.Stream(dev, priority=-1)        # a sweep launch gets freed SMs before queued side work
             total = torch.cuda.get_device_properties(dev).multi_processor_count
-            r = max(0, min(int(self.reserve_sms), total - 2))
+            # one rank: no collectives, the side stages are short kernels that fill the gaps between sweep launches
+            r = 0 if idx.world_size == 1 and not getattr(self, "reserve_on_one_gpu", False) else max(0, min(int(self.reserve_sms), total - 2))
             r += r % 2                                           # CTA pairs
             P.side_sms, P.sweep_sms = (r, total - r) if r > 0 else (0, 0)
         self._pipe_state = P
@@ -490,8 +534,8 @@ class Retriever:
         first = next(iter(caption_feat_dict.values()))
         Q = first.shape[0]
         cuda = dev.type == "cuda"
-        if pieces is None:
-            pieces = max(1, min(4, (Q + 2559) // 2560))          # the sweep's own row groups (10 row tiles of 256)
+        if pieces is None:                                       # the sweep's own row groups (10 row tiles of 256), at most 4;
+            pieces = max(1, min(4 if idx.world_size == 1 else 2, (Q + 2559) // 2560))   # with collectives per piece: 2
         pieces = max(1, min(int(pieces), max(1, Q)))
         per = (Q + pieces - 1) // pieces
         per = (per + 255) // 256 * 256 if per > 256 else per     # whole row tiles per piece
@@ -529,7 +573,8 @@ class Retriever:
                         t.record_stream(P.pre)
                 q16 = self.encode_queries(part, total=n, group=P.g_pre) if idx.world_size > 1 else self.encode_queries(part)
                 g32 = g.to(torch.int32)
-                sgt = idx._gt_scores(q16, g32, group=P.g_pre)
+                with ops.nvtx_range("gt_scores"):
+                    sgt = idx._gt_scores(q16, g32, group=P.g_pre)
                 if cuda:
                     ready = torch.cuda.Event()
                     ready.record(P.pre)
@@ -538,7 +583,8 @@ class Retriever:
                     P.sweep.wait_event(ready)
                     for t in (q16, g32, sgt):
                         t.record_stream(P.sweep)
-                count, tv, ti = idx._sweep(q16, sgt, g32, k)
+                with ops.nvtx_range("sweep_rank_topk"):
+                    count, tv, ti = idx._sweep(q16, sgt, g32, k)
                 if cuda:
                     swept = torch.cuda.Event()
                     swept.record(P.sweep)
@@ -547,7 +593,8 @@ class Retriever:
                     P.post.wait_event(swept)
                     for t in (count, tv, ti):
                         t.record_stream(P.post)
-                outs.append(idx._merge(count, tv, ti, k, group=P.g_post))
+                with ops.nvtx_range("merge"):
+                    outs.append(idx._merge(count, tv, ti, k, group=P.g_post))
         with stream(P.post), ops.sm_limit(P.side_sms) if cuda else contextlib.nullcontext():
             rank0 = outs[0][0] if len(outs) == 1 else torch.cat([o[0] for o in outs])
             tv = outs[0][1] if len(outs) == 1 else torch.cat([o[1] for o in outs])

@@ -277,6 +277,22 @@ def test_ranked_lists_threshold_path_equals_dense_path(monkeypatch):
     rv2, ri2 = O.tie_rule_topk(s, 900)
     assert np.array_equal(li2.cpu().numpy().astype(np.int64), ri2) and np.array_equal(lv2.cpu().numpy(), rv2)
     assert n_collect < 12
+    # lists AND ranks of the ground truth from ONE sweep (laff_sim_collect_rank): same lists, ranks equal to the fused rank
+    # sweep's and to the oracle's tie rule on the device's own scores -- on the threshold path, through the dense fallback
+    # (k = 900) and for ground truths tied with other videos (the duplicates planted above)
+    gt_t = torch.from_numpy(gt).cuda().to(torch.int32)
+    ref = idx.search(q16, gt_t, 10)
+    for kk in (k, 900):
+        lv3, li3, r3 = idx.ranked_lists(q16, kk, query_chunk=64, gt_global=gt_t)
+        assert torch.equal(r3, ref.rank0) and torch.equal(li3[:, :10], ref.topk_idx)
+        np.testing.assert_array_equal(r3.cpu().numpy(), O.tie_rule_rank(s, gt))
+    assert torch.equal(li3, li2) and torch.equal(lv3, lv2)
+    cnt4, _, _, rk4 = ops.sim_collect(q16, g16[:777], thr, 1024, 1.0 / H, 100, sgt_raw=ops.sim_gt_scores(q16, g16, gt_t), gt_global=gt_t)
+    sub = s[:, :777]
+    sg = s[np.arange(Q), gt][:, None]
+    cols = np.arange(777)[None, :] + 100
+    want_rank = ((sub > sg) | ((sub == sg) & (cols > gt[:, None]))).sum(1)   # a shard that starts at global column 100, ragged last tile
+    np.testing.assert_array_equal(rk4.cpu().numpy(), want_rank)
 
 
 @pytest.mark.parametrize("V", [1000000])

@@ -94,11 +94,14 @@ def _worker(rank, world, port, out):
         idx = GalleryIndex(torch.from_numpy(g[lo:hi]).to(torch.bfloat16), g.shape[0], H, rank, world, backend=NumpyBackend())
         res = idx.search(torch.from_numpy(q).to(torch.bfloat16), torch.from_numpy(gt), k=7)
         lv, li = idx.ranked_lists(torch.from_numpy(q).to(torch.bfloat16), k=150, query_chunk=20)
+        # lists + exact ranks in one call (one sweep on the CUDA backend; a rank-only sweep per chunk on backends without it)
+        lv3, li3, r3 = idx.ranked_lists(torch.from_numpy(q).to(torch.bfloat16), k=150, query_chunk=20, gt_global=torch.from_numpy(gt))
+        lists_ok = torch.equal(r3, res.rank0) and torch.equal(li3, li) and torch.equal(lv3, lv)
         # query fusion is sharded too: every rank encodes 1/W of the queries and the slices are all-gathered; a host
         # caller may hand over only its own slice (total=Q) -- both must reproduce the unsharded embeddings, also when
         # the last ranks get short or empty slices (Q = 5, W = 3)
         retr = Retriever(_StubTxtNet(), idx)
-        enc_ok = True
+        enc_ok = bool(lists_ok)
         for Qs in (q.shape[0], 5, 1):
             feats = {"x": torch.from_numpy(q[:Qs]).clone()}
             want = _StubTxtNet().encode(feats, out16_dtype=torch.bfloat16)[1].reshape(Qs, -1)
