@@ -428,9 +428,15 @@ def run_ours(args, rank, world, local_rank):
     with torch.no_grad():
         _, q16 = txt_net.encode(feats_dev, out16_dtype=dt16, precision=args.precision)
     sigma = synth.sigma_for_recall(V, D)
-    lo, hi = shard_bounds(V, world, rank)
+    # shard sizes: equal, or (--balance 1, W > 1) proportional to every GPU's sustained sweep rate measured here -- the
+    # GPUs of one box settle at different clocks under the power cap and a step is as slow as its slowest shard
+    weights = None
+    if world > 1 and args.balance:
+        from laff_b200.retrieval import calibrate_rank_weights
+        weights = calibrate_rank_weights(dev, world, seconds=args.balance_seconds)
+    lo, hi = shard_bounds(V, world, rank, weights)
     g16 = build_gallery_shard(lo, hi, q16.reshape(Q, D), gt_dev, sigma, dev, dt16)
-    index = GalleryIndex(g16, V, HEADS, rank, world)
+    index = GalleryIndex(g16, V, HEADS, rank, world, weights=weights)
     retr = Retriever(txt_net, index)
     retr.reserve_sms, retr.side_max_ctas = args.reserve_sms, args.side_ctas
     pieces = args.pieces if args.pieces > 0 else None
@@ -536,7 +542,12 @@ def run_ours(args, rank, world, local_rank):
 
     times = torch.tensor([total_ms, e2e_ms, sweeps_per_step * sum(sweep_ms) / max(1, len(sweep_ms)), modeb_ms, modeb_fuse_ms],
                          dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        mine = times[2:3].clone()
+        allr = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = [round(float(x), 4) for x in allr.cpu()]
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, sweep_avg_ms, modeb_ms, modeb_fuse_ms = [float(x) for x in times.cpu()]
 
@@ -547,7 +558,8 @@ def run_ours(args, rank, world, local_rank):
     value = Q / (ms_per_step * 1e-3)
     e2e_value = Q / (e2e_ms / args.steps * 1e-3)
     n_local = hi - lo
-    achieved = Q * n_local * FLOP_PER_PAIR / (sweep_avg_ms * 1e-3) / 1e12
+    # per-GPU rate: the average shard (V / W videos) over the slowest rank's sweep time
+    achieved = Q * (V / world) * FLOP_PER_PAIR / (sweep_avg_ms * 1e-3) / 1e12
     # summed over the ranks: every rank copies its 1/W slice of the query features and the whole ground-truth vector
     h2d = feature_bytes(feats_host) + world * gt_host.numel() * 4
     d2h = world * (Q * 4 + Q * TOPK * 8 + 8 * 8)   # every rank reads the (replicated) ranks, top-k lists and metrics back
@@ -558,7 +570,10 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": "C5: %d queries (gru1024+w2v500 FC -> 4096, bow3981 as CSR token ids -> gather-sum FC, CLIP512 tiled, LAFF pooling, 8x512) "
                                "ranked against a %d-video gallery of fused embeddings resident in HBM: similarity "
                                "sweep + exact rank + top-%d + R@K/MedR" % (Q, V, TOPK),
-                   "queries": Q, "gallery": V, "gallery_per_gpu": n_local, "topk": TOPK, "sharding": "gallery rows / %d" % world,
+                   "queries": Q, "gallery": V, "gallery_per_gpu": n_local, "topk": TOPK,
+                   "sharding": "gallery rows / %d" % world if weights is None else
+                               "gallery rows over %d ranks in proportion to each GPU's sustained sweep rate (calibrated at start-up, "
+                               "%.1f s per rank): fractions %s" % (world, args.balance_seconds, [round(w, 4) for w in weights]),
                    "l2": "inputs exceed L2 (gallery shard %.1f GB)" % (n_local * D * 2 / 1e9),
                    "recall": {"r1": metrics[0], "r5": metrics[1], "r10": metrics[2], "medr": metrics[3]},
                    "pipeline": None if not args.pipeline else {
@@ -584,7 +599,8 @@ def run_ours(args, rank, world, local_rank):
                                                      if args.pipeline and args.reserve_sms > 0 else ""),
                      "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tensor_tflops"],
                      "peak_source": pk["source"] + " (bf16 dense sustained; fp16 and bf16 operands share the kind::f16 MMA rate)",
-                     "flop_per_launch": Q * n_local * FLOP_PER_PAIR, "avg_launch_ms": sweep_avg_ms,
+                     "flop_per_launch": Q * (V / world) * FLOP_PER_PAIR, "avg_launch_ms": sweep_avg_ms,
+                     "avg_launch_ms_per_rank": per_rank,
                      "traffic": recorded_traffic() if world == 1 and V == V_FULL and Q == Q_FULL else None,
                      "traffic_source": "recorded: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
                                        "sweep (profiles/roofline_traffic.json), not measured in this run"},
@@ -621,6 +637,8 @@ def main():
     ap.add_argument("--videos", type=int, default=V_FULL)
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--balance", type=int, default=0, help="1: size the gallery shards by each GPU's measured sweep rate (W > 1)")
+    ap.add_argument("--balance-seconds", type=float, default=2.0)
     ap.add_argument("--pipeline", type=int, default=1, help="1: Retriever.submit (staged, overlapping steps); 0: serial Retriever.rank")
     ap.add_argument("--pieces", type=int, default=0,
                     help="query pieces per step of the pipelined path (0 = one per 2560 queries, at most 4 on one GPU and 2 with several)")

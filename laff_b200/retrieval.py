@@ -28,11 +28,69 @@ import torch.distributed as dist
 from . import ops
 
 
-def shard_bounds(V: int, world_size: int, rank: int) -> Tuple[int, int]:
-    """Contiguous row range of the gallery held by `rank` (the last shards may be short or empty)."""
-    per = (V + world_size - 1) // world_size
-    lo = min(V, rank * per)
-    return lo, min(V, lo + per)
+def shard_bounds(V: int, world_size: int, rank: int, weights=None, align: int = 256) -> Tuple[int, int]:
+    """Contiguous row range of the gallery held by `rank` (the last shards may be short or empty).
+
+    weights (one positive number per rank, e.g. from calibrate_rank_weights): shard sizes proportional to them instead
+    of equal, cut at multiples of `align` rows (whole column tiles of the sweep) -- the GPUs of one box do not sustain
+    the same clock under the power cap, and a step is as slow as its slowest shard."""
+    if weights is None:
+        per = (V + world_size - 1) // world_size
+        lo = min(V, rank * per)
+        return lo, min(V, lo + per)
+    w = [max(float(x), 0.0) for x in weights]
+    if len(w) != world_size or sum(w) <= 0:
+        raise ValueError("shard_bounds: need %d positive weights, got %r" % (world_size, weights))
+    cuts, acc = [0], 0.0
+    for x in w[:-1]:
+        acc += x / sum(w)
+        c = int(round(V * acc / align)) * align
+        cuts.append(min(V, max(cuts[-1], c)))
+    cuts.append(V)
+    return cuts[rank], cuts[rank + 1]
+
+
+@torch.no_grad()
+def calibrate_rank_weights(device, world_size: int, group=None, seconds: float = 1.5, heads: int = 8, dim: int = 4096,
+                           clamp: float = 0.15):
+    """Relative sweep throughput of every rank's GPU under sustained load, for weighted gallery shards.  Every rank runs
+    the similarity sweep (2560 queries x 131 072 synthetic videos, one kernel launch of ~2.7 ms) back to back for
+    `seconds` -- long enough for the power cap to settle -- and times the second half; weights = 1 / time, clamped to
+    +-`clamp` around their mean (a guard against a noisy measurement), identical on all ranks after one all_gather."""
+    if world_size == 1:
+        return [1.0]
+    Q, V = 2560, 131072
+    gen = torch.Generator(device=device).manual_seed(99)
+    g = torch.randn(V, dim, generator=gen, device=device).to(torch.float16)
+    q = torch.randn(Q, dim, generator=gen, device=device).to(torch.float16)
+    gt = torch.zeros(Q, dtype=torch.int32, device=device)
+    sgt = torch.full((Q,), 1e30, dtype=torch.float32, device=device)
+    ws = None
+    import time
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    t_end = time.perf_counter() + seconds / 2
+    while time.perf_counter() < t_end:                      # warm the clocks into their sustained state
+        for _ in range(8):
+            ops.sim_rank_topk(q, g, sgt, gt, 10, 1.0 / heads)
+        torch.cuda.synchronize(device)
+    n = 0
+    e0.record()
+    t_end = time.perf_counter() + seconds / 2
+    while time.perf_counter() < t_end:
+        for _ in range(8):
+            ops.sim_rank_topk(q, g, sgt, gt, 10, 1.0 / heads)
+        n += 8
+        torch.cuda.synchronize(device)
+    e1.record()
+    torch.cuda.synchronize(device)
+    mine = torch.tensor([e0.elapsed_time(e1) / max(1, n)], dtype=torch.float64, device=device)
+    allt = torch.empty(world_size, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(allt, mine, group=group)
+    inv = 1.0 / allt.cpu()
+    w = inv / inv.mean()
+    w = w.clamp(1.0 - clamp, 1.0 + clamp)
+    return [float(x) for x in (w / w.sum())]
 
 
 class CudaBackend:
@@ -182,8 +240,8 @@ class GalleryIndex:
     model/model.py:1026-1034, kept on the device and in the tensor-core operand type)."""
 
     def __init__(self, shard16: torch.Tensor, total: int, heads: int, rank: int = 0, world_size: int = 1,
-                 group=None, backend=None):
-        lo, hi = shard_bounds(total, world_size, rank)
+                 group=None, backend=None, weights=None):
+        lo, hi = shard_bounds(total, world_size, rank, weights)
         if shard16.shape[0] != hi - lo:
             raise ValueError("shard has %d rows, expected %d for rank %d/%d of a %d-row gallery"
                              % (shard16.shape[0], hi - lo, rank, world_size, total))

@@ -161,6 +161,22 @@ def test_shard_bounds_cover_the_gallery():
             assert all(lo <= hi for lo, hi in spans)
 
 
+def test_weighted_shard_bounds():
+    """Shards proportional to per-rank weights: cover the gallery, cut at whole column tiles, equal weights ~ equal
+    shards, a slower rank gets fewer rows."""
+    V = 1000000
+    for W in (2, 4, 8):
+        spans = [shard_bounds(V, W, r, [1.0] * W) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == V and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(lo % 256 == 0 for lo, _ in spans) and max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 512
+    w = [1.0, 0.9, 1.0, 1.1]
+    sizes = [b - a for a, b in (shard_bounds(V, 4, r, w) for r in range(4))]
+    assert sum(sizes) == V and sizes[1] < sizes[0] < sizes[3] and abs(sizes[1] / V - 0.9 / 4.0) < 1e-3
+    assert shard_bounds(100, 3, 1, [1, 1, 1], align=1) == (33, 67)
+    with pytest.raises(ValueError):
+        shard_bounds(V, 4, 0, [1.0, 1.0])
+
+
 def test_gallery_index_rejects_wrong_shard():
     with pytest.raises(ValueError):
         GalleryIndex(torch.zeros(5, 8), 100, 2, rank=0, world_size=2, backend=NumpyBackend())
