@@ -644,7 +644,7 @@ def main():
                     help="query pieces per step of the pipelined path (0 = one per 2560 queries, at most 4 on one GPU and 2 with several)")
     ap.add_argument("--reserve-sms", type=int, default=-1,
                     help="SMs the sweep leaves to the pipeline's side streams (-1 = 0 on one GPU, where the side stages are "
-                         "short kernels that fill the gaps between sweep launches, 6 with several ranks, where NCCL kernels wait "
+                         "short kernels that fill the gaps between sweep launches, 4 with several ranks, where NCCL kernels wait "
                          "for their peers and must not hold SMs the sweep's persistent CTAs were sized for)")
     ap.add_argument("--side-ctas", type=int, default=2, help="CTAs per NCCL kernel on the side communicators")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
@@ -665,7 +665,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.reserve_sms < 0:
-        args.reserve_sms = 0 if world == 1 else 6
+        args.reserve_sms = 0 if world == 1 else 4
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -523,12 +523,64 @@ class Retriever:
                             self.index.backend.metrics(rank0))
 
     # ------------------------------------------------------------------------------------------------------------
+    # latency path: small batches are launch-bound (C2, 2990 x 2990: ~40 launches for ~0.2 ms of tensor work)
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def rank_graphed(self, caption_feat_dict, gt_global, k: int = 10) -> SearchResult:
+        """rank() replayed as ONE CUDA graph: the first call with a given set of input shapes runs eagerly once (lazy
+        operand caches), captures fuse -> ground-truth scores -> sweep -> metrics, and every later call with those shapes
+        copies its inputs into the graph's static buffers and replays it.  One process (no collectives), device-resident
+        inputs.  The returned tensors are the graph's static outputs: read them before the next call with these shapes."""
+        idx = self.index
+        if idx.world_size != 1:
+            raise ops.LaffError("rank_graphed: one process per gallery (use submit() with several ranks)")
+        dev = idx.g16.device
+        feats = {n: v.to(dev) for n, v in caption_feat_dict.items()}
+        gt = gt_global.to(dev)
+
+        def sig_of(v):
+            if isinstance(v, ops.SparseRows):
+                return ("csr", v.shape, v.ids.numel(), v.base)
+            return (tuple(v.shape), str(v.dtype))
+        sig = tuple((n, sig_of(v)) for n, v in feats.items()) + (k, tuple(gt.shape), str(gt.dtype))
+        cache = self.__dict__.setdefault("_rank_graphs", {})
+        g = cache.get(sig)
+        if g is None:
+            def clone(v):
+                if isinstance(v, ops.SparseRows):
+                    return ops.SparseRows(v.offsets.clone(), v.ids.clone(), v.ndims, v.base,
+                                          None if v.row_scale is None else v.row_scale.clone())
+                return v.clone()
+            static = {n: clone(v) for n, v in feats.items()}
+            sgt = gt.clone()
+            self.rank(static, sgt, k)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                res = self.rank(static, sgt, k)
+            if len(cache) >= 8:
+                cache.pop(next(iter(cache)))
+            g = cache[sig] = (graph, static, sgt, res)
+        graph, static, sgt, res = g
+        for n, v in feats.items():
+            if isinstance(v, ops.SparseRows):
+                static[n].offsets.copy_(v.offsets, non_blocking=True)
+                static[n].ids.copy_(v.ids, non_blocking=True)
+            else:
+                static[n].copy_(v, non_blocking=True)
+        sgt.copy_(gt, non_blocking=True)
+        graph.replay()
+        return res
+
+    # ------------------------------------------------------------------------------------------------------------
     # pipelined path
     # ------------------------------------------------------------------------------------------------------------
-    # Measured at 8 GPUs (profiles/r02_scale_experiments.md): the pre-stage collective, the post-stage collective and one
-    # 2-CTA compute cluster must fit the reserved SMs TOGETHER -- a post-stage all-gather spins until the slowest rank's
-    # sweep is done, and if it leaves no SM for the pre stage, every rank's next sweep waits.  2 + 2 + 2 = 6.
-    reserve_sms = 6      # SMs left to the side streams while a sweep runs with W > 1 ranks (W = 1: none, see _pipe)
+    # Measured at 4 and 8 GPUs (profiles/r02_scale_experiments.md).  The side stages need SMs of their own while a sweep runs:
+    # a post-stage all-gather spins until the slowest rank's sweep is done, and if it (plus the pre-stage collective) leaves
+    # no SM for the pre stage's compute kernels, every rank's next sweep waits (reserve 2 / 1 CTA: 12.3 ms per step at 8
+    # GPUs instead of 9.1 serial).  4 reserved SMs with 2-CTA collectives is the measured optimum (8.31 ms); 6 and 8 cost
+    # the sweep more than they save (72 CTA pairs still cover a launch of 4890 units in 68 waves, 71 need 69).
+    reserve_sms = 4      # SMs left to the side streams while a sweep runs with W > 1 ranks (W = 1: none, see _pipe)
     side_max_ctas = 2    # CTAs of an NCCL kernel on the side communicators
 
     def _side_group(self):

@@ -65,6 +65,9 @@ def test_predict_collection_end_to_end(tmp_path):
         c.t2v_bow, c.t2v_w2v, c.t2v_idx = bow, w2v, idx
         c.we_dim, c.rnn_size, c.rnn_layer, c.we = 500, 1024, 1, None
         c.text_encoding["CLIP_encoding"]["dir_name"] = "CLIP_feats"
+        # base_config.py:171-173 ships a non-empty vid_frame_feats with frame_feat_input = False: plain LAFF configs (and the
+        # config stored in a reference checkpoint) carry both, and only the flag may decide (predictor.py:191)
+        c.vid_frame_feats, c.frame_feat_input = [synth.VIS_FRAME], False
         model = M.get_model("LAFF", torch.device("cuda"), c)
         load_numpy_state(model, {k: np.asarray(synth.param(5, k, tuple(v.shape))) for k, v in model.state_dict().items()})
         V, cpv = 60, 2

@@ -228,3 +228,22 @@ def test_predict_large_gallery_branch_returns_ranked_scores(golden, tmp_path):
     big.dense_limit_bytes = 100
     with pytest.raises(MemoryError):
         big.numpy()
+
+
+def test_mrl_with_score_accepts_a_strided_view():
+    """MarginRankingLossWithScore on a score block sliced out of a wider matrix (row pitch > B): same loss and gradient
+    as on the contiguous copy, and nothing is written outside the [B, B] gradient (the C entry point uses one pitch for
+    the scores and their gradient)."""
+    B = 37
+    wide = torch.randn(B, 3 * B + 5, device="cuda")
+    view = wide[:, 7:7 + B]
+    assert not view.is_contiguous()
+    l1, d1 = ops.mrl_score_forward_backward(view, 0.2, True, "t2i", "sum")
+    l2, d2 = ops.mrl_score_forward_backward(view.contiguous(), 0.2, True, "t2i", "sum")
+    assert d1.shape == (B, B) and d1.is_contiguous() and torch.equal(d1, d2) and float(l1) == float(l2)
+    crit = L.MarginRankingLossWithScore(margin=0.2, max_violation=True, cost_style="sum", direction="bidir")
+    v = view.clone().requires_grad_(True)
+    w = wide.clone().requires_grad_(True)
+    crit(v).backward()
+    crit(w[:, 7:7 + B]).backward()
+    assert torch.equal(w.grad[:, 7:7 + B], v.grad) and float(w.grad[:, :7].abs().sum()) == 0 and float(w.grad[:, 7 + B:].abs().sum()) == 0
