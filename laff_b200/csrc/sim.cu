@@ -844,28 +844,36 @@ int laff_sim_rank_topk(const void* q, const void* g, int Q, int V, int D, long l
   // 67.0 / 69.7 / 67.7 ms as one launch, 62.7 / 65.6 / 65.5 ms as four; profiles/r01_sched_experiments.md).
   static const bool split_groups = [] { const char* e = getenv("LAFF_SWEEP_SPLIT"); return !e || atoi(e) != 0; }();
   const int rows_per_launch = split_groups ? s.m_group * s.rows_per_mtile : Q;
-  for (int r0 = 0; r0 < Q; r0 += rows_per_launch) {
-    const int rows = Q - r0 < rows_per_launch ? Q - r0 : rows_per_launch;
-    GemmOperands ops = op;
-    if (r0 > 0 || rows < Q) {
-      rc = prepare_operands(&ops, static_cast<const uint16_t*>(q) + static_cast<long long>(r0) * ldq, g, rows, V, D, ldq, ldg, dtype,
-                            t.cta_group);
-      if (rc) return rc;
-    }
+  // A trailing row tile that is at most half full (10 000 queries = 39 tiles of 256 + 16 rows) is swept by the
+  // cta_group::1 kernel (128-row tiles on single CTAs): a CTA pair would spend a full 256-row MMA on it, the single CTAs
+  // spend half of that -- 1.2 % of a 10 000-query sweep.  Rows are independent, so the results do not change.
+  static const bool split_tail = [] { const char* e = getenv("LAFF_SWEEP_TAIL_CG1"); return !e || atoi(e) != 0; }();
+  auto sweep_rows = [&](int r0, int rows, int cg) -> int {
     const int tiles = (V + kBlockN - 1) / kBlockN;
     const int tiles_per = sweep_tiles_per_launch(tiles);
     for (int c0 = 0; c0 < V; c0 += tiles_per * kBlockN) {
       const int cols = V - c0 < tiles_per * kBlockN ? V - c0 : tiles_per * kBlockN;
-      GemmOperands oc = ops;
-      if (c0 > 0 || cols < V) {
-        rc = prepare_operands(&oc, static_cast<const uint16_t*>(q) + static_cast<long long>(r0) * ldq,
-                              static_cast<const uint16_t*>(g) + static_cast<long long>(c0) * ldg, rows, cols, D, ldq, ldg, dtype, t.cta_group);
-        if (rc) return rc;
-      }
+      GemmOperands oc;
+      int rc2 = prepare_operands(&oc, static_cast<const uint16_t*>(q) + static_cast<long long>(r0) * ldq,
+                                 static_cast<const uint16_t*>(g) + static_cast<long long>(c0) * ldg, rows, cols, D, ldq, ldg, dtype, cg);
+      if (rc2) return rc2;
       const Sched ss = make_sched(rows, cols, oc.cg, t.chunk_tiles, t.m_group, 0);
       EpiRank<LAFF_MAX_TOPK>::Params ep{sgt_raw + r0, gt_global + r0, count + r0, thr_key + r0,
                                        slots + static_cast<long long>(r0) * LAFF_MAX_TOPK, rows, cols, col_offset + c0, k};
-      rc = launch_gemm<EpiRank<LAFF_MAX_TOPK>>(oc, ss, ep, st);
+      rc2 = launch_gemm<EpiRank<LAFF_MAX_TOPK>>(oc, ss, ep, st);
+      if (rc2) return rc2;
+    }
+    return LAFF_OK;
+  };
+  for (int r0 = 0; r0 < Q; r0 += rows_per_launch) {
+    int rows = Q - r0 < rows_per_launch ? Q - r0 : rows_per_launch;
+    const int rem = rows % s.rows_per_mtile;
+    const bool tail = split_tail && op.cg == 2 && rem > 0 && rem <= kBlockM && rows > rem;
+    if (tail) rows -= rem;
+    rc = sweep_rows(r0, rows, op.cg);
+    if (rc) return rc;
+    if (tail) {
+      rc = sweep_rows(r0 + rows, rem, 1);
       if (rc) return rc;
     }
   }

@@ -248,10 +248,10 @@ def evaluate_and_write_ranked(pred, txt_ids, vis_ids, output_dir, predict_result
         out["t2v"] = _metrics_tuple(ops.rank_metrics(rank0))
         out["rank0"] = rank0
         names = ("r1", "r5", "r10", "medr", "meanr", "mir", "mAP")
-        vals = dict(zip(names, out["t2v"]))
+        m = dict(zip(names, out["t2v"]))
         print(" * Text to video:")
-        print(" * r_1_5_10: {}".format([round(vals["r1"], 3), round(vals["r5"], 3), round(vals["r10"], 3)]))
-        print(" * medr, meanr, mir: {}".format([round(vals["medr"], 3), round(vals["meanr"], 3), round(vals["mir"], 3)]))
+        print(" * r_1_5_10: {}".format([round(m["r1"], 3), round(m["r5"], 3), round(m["r10"], 3)]))
+        print(" * medr, meanr, mir: {}".format([round(m["medr"], 3), round(m["meanr"], 3), round(m["mir"], 3)]))
         write_to_predict_result_file(os.path.join(os.path.dirname(predict_result_file), "TextToVideo", os.path.basename(predict_result_file)),
                                      model_path, checkpoint, out["t2v"])
     else:

@@ -424,3 +424,22 @@ def test_rank_graphed_equals_eager_and_cuts_latency():
     t_eager, t_graph = timed(lambda: retr.rank(feats, gt, 10)), timed(lambda: retr.rank_graphed(feats, gt, 10))
     print("\nC2 2990 x 2990 fused encode + sweep + rank + metrics: eager %.3f ms, CUDA graph %.3f ms" % (t_eager, t_graph))
     assert t_graph <= t_eager * 1.05
+
+
+@pytest.mark.parametrize("Q", [296, 256 + 128, 2560 + 16, 257])
+def test_half_empty_trailing_row_tile_takes_the_single_cta_kernel(Q):
+    """A trailing row tile with <= 128 valid rows is swept by the cta_group::1 kernel (laff_sim_rank_topk): the ranks /
+    top-k of those rows must still be the oracle's on the device's own dense scores -- in particular the ground truth's
+    own column must compare equal to s_gt (computed by the pair kernel), or every tail row would count itself."""
+    V, H, dh, k = 5003, 8, 512, 10
+    q, g, gt = synth.retrieval_embeddings(17, Q, V, H, dh, sigma=3.0)
+    g[V - 1] = g[gt[Q - 1]]                       # exact ties with ground truths of tail rows
+    g[3] = g[gt[Q - 2]]
+    q16 = torch.from_numpy(q).cuda().to(torch.float16)
+    g16 = torch.from_numpy(g).cuda().to(torch.float16)
+    gt_t = torch.from_numpy(gt).cuda().to(torch.int32)
+    res = GalleryIndex(g16, V, H).search(q16, gt_t, k)
+    dense = ops.sim_dense(q16, g16, 1.0 / H).cpu().numpy()
+    np.testing.assert_array_equal(res.rank0.cpu().numpy(), O.tie_rule_rank(dense, gt))
+    np.testing.assert_array_equal(res.topk_idx.cpu().numpy(), O.tie_rule_topk(dense, k)[1])
+    np.testing.assert_array_equal(res.topk_val.cpu().numpy(), O.tie_rule_topk(dense, k)[0])
