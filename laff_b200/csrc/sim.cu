@@ -844,10 +844,11 @@ int laff_sim_rank_topk(const void* q, const void* g, int Q, int V, int D, long l
   // 67.0 / 69.7 / 67.7 ms as one launch, 62.7 / 65.6 / 65.5 ms as four; profiles/r01_sched_experiments.md).
   static const bool split_groups = [] { const char* e = getenv("LAFF_SWEEP_SPLIT"); return !e || atoi(e) != 0; }();
   const int rows_per_launch = split_groups ? s.m_group * s.rows_per_mtile : Q;
-  // A trailing row tile that is at most half full (10 000 queries = 39 tiles of 256 + 16 rows) is swept by the
-  // cta_group::1 kernel (128-row tiles on single CTAs): a CTA pair would spend a full 256-row MMA on it, the single CTAs
-  // spend half of that -- 1.2 % of a 10 000-query sweep.  Rows are independent, so the results do not change.
-  static const bool split_tail = [] { const char* e = getenv("LAFF_SWEEP_TAIL_CG1"); return !e || atoi(e) != 0; }();
+  // Experiment kept behind LAFF_SWEEP_TAIL_CG1=1 (off): sweep a trailing row tile that is at most half full (10 000 queries
+  // = 39 tiles of 256 + 16 rows) with the cta_group::1 kernel (128-row tiles on single CTAs) instead of a full 256-row
+  // pair MMA.  On paper 1.2 % of the sweep; measured (three A/B pairs on one box) 64.38 vs 64.13 ms, i.e. nothing: the
+  // sweep is power-bound, and an MMA over mostly-zero rows draws little power while eight extra launches are not free.
+  static const bool split_tail = [] { const char* e = getenv("LAFF_SWEEP_TAIL_CG1"); return e && atoi(e) != 0; }();
   auto sweep_rows = [&](int r0, int rows, int cg) -> int {
     const int tiles = (V + kBlockN - 1) / kBlockN;
     const int tiles_per = sweep_tiles_per_launch(tiles);

@@ -427,10 +427,10 @@ def test_rank_graphed_equals_eager_and_cuts_latency():
 
 
 @pytest.mark.parametrize("Q", [296, 256 + 128, 2560 + 16, 257])
-def test_half_empty_trailing_row_tile_takes_the_single_cta_kernel(Q):
-    """A trailing row tile with <= 128 valid rows is swept by the cta_group::1 kernel (laff_sim_rank_topk): the ranks /
-    top-k of those rows must still be the oracle's on the device's own dense scores -- in particular the ground truth's
-    own column must compare equal to s_gt (computed by the pair kernel), or every tail row would count itself."""
+def test_half_empty_trailing_row_tile(Q):
+    """Query counts that leave a trailing row tile with <= 128 valid rows (10 000 = 39 x 256 + 16): the ranks / top-k of
+    those rows are the oracle's on the device's own dense scores, ties with their ground truths included (also under
+    LAFF_SWEEP_TAIL_CG1=1, which sweeps that tile with the cta_group::1 kernel)."""
     V, H, dh, k = 5003, 8, 512, 10
     q, g, gt = synth.retrieval_embeddings(17, Q, V, H, dh, sigma=3.0)
     g[V - 1] = g[gt[Q - 1]]                       # exact ties with ground truths of tail rows
