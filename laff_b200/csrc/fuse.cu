@@ -66,6 +66,57 @@ __global__ void l2norm_quantize_kernel(const float* __restrict__ x, long long ro
   }
 }
 
+// Vector form for head sizes that are multiples of 128 with 16-byte aligned rows (every shipped setting: d_h = 512): the
+// head is read ONCE with 16-byte loads (NV float4 per lane, all in flight together), kept in registers across the
+// reduction, and written with 16-byte (fp32) / 8-byte (16-bit) stores -- the scalar kernel above reads it twice with
+// 4-byte accesses (0.78 of the measured copy bandwidth).
+template <int NV>
+__global__ void __launch_bounds__(256) l2norm_quantize_vec_kernel(const float* __restrict__ x, long long rows, int heads, long long ldx,
+                                                                  float eps, int normalise, int out_dtype, void* __restrict__ out,
+                                                                  long long ld_out) {
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = rows * heads;
+  if (warp >= total) return;
+  const long long row = warp / heads;
+  const int h = static_cast<int>(warp - row * heads);
+  constexpr int dh = NV * 128;
+  const float4* src = reinterpret_cast<const float4*>(x + row * ldx + static_cast<long long>(h) * dh);
+  float4 v[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) v[q] = __ldcs(src + lane + 32 * q);   // streamed: read once
+  float inv = 1.0f;
+  float den = 1.0f;
+  if (normalise) {
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      ss = fmaf(v[q].x, v[q].x, ss);
+      ss = fmaf(v[q].y, v[q].y, ss);
+      ss = fmaf(v[q].z, v[q].z, ss);
+      ss = fmaf(v[q].w, v[q].w, ss);
+    }
+    ss = warp_sum(ss);
+    den = sqrtf(ss) + eps;  // loss.py:11
+  }
+  (void)inv;
+  const long long o = row * ld_out + static_cast<long long>(h) * dh;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    float4 r = v[q];
+    if (normalise) { r.x = r.x / den; r.y = r.y / den; r.z = r.z / den; r.w = r.w / den; }  // loss.py:12 torch.div
+    const int c = 4 * (lane + 32 * q);
+    if (out_dtype == LAFF_F32) {
+      *reinterpret_cast<float4*>(static_cast<float*>(out) + o + c) = r;
+    } else {
+      uint2 pk;
+      pk.x = static_cast<uint32_t>(to16(r.x, out_dtype)) | (static_cast<uint32_t>(to16(r.y, out_dtype)) << 16);
+      pk.y = static_cast<uint32_t>(to16(r.z, out_dtype)) | (static_cast<uint32_t>(to16(r.w, out_dtype)) << 16);
+      *reinterpret_cast<uint2*>(static_cast<uint16_t*>(out) + o + c) = pk;
+    }
+  }
+}
+
 // fp32 -> 16-bit operand copies.  HBM-bound: one thread moves 8 consecutive columns (two 16-byte loads, one 16-byte store
 // per output plane); VEC = false is the element-wise path for pitches / pointers that are not 16-byte aligned.
 __device__ __forceinline__ void load8(const float* __restrict__ src, int valid, bool vec, float (&v)[8]) {
@@ -474,8 +525,26 @@ int laff_l2norm_quantize(const float* x, long long rows, int heads, int head_dim
   const int block = 256;
   const long long blocks = (warps * 32 + block - 1) / block;
   LAFF_REQUIRE(blocks < (1LL << 31), LAFF_ENOTSUP, "laff_l2norm_quantize: too many rows");
-  l2norm_quantize_kernel<<<static_cast<unsigned>(blocks), block, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rows, heads, head_dim, ldx, static_cast<float>(eps < 0 ? 0.0 : eps), eps >= 0 ? 1 : 0, out_dtype, out, ld_out); laff::count_launch();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float feps = static_cast<float>(eps < 0 ? 0.0 : eps);
+  const int norm = eps >= 0 ? 1 : 0;
+  const size_t esz = out_dtype == LAFF_F32 ? 4 : 2;
+  const bool vec = head_dim % 128 == 0 && head_dim <= 1024 && (head_dim & (head_dim - 1)) == 0 && ldx % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   (ld_out * esz) % 16 == 0;
+  if (vec) {
+    const unsigned nb = static_cast<unsigned>(blocks);
+    switch (head_dim / 128) {
+      case 1: l2norm_quantize_vec_kernel<1><<<nb, block, 0, st>>>(x, rows, heads, ldx, feps, norm, out_dtype, out, ld_out); break;
+      case 2: l2norm_quantize_vec_kernel<2><<<nb, block, 0, st>>>(x, rows, heads, ldx, feps, norm, out_dtype, out, ld_out); break;
+      case 4: l2norm_quantize_vec_kernel<4><<<nb, block, 0, st>>>(x, rows, heads, ldx, feps, norm, out_dtype, out, ld_out); break;
+      default: l2norm_quantize_vec_kernel<8><<<nb, block, 0, st>>>(x, rows, heads, ldx, feps, norm, out_dtype, out, ld_out); break;
+    }
+  } else {
+    l2norm_quantize_kernel<<<static_cast<unsigned>(blocks), block, 0, st>>>(x, rows, heads, head_dim, ldx, feps, norm, out_dtype, out,
+                                                                           ld_out);
+  }
+  laff::count_launch();
   LAFF_CUDA(cudaGetLastError());
   return LAFF_OK;
 }
