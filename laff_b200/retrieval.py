@@ -583,21 +583,30 @@ class Retriever:
     reserve_sms = 4      # SMs left to the side streams while a sweep runs with W > 1 ranks (W = 1: none, see _pipe)
     side_max_ctas = 2    # CTAs of an NCCL kernel on the side communicators
 
-    def _side_group(self):
+    _side_groups: dict = {}   # (ranks, max_ctas, stage) -> communicator, shared by every Retriever of the process
+
+    def _side_group(self, stage: str):
         """A communicator over the index's ranks for one side stream; NCCL kernels limited to `side_max_ctas` CTAs so that
         the collective of the stage before a sweep and the one after it fit the reserved SMs together (a kernel waiting
-        for its peers then never blocks the other stage's)."""
+        for its peers then never blocks the other stage's).  Created once per (ranks, CTA limit, stage) and reused:
+        new_group is a collective call and communicators are not free."""
         idx = self.index
-        ranks = dist.get_process_group_ranks(idx.group) if idx.group is not None else list(range(dist.get_world_size()))
-        if dist.get_backend(idx.group) == "nccl":
-            opts = dist.ProcessGroupNCCL.Options()
-            try:
-                opts.config.max_ctas = int(self.side_max_ctas)
-                opts.config.min_ctas = 1
-            except Exception:
-                pass
-            return dist.new_group(ranks, pg_options=opts)
-        return dist.new_group(ranks)
+        ranks = tuple(dist.get_process_group_ranks(idx.group) if idx.group is not None else range(dist.get_world_size()))
+        key = (ranks, int(self.side_max_ctas), stage)
+        g = Retriever._side_groups.get(key)
+        if g is None:
+            if dist.get_backend(idx.group) == "nccl":
+                opts = dist.ProcessGroupNCCL.Options()
+                try:
+                    opts.config.max_ctas = int(self.side_max_ctas)
+                    opts.config.min_ctas = 1
+                except Exception:
+                    pass
+                g = dist.new_group(list(ranks), pg_options=opts)
+            else:
+                g = dist.new_group(list(ranks))
+            Retriever._side_groups[key] = g
+        return g
 
     def _pipe(self):
         P = getattr(self, "_pipe_state", None)
@@ -608,7 +617,7 @@ class Retriever:
         P = types.SimpleNamespace(pre=None, sweep=None, post=None, copy=None, g_pre=idx.group, g_post=idx.group,
                                   sweep_sms=0, side_sms=0)
         if idx.world_size > 1:                                   # collective calls: every rank creates them in this order
-            P.g_pre, P.g_post = self._side_group(), self._side_group()
+            P.g_pre, P.g_post = self._side_group("pre"), self._side_group("post")
         if dev.type == "cuda":
             P.pre, P.post, P.copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             P.sweep = torch.cuda.Stream(dev, priority=-1)        # a sweep launch gets freed SMs before queued side work
@@ -644,6 +653,8 @@ class Retriever:
         first = next(iter(caption_feat_dict.values()))
         Q = first.shape[0]
         cuda = dev.type == "cuda"
+        if Q == 0:
+            raise ValueError("submit: empty query batch")
         if pieces is None:                                       # the sweep's own row groups (10 row tiles of 256), at most 4;
             pieces = max(1, min(4 if idx.world_size == 1 else 2, (Q + 2559) // 2560))   # with collectives per piece: 2
         pieces = max(1, min(int(pieces), max(1, Q)))

@@ -37,6 +37,9 @@ def main():
     lo, hi = shard_bounds(V, world, rank)
     res = GalleryIndex(g16[lo:hi].contiguous(), V, H, rank, world).search(q16, gt.to(torch.int32), k)
     lv, li = GalleryIndex(g16[lo:hi].contiguous(), V, H, rank, world).ranked_lists(q16[:300], 500, query_chunk=128)
+    # lists + exact ranks from one sweep per shard (laff_sim_collect_rank), counts summed over the shards
+    lv_r, li_r, rk_r = GalleryIndex(g16[lo:hi].contiguous(), V, H, rank, world).ranked_lists(q16[:300], 500, query_chunk=128,
+                                                                                         gt_global=gt[:300].to(torch.int32))
     # the public query path: pinned host features in 3 pieces, each rank copies and fuses only its slice of every piece
     import bench  # noqa: E402  (synthetic text net + query features of the bench)
     txt_net = bench.build_txt_net(dev)
@@ -67,7 +70,8 @@ def main():
         rv, ri = single.ranked_lists(q16[:300], 500, query_chunk=128)
         ok = ok and (torch.equal(res.rank0, ref.rank0) and torch.equal(res.topk_idx, ref.topk_idx)
               and torch.equal(res.topk_val, ref.topk_val) and torch.equal(res.metrics, ref.metrics)
-              and torch.equal(li, ri) and torch.equal(lv, rv) and torch.equal(ri[:, :k], ref.topk_idx[:300]))
+              and torch.equal(li, ri) and torch.equal(lv, rv) and torch.equal(ri[:, :k], ref.topk_idx[:300])
+              and torch.equal(li_r, ri) and torch.equal(lv_r, rv) and torch.equal(rk_r, ref.rank0[:300]))
         print("multi-GPU parity world=%d: %s  R@1=%.2f R@10=%.2f MedR=%.0f" % (
             world, "OK" if ok else "MISMATCH", ref.metrics[0].item(), ref.metrics[2].item(), ref.metrics[3].item()), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
