@@ -289,8 +289,11 @@ __device__ __forceinline__ void pool_load(const float* __restrict__ p, int lane,
   }
 }
 
-template <int VPL, int LMAX, bool VEC>
-__global__ void __launch_bounds__(128) attention_pool_kernel(laff_pool_desc d, long long rows, float* __restrict__ out,
+// PLAIN = neither with_ave nor mul (the shipped setting): the mean-pooled vector is never needed, which frees VPL registers
+// per lane and lets a fifth block of the d_h = 512, L <= 4 instantiation fit an SM (a warp holds its L heads in registers
+// from the loads to the final normalisation, so occupancy is what keeps enough loads in flight).
+template <int VPL, int LMAX, bool VEC, bool PLAIN>
+__global__ void __launch_bounds__(128, (PLAIN && VPL == 16 && LMAX == 4) ? 5 : 1) attention_pool_kernel(laff_pool_desc d, long long rows, float* __restrict__ out,
                                                             long long ld_out, void* __restrict__ out16, int out16_dtype,
                                                             long long ld_out16, float* __restrict__ att) {
   const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -344,15 +347,17 @@ __global__ void __launch_bounds__(128) attention_pool_kernel(laff_pool_desc d, l
   pool_load<VPL, VEC>(d.att_weight + static_cast<long long>(h) * dh, lane, w);
 
   // raw_global_emb = mean over features (Attention.py:81)
-  float mean[VPL];
-  const float invL = 1.0f / static_cast<float>(L);
+  float mean[PLAIN ? 1 : VPL];
+  if constexpr (!PLAIN) {
+    const float invL = 1.0f / static_cast<float>(L);
 #pragma unroll
-  for (int t = 0; t < VPL; ++t) {
-    float s = 0.f;
+    for (int t = 0; t < VPL; ++t) {
+      float s = 0.f;
 #pragma unroll
-    for (int l = 0; l < LMAX; ++l)
-      if (l < L) s += y[l][t];
-    mean[t] = s * invL;
+      for (int l = 0; l < LMAX; ++l)
+        if (l < L) s += y[l][t];
+      mean[t] = s * invL;
+    }
   }
 
   // logits e_l = w_h . common_l + c_h  (Attention.py:88), common = local (* mean if mul, Attention.py:83-86)
@@ -364,7 +369,10 @@ __global__ void __launch_bounds__(128) attention_pool_kernel(laff_pool_desc d, l
     if (l < L) {
       float s = 0.f;
 #pragma unroll
-      for (int t = 0; t < VPL; ++t) s = fmaf(w[t], d.mul ? y[l][t] * mean[t] : y[l][t], s);
+      for (int t = 0; t < VPL; ++t) {
+        if constexpr (PLAIN) s = fmaf(w[t], y[l][t], s);
+        else s = fmaf(w[t], d.mul ? y[l][t] * mean[t] : y[l][t], s);
+      }
       e[l] = warp_sum(s) + cb;
       emax = fmaxf(emax, e[l]);
     } else {
@@ -390,7 +398,9 @@ __global__ void __launch_bounds__(128) attention_pool_kernel(laff_pool_desc d, l
 #pragma unroll
     for (int l = 0; l < LMAX; ++l)
       if (l < L) s = fmaf(e[l] * invz, y[l][t], s);
-    if (d.with_ave) s = fmaf(d.omega, mean[t] * static_cast<float>(L), s);  // sum_l omega * raw_global_emb
+    if constexpr (!PLAIN) {
+      if (d.with_ave) s = fmaf(d.omega, mean[t] * static_cast<float>(L), s);  // sum_l omega * raw_global_emb
+    }
     g[t] = s;
     ss = fmaf(s, s, ss);
   }
@@ -675,9 +685,14 @@ int laff_attention_pool(const laff_pool_desc* desc, long long rows, float* out, 
     if (s.kind == 1) vec = vec && s.in_dim % 4 == 0 && (!s.bn_scale || (al16(s.bn_scale) && al16(s.bn_shift)));
   }
   const int L = desc->n_features;
+  const bool plain = !desc->with_ave && !desc->mul;
 #define LAFF_POOL_LAUNCH(V, LM, VE)                                                                                    \
-  attention_pool_kernel<V, LM, VE><<<static_cast<unsigned>(blocks), block, 0, st>>>(*desc, rows, out, ld_out, out16,     \
-                                                                                    out16_dtype, ld_out16, att)
+  do {                                                                                                                 \
+    if (plain) attention_pool_kernel<V, LM, VE, true><<<static_cast<unsigned>(blocks), block, 0, st>>>(                 \
+        *desc, rows, out, ld_out, out16, out16_dtype, ld_out16, att);                                                  \
+    else attention_pool_kernel<V, LM, VE, false><<<static_cast<unsigned>(blocks), block, 0, st>>>(                      \
+        *desc, rows, out, ld_out, out16, out16_dtype, ld_out16, att);                                                  \
+  } while (0)
 #define LAFF_POOL_CASE(V)                                                                                              \
   case V:                                                                                                              \
     if (vec && V >= 4) {                                                                                               \
