@@ -20,6 +20,8 @@ is the "next" row N4 of SURVEY §8(f) and raises NotImplementedError instead of 
 """
 from __future__ import annotations
 
+import contextlib
+
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -276,9 +278,25 @@ def set_single_kernel_fusion(flag: bool) -> None:
     _SINGLE_KERNEL = bool(flag)
 
 
+# SMs that cast the next chunk's features while the fused kernel works on this one.  0 = serial, the default: measured
+# (tools/bench_modeb.py, 1 M videos) serial 39.1 ms, overlapped on 8 / 12 / 16 / 24 SMs 43.4 / 41.4 / 41.8 / 41.4 ms -- the
+# HBM-bound cast needs far more SMs than the fused kernel can spare (profiles/README.md).
+_CAST_OVERLAP_SMS = 0
+_CAST_STREAMS: Dict[int, tuple] = {}   # device index -> (cast stream, high-priority fused-kernel stream)
+
+
+def set_cast_overlap(sms: int) -> None:
+    global _CAST_OVERLAP_SMS
+    _CAST_OVERLAP_SMS = max(0, int(sms))
+
+
 def _fuse_single_kernel(features, attention, precision, out16_dtype, want_f32=True):
     """All projections + pooling in one kernel (csrc/fused.cu), `_FUSED_ROW_CHUNK` rows per launch so the 16-bit copies
-    of the input features stay a bounded scratch (a 1 M-video gallery shard is fused in 8 launches)."""
+    of the input features stay a bounded scratch (a 1 M-video gallery shard is fused in 8 launches).
+
+    Experiment, off by default (set_cast_overlap): with more than one chunk the fp32 -> 16-bit casts of chunk c + 1 can
+    run on a side stream, on `_CAST_OVERLAP_SMS` SMs, while the fused kernel of chunk c has the rest (double-buffered
+    scratch, same results).  It measured slower than alternating the two, see the note at _CAST_OVERLAP_SMS."""
     B = features[0][0].shape[0]
     dev = features[0][0].device
     D = attention.multi_heads * attention.dim_per_head
@@ -287,9 +305,46 @@ def _fuse_single_kernel(features, attention, precision, out16_dtype, want_f32=Tr
     out = torch.empty((B, D), dtype=torch.float32, device=dev) if want_f32 else None
     out16 = torch.empty((B, D), dtype=ops.torch_dtype(out16_dtype), device=dev) if out16_dtype is not None else None
     chunk = min(max(B, 1), _FUSED_ROW_CHUNK)
-    scratch: Dict[int, torch.Tensor] = {}
-    for s in range(0, B, chunk):
-        e = min(B, s + chunk)
+    n_chunks = (B + chunk - 1) // chunk if B > 0 else 0
+    cast_ids = [i for i, (x, tn) in enumerate(features) if tn.fc1 is not None and not isinstance(x, ops.SparseRows)]
+    overlap = n_chunks > 1 and precision != "bf16x3" and _CAST_OVERLAP_SMS > 0 and bool(cast_ids)
+    scratch: Dict[tuple, torch.Tensor] = {}
+
+    def cast_chunk(ci):
+        """16-bit copies of chunk ci's projected features into scratch buffer set ci % 2 (one set when not overlapping)."""
+        s, e = ci * chunk, min(B, (ci + 1) * chunk)
+        outs = {}
+        for i in cast_ids:
+            x = features[i][0]
+            key = (i, ci % 2 if overlap else 0)
+            if n_chunks > 1 and key not in scratch:
+                scratch[key] = torch.empty((chunk, (x.shape[1] + 7) // 8 * 8), dtype=_op_dtype(precision), device=dev)
+            outs[i] = ops.cast_pad_16(x[s:e], _op_dtype(precision), out=scratch.get(key))
+        return outs
+
+    if overlap:
+        # the fused kernel goes to a high-priority stream so that, when it and the next cast become runnable together,
+        # its persistent CTAs get their SMs first and the cast's blocks land on the SMs it leaves free
+        main = torch.cuda.current_stream(dev)
+        di = dev.index if dev.index is not None else torch.cuda.current_device()
+        if di not in _CAST_STREAMS:
+            _CAST_STREAMS[di] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1))
+        side, fstream = _CAST_STREAMS[di]
+        total_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        side_sms = min(_CAST_OVERLAP_SMS, total_sms // 4)
+        side_sms -= side_sms % 2
+        cast_done, fuse_done = {}, {}
+        casted = {0: cast_chunk(0)}                       # the first chunk has nothing to hide behind: whole device
+        cast_done[0] = torch.cuda.Event()
+        cast_done[0].record(main)
+        side.wait_stream(main)
+        fstream.wait_stream(main)
+    for ci in range(n_chunks):
+        s, e = ci * chunk, min(B, (ci + 1) * chunk)
+        x16s = None
+        if overlap:
+            fstream.wait_event(cast_done[ci])
+            x16s = casted.pop(ci)
         fc, tiled = [], []
         for i, ((x, tn), c) in enumerate(zip(features, prepared)):
             xs = x[s:e]
@@ -299,16 +354,39 @@ def _fuse_single_kernel(features, attention, precision, out16_dtype, want_f32=Tr
             elif tn.fc1 is not None:
                 if precision == "bf16x3":
                     x16 = ops.split3_16(xs, 0, torch.bfloat16)
+                elif x16s is not None:
+                    x16 = x16s[i]
                 else:
-                    if B > chunk and i not in scratch:
-                        scratch[i] = torch.empty((chunk, (x.shape[1] + 7) // 8 * 8), dtype=_op_dtype(precision), device=dev)
-                    x16 = ops.cast_pad_16(xs, _op_dtype(precision), out=scratch.get(i))
+                    key = (i, 0)
+                    if n_chunks > 1 and key not in scratch:
+                        scratch[key] = torch.empty((chunk, (x.shape[1] + 7) // 8 * 8), dtype=_op_dtype(precision), device=dev)
+                    x16 = ops.cast_pad_16(xs, _op_dtype(precision), out=scratch.get(key))
                 fc.append({"x16": x16, "w16": c["w16"], "bias": c["bias"], "activation": tn.activation_name,
                            "bn_scale": c.get("bn_scale"), "bn_shift": c.get("bn_shift")})
             else:
                 tiled.append({"x": xs, "bn_scale": c.get("bn_scale"), "bn_shift": c.get("bn_shift")})
-        ops.fuse_forward(fc, tiled, w, b, attention.multi_heads, attention.dim_per_head, want_f32=False,
-                         out=None if out is None else out[s:e], out16=None if out16 is None else out16[s:e])
+        # an enclosing SM budget (the retrieval pipeline's side stages) stays in force unless this loop sets its own
+        with (torch.cuda.stream(fstream) if overlap else contextlib.nullcontext()), \
+                (ops.sm_limit(total_sms - side_sms) if overlap and ci + 1 < n_chunks else contextlib.nullcontext()):
+            ops.fuse_forward(fc, tiled, w, b, attention.multi_heads, attention.dim_per_head, want_f32=False,
+                             out=None if out is None else out[s:e], out16=None if out16 is None else out16[s:e])
+        if overlap:
+            fuse_done[ci] = torch.cuda.Event()
+            fuse_done[ci].record(fstream)
+            if ci + 1 < n_chunks:                         # issued AFTER the fused kernel of this chunk
+                with torch.cuda.stream(side), ops.sm_limit(side_sms):
+                    if ci - 1 in fuse_done:               # the buffer set of chunk ci + 1 was read by the fused kernel of ci - 1
+                        side.wait_event(fuse_done[ci - 1])
+                    casted[ci + 1] = cast_chunk(ci + 1)
+                    cast_done[ci + 1] = torch.cuda.Event()
+                    cast_done[ci + 1].record(side)
+    if overlap:
+        main.wait_stream(fstream)
+        main.wait_stream(side)
+        for t in list(scratch.values()) + [t for t in (out, out16) if t is not None]:   # used on streams they were not allocated on
+            t.record_stream(side)
+            t.record_stream(fstream)
+            t.record_stream(main)
     H, dh = attention.multi_heads, attention.dim_per_head
     return (None if out is None else out.view(B, H, dh)), (None if out16 is None else out16.view(B, H, dh))
 
