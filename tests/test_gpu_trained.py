@@ -92,3 +92,65 @@ def test_trained_checkpoint_ranks_identical_to_reference(tag):
     print("\n%s trained fixture (reference R@1/5/10/MedR %s): " % (tag, np.round(ref_m[:4], 2)) +
           "; ".join("%s ranks moved %.2f%% max|dR@K| %.2f dMedR %+.0f" % (p, 100 * v[0], max(v[1]), v[2]) for p, v in report.items()))
     assert report["fp16"][0] <= report["bf16"][0] + 1e-9      # fp16 rounds 8x finer than bf16 at the same MMA rate
+
+
+def test_full_dims_model_trained_on_device_ranks_like_the_oracle():
+    """T2 at the shipped dimensions (D = 4096, 8 heads, gru 1024 / bow 3981 / w2v 500 / tf 768 / x3d, ircsn 2048): a LAFF
+    model is trained here for 300 steps by the device training step (itself pinned to the reference's, tests/test_gpu_train.py)
+    on the latent-factor collection, then 1000 held-out queries are ranked against 1000 held-out videos.  The oracle --
+    pinned to the reference on the reference-trained fixture -- runs the same weights in numpy; the fp32-grade device
+    pipeline must return its ranks / top-10 / R@K / MedR wherever the oracle's own margins exceed the noise window, and
+    the 16-bit pipelines are reported and bounded like on the fixture."""
+    from laff_b200 import ops as _ops
+    from oracle import laff_oracle as O
+    H, D, n_train, n_eval = 8, 4096, 4096, 1000
+    noise = dict(vis_noise=2.0, cap_noise=1.3, txt_noise=2.0)     # wide features average their noise: more of it than on the fixture
+    c = cfg.laff_config(D, H, synth.DIMS)
+    c.dropout = 0.2
+    torch.manual_seed(0)
+    model = M.get_model("LAFF", torch.device("cuda"), c)
+    vis_tr, txt_tr = synth.latent_collection(500, n_train, dims=synth.DIMS, **noise)
+    pick = np.random.RandomState(3)
+    model.train()
+    losses = []
+    for step in range(300):
+        b = pick.choice(n_train, 128, replace=False)
+        td = {"vis_feats": {k: torch.from_numpy(v[b]) for k, v in vis_tr.items()}, "captions": {k: torch.from_numpy(v[b]) for k, v in txt_tr.items()},
+              "captions_task2": None, "vis_frame_feat_dict": {}, "vis_origin_frame_tuple": None}
+        losses.append(float(model(td, epoch=0)["triplet_loss"]))
+    assert losses[-1] < 0.7 * losses[0], (losses[0], losses[-1])
+    model.eval()
+    vis, txt = synth.latent_collection(501, n_eval, dims=synth.DIMS, **noise)
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    vsd = {k[len("vis_net."):]: v for k, v in sd.items() if k.startswith("vis_net.")}
+    tsd = {k[len("txt_net."):]: v for k, v in sd.items() if k.startswith("txt_net.")}
+    ov, _ = O.vis_net_forward(vis, vsd, [synth.VIS_CLIP_FT], H)
+    ot, _ = O.txt_net_forward(txt, tsd, ["CLIP_encoder"], H)
+    s_ref = O.txt2vis_matrix(ot, ov)
+    gt = np.arange(n_eval)
+    r_ref = O.tie_rule_rank(s_ref, gt)
+    m_ref = O.metrics_from_rank0(r_ref)
+    assert 10 < m_ref[0] < 96, m_ref                      # a trained, non-saturated task
+    r, ti, tv, m = run(model, H, vis, txt, "bf16x3")
+    sg = s_ref[gt, gt][:, None]
+    d = np.abs(s_ref - sg)
+    d[gt, gt] = np.inf
+    clean = d.min(1) > 2e-5                                # fp32 oracle noise + split residual at D = 4096
+    assert clean.mean() > 0.95, clean.mean()
+    np.testing.assert_array_equal(r[clean], r_ref[clean])
+    assert np.abs(r[~clean] - r_ref[~clean]).max(initial=0) <= 3
+    assert m[3] == m_ref[3] and all(abs(m[i] - m_ref[i]) <= 100.0 * (~clean).sum() / n_eval + 1e-9 for i in range(3))
+    srt = -np.sort(-s_ref, axis=1)[:, :12]
+    lists_clean = (srt[:, :-1] - srt[:, 1:])[:, :11].min(1) > 2e-5
+    np.testing.assert_array_equal(ti[lists_clean], O.tie_rule_topk(s_ref, 10)[1][lists_clean])
+    assert np.abs(tv - srt[:, :10]).max() <= 2e-5
+    report = {}
+    for precision, bound in (("fp16", 0.03), ("bf16", 0.15)):
+        r16, _, tv16, m16 = run(model, H, vis, txt, precision)
+        moved = float((r16 != r_ref).mean())
+        report[precision] = (moved, max(abs(m16[i] - m_ref[i]) for i in range(3)), m16[3] - m_ref[3])
+        assert moved <= bound and report[precision][1] <= 0.5 and abs(report[precision][2]) <= 1, (precision, report[precision])
+    print("\nfull-dims model trained on the device (oracle R@1/5/10/MedR %s): bf16x3 ranks moved %.2f%%; " % (
+        np.round(m_ref[:4], 2), 100 * float((r != r_ref).mean())) +
+        "; ".join("%s ranks moved %.2f%% max|dR@K| %.2f dMedR %+.0f" % (p, 100 * v[0], v[1], v[2]) for p, v in report.items()))
+    assert report["fp16"][0] <= report["bf16"][0] + 1e-9
