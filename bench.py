@@ -245,7 +245,7 @@ def cpu_reference_steps(q_emb, g_host, gt, sample, steps, warmup, threads):
 
 
 def staged_reference():
-    """(model.model, evaluation) of the unmodified reference staged under oracle/_ref (oracle/stage_reference.py), or None."""
+    """(model.model, evaluation) of the unmodified reference staged under baseline/_ref (oracle/stage_reference.py), or None."""
     try:
         from oracle import ref_loader
         return ref_loader.load() if ref_loader.available() else None
@@ -331,7 +331,7 @@ def run_reference(args, rank, world):
     if ref is not None:
         times, _ = reference_cpu_steps(ref, q, g_host, gt, sample, args.steps, args.warmup, cores)
         kind = "reference"
-        what = ("%d queries x %d videos per step through the UNMODIFIED reference staged under oracle/_ref: W2VVPP.get_txt2vis_matrix "
+        what = ("%d queries x %d videos per step through the UNMODIFIED reference staged under baseline/_ref: W2VVPP.get_txt2vis_matrix "
                 "over 100k-video gallery tiles (model/model.py:1003-1016), get_predict_file's np.argsort + id-matching loop "
                 "(predictor.py:232-246) and evaluation.eval (evaluation.py:92-109); torch + numpy on %d threads" % (sample, V, cores))
     else:
@@ -623,7 +623,7 @@ def run_ours(args, rank, world, local_rank):
         ref = staged_reference()
         if ref is not None:
             tms, ref_metrics = reference_cpu_steps(ref, q_host, g_host, gt.numpy()[: len(q_host)], sample, 2, 1, cores)
-            kind, how = "reference", ("the unmodified reference staged under oracle/_ref: get_txt2vis_matrix + predictor.py:232-246 "
+            kind, how = "reference", ("the unmodified reference staged under baseline/_ref: get_txt2vis_matrix + predictor.py:232-246 "
                                       "argsort / id-matching loop + evaluation.eval")
         else:
             tms = cpu_reference_steps(q_host, g_host, gt.numpy()[: len(q_host)], sample, 2, 1, cores)

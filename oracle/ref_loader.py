@@ -1,4 +1,4 @@
-"""Imports the staged, unmodified reference (oracle/_ref/laff_reference, see stage_reference.py) on a box that has
+"""Imports the staged, unmodified reference (baseline/_ref/laff_reference, see stage_reference.py) on a box that has
 neither the reference tree nor its optional dependencies -- TEST / BASELINE INFRASTRUCTURE (bench.py's CPU arm).
 
 Leaf imports that are absent are shimmed exactly as tests/golden/make_golden.py does (ftfy, nltk, prefetch_generator,
@@ -14,7 +14,7 @@ import sys
 import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-STAGED = os.path.join(HERE, "_ref", "laff_reference")
+STAGED = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "laff_reference")
 
 
 def available() -> bool:

@@ -1,11 +1,12 @@
 """Stages the UNMODIFIED pure-Python reference (ruc-aimc-lab/LAFF) for the CPU arm of bench.py -- TEST / BASELINE
 INFRASTRUCTURE, never imported by the product path.
 
-The reference has no compiled code, so "building" `oracle/_ref` is a file copy: the modules its evaluation
-path imports (model/, loss.py, evaluation.py, util.py, ...) are copied verbatim from /root/reference into
-`oracle/_ref/laff_reference/` together with a MANIFEST of their sha256 sums.  `oracle/_ref/` is git-ignored (no
-reference source enters the history) but not gpurun-ignored, so the copy travels to the GPU box, where /root/reference
-does not exist, and `bench.py --impl reference` can time the reference's own functions there (`kind: "reference"`).
+The reference has no compiled code and no setup.py, so "installing" it is a file copy: the modules its
+evaluation path imports (model/, loss.py, evaluation.py, util.py, ...) are copied verbatim from /root/reference into
+`baseline/_ref/laff_reference/` -- the location the bench contract reserves for the unmodified reference -- together
+with a MANIFEST of their sha256 sums.  `baseline/_ref/` is git-ignored (no reference source enters the history) but not
+gpurun-ignored, so the copy travels to the GPU box, where /root/reference does not exist, and `bench.py --impl
+reference` can time the reference's own functions there (`kind: "reference"`).
 Run by `__graft_entry__.build()` whenever /root/reference is present.
 
     python oracle/stage_reference.py
@@ -18,7 +19,7 @@ import os
 import shutil
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEST = os.path.join(HERE, "_ref", "laff_reference")
+DEST = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "laff_reference")
 SOURCE = os.environ.get("LAFF_REFERENCE", "/root/reference")
 # what `import model.model`, `import evaluation`, `import loss` pull in (model/model.py:1-26)
 FILES = ["__init__.py", "bigfile.py", "common.py", "evaluation.py", "generic_utils.py", "loss.py", "textlib.py", "txt2vec.py",

@@ -1,4 +1,4 @@
-"""bench.py contract pieces that need no GPU: the reference arm (the unmodified reference staged under oracle/_ref when it
+"""bench.py contract pieces that need no GPU: the reference arm (the unmodified reference staged under baseline/_ref when it
 is there, else the oracle port of its CPU path) prints
 exactly one JSON line with the keys the driver reads, rank != 0 of a multi-rank launch stays silent, and the product
 arm refuses to run without a CUDA device instead of falling back."""
@@ -24,7 +24,7 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "queries/sec ranked vs 1M-video gallery" and d["unit"] == "queries/s"
     assert d["higher_is_better"] is True and d["steps"] == 2 and d["value"] > 0 and d["ms_per_step"] > 0
-    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "laff_reference", "MANIFEST.json"))
+    staged = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "laff_reference", "MANIFEST.json"))
     assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
