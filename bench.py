@@ -514,6 +514,38 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = t0.elapsed_time(t1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- the other 16-bit operand type on the same box, back to back (one GPU only): the price / gain of the parity choice
+    other = None
+    if world == 1 and args.ab_steps > 0:
+        odt = torch.bfloat16 if dt16 == torch.float16 else torch.float16
+        retr_o = Retriever(txt_net, GalleryIndex(g16.to(odt), V, HEADS, rank, world))
+        retr_o.reserve_sms, retr_o.side_max_ctas = args.reserve_sms, args.side_ctas
+
+        def run_o(n):
+            last = None
+            for _ in range(n):
+                last = retr_o.submit(feats_dev, gt_dev, TOPK, pieces=pieces, inputs_ready=False) if args.pipeline else retr_o.rank(feats_dev, gt_dev, TOPK)
+            return last.result() if args.pipeline else last
+        run_o(3)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        ro = run_o(args.ab_steps)
+        a1.record()
+        barrier()
+        o_ms = a0.elapsed_time(a1) / args.ab_steps
+        om = ro.metrics.cpu().tolist()
+        other = {"what": "the same step with %s operands (gallery converted from the %s one), %d steps right after the timed legs on the same "
+                         "GPU: fp16 and bf16 share the nominal MMA rate, the power cap does not treat them alike; fp16 is the default "
+                         "because it moves ~7x fewer ranks against the fp32 reference (tests/test_gpu_trained.py)"
+                         % ("bf16" if odt == torch.bfloat16 else "fp16", args.precision, args.ab_steps),
+                 "dtype": "bf16" if odt == torch.bfloat16 else "fp16", "ms_per_step": o_ms, "value": Q / (o_ms * 1e-3), "unit": UNIT,
+                 "step_tflops": (Q * V * FLOP_PER_PAIR + Q * FLOP_PER_QUERY_FUSE) / (o_ms * 1e-3) / 1e12,
+                 "step_frac_of_peak": (Q * V * FLOP_PER_PAIR + Q * FLOP_PER_QUERY_FUSE) / (o_ms * 1e-3) / 1e12 / peaks()["tensor_tflops"],
+                 "recall": {"r1": om[0], "r5": om[1], "r10": om[2], "medr": om[3]}}
+        del retr_o, ro
+        torch.cuda.empty_cache()
+
     metrics = res.metrics.cpu().tolist()
     parity = parity_block(txt_net, index, feats_dev, gt_dev, res, args.parity_queries, world, args.precision) if args.parity_queries > 0 else None
 
@@ -584,6 +616,7 @@ def run_ours(args, rank, world, local_rank):
                                "%.1f s per rank): fractions %s" % (world, args.balance_seconds, [round(w, 4) for w in weights]),
                    "l2": "inputs exceed L2 (gallery shard %.1f GB)" % (n_local * D * 2 / 1e9),
                    "recall": {"r1": metrics[0], "r5": metrics[1], "r10": metrics[2], "medr": metrics[3]},
+                   "other_precision": other,
                    "pipeline": None if not args.pipeline else {
                        "what": "Retriever.submit: per piece of the batch fuse+all-gather+ground-truth scores | sweep | merge on three "
                                "streams (collectives of the side stages on their own communicators); stages of consecutive "
@@ -660,6 +693,9 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit operand type of the projections and the similarity sweep (same MMA rate; fp16 moves ~7x fewer "
                          "ranks against the fp32 reference, tests/test_gpu_trained.py)")
+    ap.add_argument("--ab-steps", type=int, default=5,
+                    help="timed steps of the same workload with the other 16-bit operand type, reported as config.other_precision "
+                         "(one GPU only; 0 = skip)")
     ap.add_argument("--parity-queries", type=int, default=256,
                     help="queries of the parity block: re-ranked with fp32-grade (bf16x3) fusion + sweep and compared (0 = skip)")
     ap.add_argument("--mode-b-steps", type=int, default=2, help="timed steps of the mode-B leg (0 = skip it)")
