@@ -91,3 +91,15 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.replace("no oracle", ""), "%s mentions the oracle" % f
+
+
+def test_product_path_never_touches_the_oracle_or_the_staged_reference():
+    """oracle/ (and the reference staged under baseline/_ref) is test / baseline infrastructure: nothing under laff_b200/
+    may import, open or execute it -- only tests/, __graft_entry__.smoke() and bench.py's CPU legs do."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|baseline[/\\]_ref|oracle[/\\]_ref|ref_loader|laff_oracle", re.M)
+    for path in glob.glob(os.path.join(root, "laff_b200", "**", "*.py"), recursive=True) + glob.glob(os.path.join(root, "laff_b200", "csrc", "*")):
+        assert not pat.search(open(path, errors="ignore").read()), path
